@@ -1,0 +1,378 @@
+// CCA sufficient statistics (one fused Gram pass, fp64 accumulation) and the 32x32 solve
+// (inverse square roots by symmetric Jacobi, SVD by one-sided Jacobi) in a single CTA.
+//
+// Replaces (reference, paths relative to its root):
+//   audio_sheet_retrieval/utils/cca.py:25-53      means + three covariances (+ r*I)
+//   audio_sheet_retrieval/utils/cca.py:199-211    inv(sqrtm(S)), T, svd(T), U = S11^-1/2 U', V = S22^-1/2 V'
+//   audio_sheet_retrieval/models/lasagne_extensions/layers/cca.py:117-175  batch statistics,
+//       eigh-based inverse square roots, eigh(TT'+rT I), eigh(T'T+rT I), sign fix   (mode 1)
+//
+// Multi-GPU: every rank accumulates its rows into the same 3136-value layout; one NCCL
+// all-reduce(sum) of that buffer precedes asr_cca_solve (done by the Python host).
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace asr {
+
+constexpr int CC_THREADS = 256;
+constexpr int CC_ROWS = 128;
+constexpr int CC_PART = 64 + 64 * 64;   // per-CTA partial: sum z (64) | Gram (64x64)
+constexpr int CC_MAX_CTAS = 296;
+
+// partial[(cta)][CC_PART].  z = [x - shift1, y - shift2]
+__global__ void __launch_bounds__(CC_THREADS)
+cca_gram_kernel(const float *__restrict__ h1, const float *__restrict__ h2, int64_t n, const float *__restrict__ shift1,
+                const float *__restrict__ shift2, double *__restrict__ partial) {
+    __shared__ __align__(16) float z[CC_ROWS][64];
+    const int tid = threadIdx.x;
+    const int ti = tid >> 4, tj = tid & 15;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    double colsum = 0.0;
+    const int64_t n_tiles = (n + CC_ROWS - 1) / CC_ROWS;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int64_t r0 = t * CC_ROWS;
+        __syncthreads();
+        // coalesced load: 128 rows x 32 floats per view
+        for (int e = tid; e < CC_ROWS * 32; e += CC_THREADS) {
+            int r = e >> 5, c = e & 31;
+            int64_t gr = r0 + r;
+            float s1 = shift1 ? shift1[c] : 0.f, s2 = shift2 ? shift2[c] : 0.f;
+            z[r][c] = gr < n ? h1[gr * 32 + c] - s1 : 0.f;
+            z[r][32 + c] = gr < n ? h2[gr * 32 + c] - s2 : 0.f;
+        }
+        __syncthreads();
+        const int rows = (int)min((int64_t)CC_ROWS, n - r0);
+        for (int r = 0; r < rows; ++r) {
+            float4 a4 = *reinterpret_cast<const float4 *>(&z[r][4 * ti]);
+            float4 b4 = *reinterpret_cast<const float4 *>(&z[r][4 * tj]);
+            double a[4] = {a4.x, a4.y, a4.z, a4.w};
+            double b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+        if (tid < 64)
+            for (int r = 0; r < rows; ++r) colsum += (double)z[r][tid];
+    }
+    double *p = partial + (size_t)blockIdx.x * CC_PART;
+    if (tid < 64) p[tid] = colsum;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) p[64 + (4 * ti + i) * 64 + 4 * tj + j] = acc[i][j];
+}
+
+// fixed-order reduction of the per-CTA partials, added to sums (ASR_CCA_NSUMS layout)
+__global__ void cca_reduce_kernel(const double *__restrict__ partial, int n_part, double *__restrict__ sums) {
+    int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= ASR_CCA_NSUMS) return;
+    int src;
+    if (o < 64) src = o;                                      // sum x | sum y
+    else {
+        int m = (o - 64) >> 10, e = (o - 64) & 1023, i = e >> 5, j = e & 31;
+        int gi = (m == 1) ? 32 + i : i;                       // xx: (i,j)  yy: (32+i,32+j)  xy: (i,32+j)
+        int gj = (m == 0) ? j : 32 + j;
+        src = 64 + gi * 64 + gj;
+    }
+    double s = 0.0;
+    for (int c = 0; c < n_part; ++c) s += partial[(size_t)c * CC_PART + src];
+    sums[o] += s;
+}
+
+// ---------------------------------------------------------------------------------
+// single-CTA solve, 512 threads = 16 warps = 16 disjoint Jacobi pairs per step
+// ---------------------------------------------------------------------------------
+constexpr int SV_THREADS = 512;
+typedef double Mat[32][33];     // padded rows
+
+__device__ __forceinline__ void rr_pair(int step, int i, int &p, int &q) {   // round-robin tournament, n = 32
+    if (i == 0) { p = 31; q = step % 31; }
+    else { p = (step + i) % 31; q = (step + 31 - i) % 31; }
+    if (p > q) { int t = p; p = q; q = t; }
+}
+
+// Symmetric eigen-decomposition A = V diag(w) V^T by cyclic two-sided Jacobi (A destroyed).
+__device__ void jacobi_eigh(Mat A, Mat V, double *w, double *cs /*[16][2]*/, int tid) {
+    const int pi = tid >> 5, r = tid & 31;
+    for (int e = tid; e < 1024; e += SV_THREADS) V[e >> 5][e & 31] = ((e >> 5) == (e & 31)) ? 1.0 : 0.0;
+    __syncthreads();
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        // convergence: off-diagonal mass relative to the diagonal
+        __shared__ double off_s, diag_s;
+        if (tid == 0) { off_s = 0.0; diag_s = 0.0; }
+        __syncthreads();
+        if (tid < 32) {
+            double off = 0.0;
+            for (int j = 0; j < 32; ++j) if (j != tid) off += A[tid][j] * A[tid][j];
+            double dg = A[tid][tid] * A[tid][tid];
+            for (int o = 16; o > 0; o >>= 1) {
+                off += __shfl_xor_sync(0xffffffffu, off, o);
+                dg += __shfl_xor_sync(0xffffffffu, dg, o);
+            }
+            if (tid == 0) { off_s = off; diag_s = dg; }
+        }
+        __syncthreads();
+        if (off_s <= 1e-30 * diag_s || off_s == 0.0) break;
+        for (int step = 0; step < 31; ++step) {
+            int p, q;
+            rr_pair(step, pi, p, q);
+            if (r == 0) {
+                double app = A[p][p], aqq = A[q][q], apq = A[p][q];
+                double c = 1.0, s = 0.0;
+                if (fabs(apq) > 1e-300 && fabs(apq) > 1e-18 * sqrt(fabs(app * aqq))) {
+                    double tau = (aqq - app) / (2.0 * apq);
+                    double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                    c = 1.0 / sqrt(1.0 + t * t);
+                    s = t * c;
+                }
+                cs[2 * pi] = c; cs[2 * pi + 1] = s;
+            }
+            __syncthreads();
+            const double c = cs[2 * pi], s = cs[2 * pi + 1];
+            {   // columns: A <- A J, V <- V J
+                double ap = A[r][p], aq = A[r][q];
+                A[r][p] = c * ap - s * aq; A[r][q] = s * ap + c * aq;
+                double vp = V[r][p], vq = V[r][q];
+                V[r][p] = c * vp - s * vq; V[r][q] = s * vp + c * vq;
+            }
+            __syncthreads();
+            {   // rows: A <- J^T A
+                double ap = A[p][r], aq = A[q][r];
+                A[p][r] = c * ap - s * aq; A[q][r] = s * ap + c * aq;
+            }
+            __syncthreads();
+        }
+    }
+    if (tid < 32) w[tid] = A[tid][tid];
+    __syncthreads();
+}
+
+// One-sided Jacobi SVD: G (in: T, out: U' * diag(sigma) columns), Vr accumulates right vectors.
+__device__ void jacobi_svd(Mat G, Mat Vr, int tid) {
+    const int pi = tid >> 5, r = tid & 31;
+    for (int e = tid; e < 1024; e += SV_THREADS) Vr[e >> 5][e & 31] = ((e >> 5) == (e & 31)) ? 1.0 : 0.0;
+    __syncthreads();
+    __shared__ int rotated;
+    for (int sweep = 0; sweep < 40; ++sweep) {
+        if (tid == 0) rotated = 0;
+        __syncthreads();
+        for (int step = 0; step < 31; ++step) {
+            int p, q;
+            rr_pair(step, pi, p, q);
+            double gp = G[r][p], gq = G[r][q];
+            double al = gp * gp, be = gq * gq, ga = gp * gq;
+            for (int o = 16; o > 0; o >>= 1) {
+                al += __shfl_xor_sync(0xffffffffu, al, o);
+                be += __shfl_xor_sync(0xffffffffu, be, o);
+                ga += __shfl_xor_sync(0xffffffffu, ga, o);
+            }
+            if (fabs(ga) > 1e-15 * sqrt(al * be) && fabs(ga) > 1e-300) {
+                double zeta = (be - al) / (2.0 * ga);
+                double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                G[r][p] = c * gp - s * gq; G[r][q] = s * gp + c * gq;
+                double vp = Vr[r][p], vq = Vr[r][q];
+                Vr[r][p] = c * vp - s * vq; Vr[r][q] = s * vp + c * vq;
+                if (r == 0) rotated = 1;
+            }
+            __syncthreads();
+        }
+        if (!rotated) break;     // read after the barrier above; uniform
+        __syncthreads();
+    }
+}
+
+// C = A * B (32x32), optional transposes
+__device__ void mm32(Mat C, Mat A, bool ta, Mat B, bool tb, int tid) {
+    for (int e = tid; e < 1024; e += SV_THREADS) {
+        int i = e >> 5, j = e & 31;
+        double s = 0.0;
+        for (int k = 0; k < 32; ++k) s += (ta ? A[k][i] : A[i][k]) * (tb ? B[j][k] : B[k][j]);
+        C[i][j] = s;
+    }
+    __syncthreads();
+}
+
+// Si = V diag(w^-1/2) V^T
+__device__ void inv_sqrt_from_eig(Mat Si, Mat V, const double *w, int tid) {
+    for (int e = tid; e < 1024; e += SV_THREADS) {
+        int i = e >> 5, j = e & 31;
+        double s = 0.0;
+        for (int k = 0; k < 32; ++k) s += V[i][k] * V[j][k] / sqrt(w[k]);
+        Si[i][j] = s;
+    }
+    __syncthreads();
+}
+
+struct SolveSmem {
+    Mat S11, S22, S12, W0, W1, S11i, S22i, T, G, Vr;
+    double w[32], w2[32], mx[32], my[32], cs[32];
+    int perm[32], perm2[32];
+};
+
+__global__ void __launch_bounds__(SV_THREADS, 1)
+cca_solve_kernel(const double *__restrict__ sums, double n_total, const float *__restrict__ shift1,
+                 const float *__restrict__ shift2, double r1, double r2, double rT, int mode, double *__restrict__ m1,
+                 double *__restrict__ m2, double *__restrict__ U, double *__restrict__ V, double *__restrict__ sigma) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    SolveSmem &sm = *reinterpret_cast<SolveSmem *>(smem_raw);
+    const int tid = threadIdx.x;
+    const double n = n_total;
+    if (tid < 32) {
+        sm.mx[tid] = sums[tid] / n;
+        sm.my[tid] = sums[32 + tid] / n;
+        m1[tid] = sm.mx[tid] + (shift1 ? (double)shift1[tid] : 0.0);
+        m2[tid] = sm.my[tid] + (shift2 ? (double)shift2[tid] : 0.0);
+    }
+    __syncthreads();
+    for (int e = tid; e < 1024; e += SV_THREADS) {
+        int i = e >> 5, j = e & 31;
+        double d = (i == j) ? 1.0 : 0.0;
+        sm.S11[i][j] = (sums[64 + e] - n * sm.mx[i] * sm.mx[j]) / (n - 1.0) + r1 * d;
+        sm.S22[i][j] = (sums[64 + 1024 + e] - n * sm.my[i] * sm.my[j]) / (n - 1.0) + r2 * d;
+        sm.S12[i][j] = (sums[64 + 2048 + e] - n * sm.mx[i] * sm.my[j]) / (n - 1.0);
+    }
+    __syncthreads();
+    // S11^-1/2, S22^-1/2
+    for (int e = tid; e < 1024; e += SV_THREADS) sm.W0[e >> 5][e & 31] = sm.S11[e >> 5][e & 31];
+    __syncthreads();
+    jacobi_eigh(sm.W0, sm.W1, sm.w, sm.cs, tid);
+    inv_sqrt_from_eig(sm.S11i, sm.W1, sm.w, tid);
+    for (int e = tid; e < 1024; e += SV_THREADS) sm.W0[e >> 5][e & 31] = sm.S22[e >> 5][e & 31];
+    __syncthreads();
+    jacobi_eigh(sm.W0, sm.W1, sm.w, sm.cs, tid);
+    inv_sqrt_from_eig(sm.S22i, sm.W1, sm.w, tid);
+    // T = S11i * S12 * S22i
+    mm32(sm.W0, sm.S11i, false, sm.S12, false, tid);
+    mm32(sm.T, sm.W0, false, sm.S22i, false, tid);
+
+    if (mode == 0) {
+        // ---- CCA.fit('svd'): T = U' diag(sigma) V'^T, sigma descending ----
+        for (int e = tid; e < 1024; e += SV_THREADS) sm.G[e >> 5][e & 31] = sm.T[e >> 5][e & 31];
+        __syncthreads();
+        jacobi_svd(sm.G, sm.Vr, tid);
+        if (tid < 32) {
+            double s = 0.0;
+            for (int rr = 0; rr < 32; ++rr) s += sm.G[rr][tid] * sm.G[rr][tid];
+            sm.w[tid] = sqrt(s);
+        }
+        __syncthreads();
+        if (tid < 32) {   // rank by (sigma desc, index asc)
+            int rk = 0;
+            for (int j = 0; j < 32; ++j) rk += (sm.w[j] > sm.w[tid] || (sm.w[j] == sm.w[tid] && j < tid)) ? 1 : 0;
+            sm.perm[rk] = tid;
+        }
+        __syncthreads();
+        // W0 = U' (normalised, permuted), W1 = V' (permuted)
+        for (int e = tid; e < 1024; e += SV_THREADS) {
+            int i = e >> 5, j = e & 31, src = sm.perm[j];
+            double sg = sm.w[src];
+            sm.W0[i][j] = sg > 1e-300 ? sm.G[i][src] / sg : 0.0;
+            sm.W1[i][j] = sm.Vr[i][src];
+        }
+        __syncthreads();
+        if (tid < 32) sigma[tid] = sm.w[sm.perm[tid]];
+        mm32(sm.G, sm.S11i, false, sm.W0, false, tid);     // U = S11i U'
+        mm32(sm.Vr, sm.S22i, false, sm.W1, false, tid);    // V = S22i V'
+        for (int e = tid; e < 1024; e += SV_THREADS) { U[e] = sm.G[e >> 5][e & 31]; V[e] = sm.Vr[e >> 5][e & 31]; }
+    } else {
+        // ---- CCALayer train forward: eigh(TT'+rT I) -> E, eigh(T'T+rT I) -> F, ascending ----
+        mm32(sm.W0, sm.T, false, sm.T, true, tid);          // T T^T
+        for (int e = tid; e < 1024; e += SV_THREADS) if ((e >> 5) == (e & 31)) sm.W0[e >> 5][e & 31] += rT;
+        __syncthreads();
+        jacobi_eigh(sm.W0, sm.G, sm.w, sm.cs, tid);         // G = E (unsorted)
+        mm32(sm.W0, sm.T, true, sm.T, false, tid);          // T^T T
+        for (int e = tid; e < 1024; e += SV_THREADS) if ((e >> 5) == (e & 31)) sm.W0[e >> 5][e & 31] += rT;
+        __syncthreads();
+        jacobi_eigh(sm.W0, sm.Vr, sm.w2, sm.cs, tid);       // Vr = F (unsorted)
+        if (tid < 32) {   // ascending, ties by index
+            int rk = 0, rk2 = 0;
+            for (int j = 0; j < 32; ++j) {
+                rk += (sm.w[j] < sm.w[tid] || (sm.w[j] == sm.w[tid] && j < tid)) ? 1 : 0;
+                rk2 += (sm.w2[j] < sm.w2[tid] || (sm.w2[j] == sm.w2[tid] && j < tid)) ? 1 : 0;
+            }
+            sm.perm[rk] = tid;
+            sm.perm2[rk2] = tid;
+        }
+        __syncthreads();
+        for (int e = tid; e < 1024; e += SV_THREADS) {
+            int i = e >> 5, j = e & 31;
+            sm.W0[i][j] = sm.G[i][sm.perm[j]];
+            sm.W1[i][j] = sm.Vr[i][sm.perm2[j]];
+        }
+        __syncthreads();
+        if (tid < 32) {
+            double e1 = sm.w[sm.perm[tid]];
+            e1 = fmin(fmax(e1, 1e-7), 1.0);
+            sigma[tid] = sqrt(e1);                           // corr (cca.py:163-166)
+        }
+        mm32(sm.G, sm.S11i, false, sm.W0, false, tid);      // U = S11si E
+        mm32(sm.Vr, sm.S22i, false, sm.W1, false, tid);     // V = S22si F
+        // sign fix: s = sgn(diag(U^T S12 V)); U *= s
+        mm32(sm.W0, sm.S12, false, sm.Vr, false, tid);      // S12 V
+        if (tid < 32) {
+            double d = 0.0;
+            for (int rr = 0; rr < 32; ++rr) d += sm.G[rr][tid] * sm.W0[rr][tid];
+            sm.cs[tid] = d > 0.0 ? 1.0 : (d < 0.0 ? -1.0 : 0.0);
+        }
+        __syncthreads();
+        for (int e = tid; e < 1024; e += SV_THREADS) {
+            U[e] = sm.G[e >> 5][e & 31] * sm.cs[e & 31];
+            V[e] = sm.Vr[e >> 5][e & 31];
+        }
+    }
+}
+
+static double *g_partial = nullptr;
+
+}  // namespace asr
+
+using namespace asr;
+
+extern "C" {
+
+int asr_cca_accumulate(const float *h1_dev, const float *h2_dev, int64_t n, const float *shift1_dev,
+                       const float *shift2_dev, double *sums_dev, void *stream) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    ASR_CHECK_ARG(h1_dev && h2_dev && sums_dev, "NULL buffer");
+    ASR_CHECK_ARG(n >= 0, "n < 0");
+    if (n == 0) return ASR_OK;
+    if (!g_partial) ASR_CUDA(cudaMalloc(&g_partial, sizeof(double) * CC_PART * CC_MAX_CTAS));
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t n_tiles = (n + CC_ROWS - 1) / CC_ROWS;
+    int grid = (int)std::min<int64_t>(n_tiles, std::min(CC_MAX_CTAS, 2 * sm_count()));
+    cca_gram_kernel<<<grid, CC_THREADS, 0, st>>>(h1_dev, h2_dev, n, shift1_dev, shift2_dev, g_partial);
+    ASR_LAUNCH_CHECK();
+    cca_reduce_kernel<<<(ASR_CCA_NSUMS + 127) / 128, 128, 0, st>>>(g_partial, grid, sums_dev);
+    ASR_LAUNCH_CHECK();
+    return ASR_OK;
+}
+
+int asr_cca_solve(const double *sums_dev, int64_t n_total, const float *shift1_dev, const float *shift2_dev, double r1,
+                  double r2, double rT, int mode, double *m1_dev, double *m2_dev, double *U_dev, double *V_dev,
+                  double *sigma_dev, void *stream) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    ASR_CHECK_ARG(sums_dev && m1_dev && m2_dev && U_dev && V_dev && sigma_dev, "NULL buffer");
+    ASR_CHECK_ARG(n_total >= 2, "need at least 2 samples");
+    ASR_CHECK_ARG(mode == 0 || mode == 1, "mode must be 0 (svd) or 1 (layer)");
+    static bool attr_done = false;
+    if (!attr_done) {
+        ASR_CUDA(cudaFuncSetAttribute(cca_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(SolveSmem)));
+        attr_done = true;
+    }
+    cca_solve_kernel<<<1, SV_THREADS, sizeof(SolveSmem), (cudaStream_t)stream>>>(
+        sums_dev, (double)n_total, shift1_dev, shift2_dev, r1, r2, rT, mode, m1_dev, m2_dev, U_dev, V_dev, sigma_dev);
+    ASR_LAUNCH_CHECK();
+    return ASR_OK;
+}
+
+}  // extern "C"

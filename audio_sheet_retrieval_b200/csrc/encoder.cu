@@ -1,0 +1,851 @@
+// The two encoder branches: prepare + 8 x (conv3x3 + BN + ELU [+ 2x2 max-pool]) + 1x1 conv + BN +
+// global mean + CCA projection + length norm.
+//
+// Replaces the compiled Theano graph of (reference, paths relative to its root)
+//   audio_sheet_retrieval/models/mutopia_ccal_cont_rsz.py:54-147,170-190
+//   audio_sheet_retrieval/models/mutopia_ccal_cont.py:54-147,170-190
+//   audio_sheet_retrieval/models/lasagne_extensions/layers/cca.py:184-203 (deterministic) and :39-40
+//   audio_sheet_retrieval/retrieval_wrapper.py:33-38,47-77 ; audio_sheet_retrieval/refine_cca.py:86-89
+//
+// Product path (ASR_PATH_TCGEN05)
+//   layer 0 (Cin = 1, K = 9: not a tensor-core problem) runs on CUDA cores fused with `prepare`
+//   and writes bf16 activations in the "P8" layout below; layers 1..7 are implicit GEMMs on
+//   tcgen05 with fp32 accumulators in TMEM; BatchNorm is folded into the bf16 weights + an fp32
+//   bias, ELU and the 2x2 max-pool run in the epilogue; the head stays in fp32.
+//
+// P8 activation layout (bf16):  [sample][channel chunk of 8][(H+2) x (W+2) padded positions][8]
+//   - one padded position of one chunk = 16 bytes = one row of a UMMA "core matrix"; a run of
+//     positions is therefore directly a K-major, non-swizzled A operand (SBO = 128 B between
+//     8-row groups, LBO = plane stride between the two 8-channel halves of a K = 16 step);
+//   - a band of image rows is contiguous per plane, so it is fetched with ONE TMA bulk copy per
+//     plane, and the 9 filter taps are 9 *shifted descriptors* over the same shared-memory tile
+//     (shift = (dy*(W+2) + dx) * 16 bytes): the im2col matrix is never materialised;
+//   - the GEMM M dimension enumerates padded positions of the band in raster order, so the two
+//     border columns per row produce garbage rows that the epilogue drops (2/(W+2) waste);
+//   - borders are zero (written once at create) = the convolution's zero padding.
+#include <math_constants.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace asr {
+
+typedef __nv_bfloat16 bf16;
+
+struct LayerGeom {
+    int cin, cout, cinp, coutp;
+    int H, W;        // conv spatial size (input = output, pad 1)
+    int pool;        // 2x2 max-pool after this layer
+    int Ho, Wo;      // spatial size of the stored output
+};
+
+// launch plan of one tcgen05 conv layer
+struct ConvPlan {
+    int TH, bands, MT, n_stages, slot_cols, n_slots, tmem_cols;
+    int sps;            // smem plane stride (bytes)
+    int stage_bytes;    // 16 (front guard) + KC*sps + tail slack
+    int wbytes, staging_bytes, smem_bytes;
+    int off_bias, off_stage, off_staging, off_bar;
+};
+
+struct ConvParams {
+    const bf16 *in;
+    bf16 *out;
+    const bf16 *wblob;   // [9][KC][NP][8] bf16 followed by NP fp32 biases
+    int n_samples;
+    int H, W, Wp, Hp, KC, NP, NCH, TH, bands, MT, pool;
+    int Ho, Wo, Wpo;
+    long long in_plane, in_sample, out_plane, out_sample;   // bytes
+    int sps, stage_bytes, n_stages, slot_cols, n_slots, tmem_cols, wbytes;
+    int off_bias, off_stage, off_staging, off_bar;
+};
+
+constexpr int CONV_THREADS = 320;        // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int EPI_THREADS = 256;
+constexpr int TAIL_SLACK = 2080;
+constexpr int MAX_SLOTS = 8;
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+// --------------------------------------------------------------------------------------
+// tcgen05 implicit-GEMM convolution (layers 1..7)
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(const ConvParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t *w_sm = smem;
+    float *bias_sm = reinterpret_cast<float *>(smem + p.off_bias);
+    uint8_t *stage_sm = smem + p.off_stage;
+    uint8_t *staging_sm = smem + p.off_staging;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + p.off_bar);
+    uint64_t *w_full = bars;                       // 1
+    uint64_t *in_full = bars + 1;                  // [2]
+    uint64_t *in_empty = bars + 3;                 // [2]
+    uint64_t *acc_full = bars + 5;                 // [MAX_SLOTS]
+    uint64_t *acc_empty = bars + 5 + MAX_SLOTS;    // [MAX_SLOTS]
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 5 + 2 * MAX_SLOTS);
+
+    if (tid == 0) {
+        mbar_init(w_full, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&in_full[s], 1); mbar_init(&in_empty[s], 1); }
+        for (int s = 0; s < MAX_SLOTS; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr, (uint32_t)p.tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int n_items = p.n_samples * p.bands;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            mbar_expect_tx(w_full, (uint32_t)(p.wbytes + p.NP * 4));
+            tma_bulk_g2s(w_sm, p.wblob, (uint32_t)p.wbytes, w_full);
+            tma_bulk_g2s(bias_sm, reinterpret_cast<const uint8_t *>(p.wblob) + p.wbytes, (uint32_t)(p.NP * 4), w_full);
+            int it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int n = item / p.bands, y0 = (item % p.bands) * p.TH;
+                const int s = it % p.n_stages;
+                const uint32_t ph = (uint32_t)((it / p.n_stages) & 1);
+                mbar_wait(&in_empty[s], ph ^ 1u);
+                const int rows_in = min(p.TH + 2, p.Hp - y0);
+                const uint32_t bytes = (uint32_t)(rows_in * p.Wp * 16);
+                mbar_expect_tx(&in_full[s], bytes * (uint32_t)p.KC);
+                const uint8_t *src = reinterpret_cast<const uint8_t *>(p.in) + (long long)n * p.in_sample +
+                                     (long long)y0 * p.Wp * 16;
+                uint8_t *dst = stage_sm + (size_t)s * p.stage_bytes + 16;
+                for (int kc = 0; kc < p.KC; ++kc)
+                    tma_bulk_g2s(dst + (size_t)kc * p.sps, src + (long long)kc * p.in_plane, bytes, &in_full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(p.NP);
+            const uint32_t w_addr = smem_u32(w_sm);
+            const uint32_t b_lbo = (uint32_t)(p.NP * 16);
+            mbar_wait(w_full, 0);
+            int it = 0;
+            uint32_t tc = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int s = it % p.n_stages;
+                const uint32_t ph = (uint32_t)((it / p.n_stages) & 1);
+                mbar_wait(&in_full[s], ph);
+                tc_fence_after();
+                const uint32_t tile_addr = smem_u32(stage_sm + (size_t)s * p.stage_bytes + 16);
+                for (int mt = 0; mt < p.MT; ++mt, ++tc) {
+                    const uint32_t slot = tc % (uint32_t)p.n_slots;
+                    const uint32_t sph = (tc / (uint32_t)p.n_slots) & 1u;
+                    mbar_wait(&acc_empty[slot], sph ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + slot * (uint32_t)p.slot_cols;
+                    uint32_t acc = 0;
+#pragma unroll 1
+                    for (int t = 0; t < 9; ++t) {
+                        const int dy = t / 3 - 1, dx = t % 3 - 1;
+                        const uint32_t a0 = tile_addr + (uint32_t)((mt * 128 + (1 + dy) * p.Wp + dx) * 16);
+                        const uint32_t b0 = w_addr + (uint32_t)(t * p.KC * p.NP * 16);
+                        for (int kp = 0; kp < p.KC / 2; ++kp) {
+                            const uint64_t ad = umma_desc(a0 + (uint32_t)(2 * kp * p.sps), (uint32_t)p.sps, 128u);
+                            const uint64_t bd = umma_desc(b0 + (uint32_t)(2 * kp) * b_lbo, b_lbo, 128u);
+                            tc_mma_bf16(d_tmem, ad, bd, idesc, acc);
+                            acc = 1;
+                        }
+                    }
+                    tc_commit(&acc_full[slot]);
+                }
+                tc_commit(&in_empty[s]);
+            }
+        }
+    } else {
+        // ================= epilogue: TMEM -> bias + ELU -> bf16 -> (pool) -> global =================
+        const int ew = warp - 2;                 // 0..7
+        const int grp = ew >> 2;                 // tiles alternate between the two groups
+        const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+        const int etid = tid - 64;               // 0..255
+        mbar_wait(w_full, 0);                    // bias visible
+        uint32_t tc = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int n = item / p.bands, y0 = (item % p.bands) * p.TH;
+            uint8_t *out_n = reinterpret_cast<uint8_t *>(p.out) + (long long)n * p.out_sample;
+            for (int mt = 0; mt < p.MT; ++mt, ++tc) {
+                if ((int)(tc & 1u) != grp) continue;
+                const uint32_t slot = tc % (uint32_t)p.n_slots;
+                const uint32_t sph = (tc / (uint32_t)p.n_slots) & 1u;
+                mbar_wait(&acc_full[slot], sph);
+                tc_fence_after();
+                const int o = mt * 128 + quarter * 32 + lane;       // padded raster position in the band
+                const int r = o / p.Wp, c = o - r * p.Wp;
+                const int y = y0 + r;
+                const bool in_band = r < p.TH;
+                const bool valid = in_band && c >= 1 && c <= p.W && y < p.H;
+                const uint32_t taddr = tmem_base + slot * (uint32_t)p.slot_cols + ((uint32_t)(quarter * 32) << 16);
+                for (int ng = 0; ng < p.NP / 16; ++ng) {
+                    float v[16];
+                    tmem_ld16(taddr + (uint32_t)(ng * 16), v);
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float a = elu_f(v[2 * j] + bias_sm[ng * 16 + 2 * j]);
+                        float b = elu_f(v[2 * j + 1] + bias_sm[ng * 16 + 2 * j + 1]);
+                        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+                        pk[j] = *reinterpret_cast<uint32_t *>(&h);
+                    }
+                    if (p.pool) {
+                        if (in_band) {
+                            uint4 *d0 = reinterpret_cast<uint4 *>(staging_sm + ((size_t)(2 * ng) * p.TH * p.Wp + o) * 16);
+                            uint4 *d1 = reinterpret_cast<uint4 *>(staging_sm + ((size_t)(2 * ng + 1) * p.TH * p.Wp + o) * 16);
+                            *d0 = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            *d1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                        }
+                    } else if (valid) {
+                        const long long pos = ((long long)(y + 1) * p.Wp + c) * 16;
+                        *reinterpret_cast<uint4 *>(out_n + (long long)(2 * ng) * p.out_plane + pos) =
+                            make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4 *>(out_n + (long long)(2 * ng + 1) * p.out_plane + pos) =
+                            make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[slot]);
+            }
+            if (p.pool) {
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");   // band staged
+                const int prow = p.TH / 2;
+                const int total = p.NCH * prow * p.Wo;
+                for (int e = etid; e < total; e += EPI_THREADS) {
+                    const int ch = e / (prow * p.Wo);
+                    const int rem = e - ch * prow * p.Wo;
+                    const int pr = rem / p.Wo, pc = rem - pr * p.Wo;
+                    const int yo = y0 / 2 + pr;
+                    if (yo < p.Ho) {
+                        const uint8_t *b = staging_sm + ((size_t)ch * p.TH * p.Wp + (size_t)(2 * pr) * p.Wp + 1 + 2 * pc) * 16;
+                        uint4 q00 = *reinterpret_cast<const uint4 *>(b);
+                        uint4 q01 = *reinterpret_cast<const uint4 *>(b + 16);
+                        uint4 q10 = *reinterpret_cast<const uint4 *>(b + (size_t)p.Wp * 16);
+                        uint4 q11 = *reinterpret_cast<const uint4 *>(b + (size_t)p.Wp * 16 + 16);
+                        uint4 o4;
+                        const uint32_t *a0 = &q00.x, *a1 = &q01.x, *a2 = &q10.x, *a3 = &q11.x;
+                        uint32_t *oo = &o4.x;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            __nv_bfloat162 m0 = __hmax2(*reinterpret_cast<const __nv_bfloat162 *>(&a0[j]),
+                                                        *reinterpret_cast<const __nv_bfloat162 *>(&a1[j]));
+                            __nv_bfloat162 m1 = __hmax2(*reinterpret_cast<const __nv_bfloat162 *>(&a2[j]),
+                                                        *reinterpret_cast<const __nv_bfloat162 *>(&a3[j]));
+                            __nv_bfloat162 m = __hmax2(m0, m1);
+                            oo[j] = *reinterpret_cast<uint32_t *>(&m);
+                        }
+                        *reinterpret_cast<uint4 *>(out_n + (long long)ch * p.out_plane +
+                                                   ((long long)(yo + 1) * p.Wpo + pc + 1) * 16) = o4;
+                    }
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");   // staging free again
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+// --------------------------------------------------------------------------------------
+// layer 0: prepare + conv3x3 (Cin = 1) + BN + ELU on CUDA cores -> P8 bf16
+// --------------------------------------------------------------------------------------
+struct L0Params {
+    const void *x;          // (n,1,Hin,Win) f32 or u8
+    int x_u8, prepare;      // ASR_PREP_*
+    int Hin, Win, H, W, Wp, Hp;
+    int C, NCH;             // real channels, output chunks
+    const float *w;         // [C][9] folded (scale included), then [C] bias
+    bf16 *out;
+    long long out_plane, out_sample;
+    int n;
+};
+
+__device__ __forceinline__ float l0_fetch(const L0Params &p, const uint8_t *xu, const float *xf, int y, int x) {
+    if (y < 0 || y >= p.H || x < 0 || x >= p.W) return 0.f;
+    if (p.prepare == ASR_PREP_SCALE_HALF) {
+        int yy = 2 * y, xx = 2 * x;
+        float a, b, c, d;
+        if (p.x_u8) {
+            a = xu[yy * p.Win + xx]; b = xu[yy * p.Win + xx + 1];
+            c = xu[(yy + 1) * p.Win + xx]; d = xu[(yy + 1) * p.Win + xx + 1];
+        } else {
+            a = xf[yy * p.Win + xx]; b = xf[yy * p.Win + xx + 1];
+            c = xf[(yy + 1) * p.Win + xx]; d = xf[(yy + 1) * p.Win + xx + 1];
+        }
+        const float s = 1.0f / 255.0f;
+        return ((a * s + b * s) + (c * s + d * s)) * 0.25f;
+    }
+    float v = p.x_u8 ? (float)xu[y * p.Win + x] : xf[y * p.Win + x];
+    return p.prepare == ASR_PREP_SCALE ? v / 255.0f : v;
+}
+
+constexpr int L0_MAXC = 32;
+
+__global__ void __launch_bounds__(256) l0_conv_kernel(const L0Params p) {
+    __shared__ float w_sm[L0_MAXC * 10];
+    for (int i = threadIdx.x; i < p.C * 10; i += blockDim.x) w_sm[i] = p.w[i];
+    __syncthreads();
+    const int n = blockIdx.y;
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= p.H * p.W) return;
+    const int y = pix / p.W, x = pix - y * p.W;
+    const size_t in_off = (size_t)n * p.Hin * p.Win;
+    const uint8_t *xu = reinterpret_cast<const uint8_t *>(p.x) + in_off;
+    const float *xf = reinterpret_cast<const float *>(p.x) + in_off;
+    float v[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) v[t] = l0_fetch(p, xu, xf, y + t / 3 - 1, x + t % 3 - 1);
+    uint8_t *out_n = reinterpret_cast<uint8_t *>(p.out) + (long long)n * p.out_sample +
+                     ((long long)(y + 1) * p.Wp + x + 1) * 16;
+    for (int ch = 0; ch < p.NCH; ++ch) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float r[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = ch * 8 + 2 * j + h;
+                float acc = 0.f;
+                if (c < p.C) {
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) acc = fmaf(v[t], w_sm[c * 9 + t], acc);
+                    acc = elu_f(acc + w_sm[p.C * 9 + c]);
+                }
+                r[h] = acc;
+            }
+            __nv_bfloat162 hh = __floats2bfloat162_rn(r[0], r[1]);
+            pk[j] = *reinterpret_cast<uint32_t *>(&hh);
+        }
+        *reinterpret_cast<uint4 *>(out_n + (long long)ch * p.out_plane) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+}
+
+// --------------------------------------------------------------------------------------
+// head: spatial mean -> 1x1 conv + BN (folded) -> latent -> (latent - mean) . P -> unit norm
+// --------------------------------------------------------------------------------------
+struct HeadParams {
+    const void *in;            // P8 bf16 (tc path) or NCHW fp32 (fp32 path)
+    int is_p8;
+    int C, H, W, Wp;           // channels, interior size
+    long long plane, sample;   // bytes (P8) ; for NCHW: plane = H*W*4, sample = C*plane
+    const float *A;            // [32][C] folded 1x1 weights, then [32] bias
+    const float *cca_mean;     // [32]
+    const float *cca_proj;     // [32][32] (in, out)
+    float *codes, *latents;    // may be NULL
+};
+
+__global__ void __launch_bounds__(128) head_kernel(const HeadParams p) {
+    __shared__ float m[128];
+    __shared__ float lat[32];
+    const int n = blockIdx.x, tid = threadIdx.x;
+    const float inv = 1.0f / (float)(p.H * p.W);
+    for (int c = tid; c < p.C; c += blockDim.x) {
+        float s = 0.f;
+        if (p.is_p8) {
+            const uint8_t *base = reinterpret_cast<const uint8_t *>(p.in) + (long long)n * p.sample +
+                                  (long long)(c >> 3) * p.plane + (c & 7) * 2;
+            for (int y = 0; y < p.H; ++y)
+                for (int x = 0; x < p.W; ++x)
+                    s += __bfloat162float(*reinterpret_cast<const bf16 *>(base + ((long long)(y + 1) * p.Wp + x + 1) * 16));
+        } else {
+            const float *base = reinterpret_cast<const float *>(reinterpret_cast<const uint8_t *>(p.in) +
+                                                                (long long)n * p.sample + (long long)c * p.plane);
+            for (int i = 0; i < p.H * p.W; ++i) s += base[i];
+        }
+        m[c] = s * inv;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        float s = 0.f;
+        for (int c = 0; c < p.C; ++c) s = fmaf(p.A[tid * p.C + c], m[c], s);
+        s += p.A[32 * p.C + tid];
+        lat[tid] = s;
+        if (p.latents) p.latents[(size_t)n * 32 + tid] = s;
+    }
+    __syncthreads();
+    if (tid < 32 && p.codes) {
+        float s = 0.f;
+        for (int j = 0; j < 32; ++j) s = fmaf(lat[j] - p.cca_mean[j], p.cca_proj[j * 32 + tid], s);
+        float ss = s * s;
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        p.codes[(size_t)n * 32 + tid] = s / sqrtf(ss);
+    }
+}
+
+// --------------------------------------------------------------------------------------
+// fp32 CUDA-core path (on-device debug reference; NCHW fp32, unfolded BN exactly as the oracle)
+// --------------------------------------------------------------------------------------
+__global__ void ref_prepare_kernel(const void *x, int x_u8, int prepare, int Hin, int Win, int H, int W, int n, float *out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n * H * W) return;
+    const int s = (int)(i / ((size_t)H * W));
+    const int pix = (int)(i - (size_t)s * H * W);
+    L0Params p;
+    p.x_u8 = x_u8; p.prepare = prepare; p.Hin = Hin; p.Win = Win; p.H = H; p.W = W;
+    const size_t in_off = (size_t)s * Hin * Win;
+    out[i] = l0_fetch(p, reinterpret_cast<const uint8_t *>(x) + in_off, reinterpret_cast<const float *>(x) + in_off,
+                      pix / W, pix % W);
+}
+
+// thread per output element; w (cout,cin,3,3) already flipped if requested
+__global__ void ref_conv3x3_kernel(const float *__restrict__ in, const float *__restrict__ w, const float *__restrict__ bn,
+                                   int n, int cin, int cout, int H, int W, int apply_elu, float *__restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n * cout * H * W) return;
+    const int x = (int)(i % W), y = (int)((i / W) % H), co = (int)((i / ((size_t)W * H)) % cout);
+    const int s = (int)(i / ((size_t)W * H * cout));
+    float acc = 0.f;
+    for (int ci = 0; ci < cin; ++ci) {
+        const float *ip = in + ((size_t)s * cin + ci) * H * W;
+        const float *wp = w + ((size_t)co * cin + ci) * 9;
+        for (int t = 0; t < 9; ++t) {
+            int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) acc = fmaf(ip[yy * W + xx], wp[t], acc);
+        }
+    }
+    // bn: [beta | gamma | mean | inv_std] each cout
+    float r = (acc - bn[2 * cout + co]) * (bn[cout + co] * bn[3 * cout + co]) + bn[co];
+    if (apply_elu) r = r > 0.f ? r : expm1f(r);
+    out[i] = r;
+}
+
+__global__ void ref_pool_kernel(const float *__restrict__ in, int nc, int H, int W, float *__restrict__ out) {
+    const int Ho = H / 2, Wo = W / 2;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nc * Ho * Wo) return;
+    const int x = (int)(i % Wo), y = (int)((i / Wo) % Ho);
+    const size_t c = i / ((size_t)Wo * Ho);
+    const float *ip = in + c * H * W + (size_t)(2 * y) * W + 2 * x;
+    out[i] = fmaxf(fmaxf(ip[0], ip[1]), fmaxf(ip[W], ip[W + 1]));
+}
+
+}  // namespace asr
+
+using namespace asr;
+
+// --------------------------------------------------------------------------------------
+// handle
+// --------------------------------------------------------------------------------------
+struct asr_encoder {
+    asr_encoder_desc d;
+    int max_batch;
+    int H0, W0;                     // prepared input size
+    LayerGeom g[8];
+    int head_c, head_h, head_w;
+    double flops;
+    // tcgen05 path
+    float *l0_w = nullptr;          // [C0*9 + C0]
+    bf16 *wblob[8] = {nullptr};     // layers 1..7
+    ConvPlan plan[8];
+    bf16 *act[8] = {nullptr};       // P8 activations (output of layer l)
+    long long act_plane[8], act_sample[8];
+    // head (shared by both paths)
+    float *head_A = nullptr;        // [32*C + 32]
+    float *cca_mean = nullptr, *cca_proj = nullptr;
+    // fp32 path
+    float *ref_w[8] = {nullptr}, *ref_bn[8] = {nullptr};
+    float *ref_in = nullptr, *ref_act[8] = {nullptr}, *ref_tmp = nullptr;
+    int last_path = -1;
+    // host-buffer entry
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    void *dev_in[2] = {nullptr, nullptr};
+    void *pin_in[2] = {nullptr, nullptr};
+    float *dev_codes = nullptr, *dev_lat = nullptr;
+    int64_t out_cap = 0;
+};
+
+static bool plan_conv(const LayerGeom &g, ConvPlan &pl) {
+    const int Wp = g.W + 2, KC = g.cinp / 8, NP = g.coutp, NCH = NP / 8;
+    pl.wbytes = 9 * KC * NP * 16;
+    pl.slot_cols = NP <= 16 ? 16 : (NP <= 32 ? 32 : (NP <= 64 ? 64 : 128));
+    pl.n_slots = std::min(MAX_SLOTS, 512 / pl.slot_cols);
+    int cols = pl.n_slots * pl.slot_cols;
+    pl.tmem_cols = cols <= 32 ? 32 : (cols <= 64 ? 64 : (cols <= 128 ? 128 : (cols <= 256 ? 256 : 512)));
+    const int th_max = g.pool ? (g.H & ~1) : g.H;
+    const int step = g.pool ? 2 : 1;
+    for (int ns = 2; ns >= 1; --ns) {
+        int best = 0;
+        for (int th = step; th <= std::min(th_max, 16); th += step) {
+            long long sps = (long long)(th + 2) * Wp * 16;
+            long long stage = 16 + KC * sps + TAIL_SLACK;
+            long long staging = g.pool ? (long long)NCH * th * Wp * 16 : 0;
+            long long tot = pl.wbytes + NP * 4 + 128 + ns * stage + 128 + staging + 256 + 256;
+            if (sps / 16 >= 16384) continue;
+            if (tot <= SMEM_LIMIT) best = th;
+        }
+        if (best) {
+            pl.TH = best;
+            pl.n_stages = ns;
+            break;
+        }
+        if (ns == 1) return false;
+    }
+    pl.bands = (g.H + pl.TH - 1) / pl.TH;
+    pl.MT = (pl.TH * Wp + 127) / 128;
+    pl.sps = (pl.TH + 2) * Wp * 16;
+    pl.stage_bytes = ((16 + KC * pl.sps + TAIL_SLACK) + 127) / 128 * 128;
+    pl.staging_bytes = g.pool ? NCH * pl.TH * Wp * 16 : 0;
+    int off = pl.wbytes;
+    pl.off_bias = off; off += NP * 4; off = (off + 127) / 128 * 128;
+    pl.off_stage = off; off += pl.n_stages * pl.stage_bytes;
+    pl.off_staging = off; off += pl.staging_bytes; off = (off + 127) / 128 * 128;
+    pl.off_bar = off; off += 256;
+    pl.smem_bytes = off;
+    return off <= SMEM_LIMIT;
+}
+
+static int pad16(int c) { return (c + 15) / 16 * 16; }
+
+extern "C" {
+
+int asr_encoder_destroy(asr_encoder_t *e) {
+    if (!e) return ASR_OK;
+    cudaFree(e->l0_w);
+    for (int l = 0; l < 8; ++l) {
+        cudaFree(e->wblob[l]); cudaFree(e->act[l]); cudaFree(e->ref_w[l]); cudaFree(e->ref_bn[l]); cudaFree(e->ref_act[l]);
+    }
+    cudaFree(e->head_A); cudaFree(e->cca_mean); cudaFree(e->cca_proj); cudaFree(e->ref_in); cudaFree(e->ref_tmp);
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(e->dev_in[b]);
+        if (e->pin_in[b]) cudaFreeHost(e->pin_in[b]);
+        if (e->ev_copied[b]) cudaEventDestroy(e->ev_copied[b]);
+        if (e->ev_done[b]) cudaEventDestroy(e->ev_done[b]);
+    }
+    cudaFree(e->dev_codes); cudaFree(e->dev_lat);
+    if (e->s_copy) cudaStreamDestroy(e->s_copy);
+    if (e->s_comp) cudaStreamDestroy(e->s_comp);
+    delete e;
+    return ASR_OK;
+}
+
+int asr_encoder_set_cca(asr_encoder_t *e, const float *cca_mean, const float *cca_proj) {
+    ASR_CHECK_ARG(e && cca_mean && cca_proj, "NULL argument");
+    ASR_CUDA(cudaMemcpy(e->cca_mean, cca_mean, 32 * 4, cudaMemcpyHostToDevice));
+    ASR_CUDA(cudaMemcpy(e->cca_proj, cca_proj, 1024 * 4, cudaMemcpyHostToDevice));
+    return ASR_OK;
+}
+
+int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *d, int max_batch) {
+    ASR_CHECK_ARG(out && d, "NULL argument");
+    int rc = ensure_device();
+    if (rc) return rc;
+    ASR_CHECK_ARG(max_batch >= 1, "max_batch < 1");
+    ASR_CHECK_ARG(d->channels[8] == ASR_DIM, "last layer must have 32 channels");
+    ASR_CHECK_ARG(d->prepare >= 0 && d->prepare <= 2, "bad prepare mode");
+    for (int l = 0; l < 9; ++l)
+        ASR_CHECK_ARG(d->W[l] && d->beta[l] && d->gamma[l] && d->mean[l] && d->inv_std[l], "NULL layer parameter");
+    ASR_CHECK_ARG(d->cca_mean && d->cca_proj, "NULL CCA parameter");
+    ASR_CHECK_ARG(d->channels[0] <= L0_MAXC, "layer 0 supports at most 32 channels");
+    asr_encoder *e = new asr_encoder();
+    e->d = *d;
+    e->max_batch = max_batch;
+    e->H0 = d->prepare == ASR_PREP_SCALE_HALF ? d->in_h / 2 : d->in_h;
+    e->W0 = d->prepare == ASR_PREP_SCALE_HALF ? d->in_w / 2 : d->in_w;
+    int H = e->H0, W = e->W0, cin = 1;
+    e->flops = 0;
+    for (int l = 0; l < 8; ++l) {
+        LayerGeom &g = e->g[l];
+        g.cin = cin; g.cout = d->channels[l]; g.cinp = pad16(cin); g.coutp = pad16(g.cout);
+        g.H = H; g.W = W; g.pool = (l & 1);
+        g.Ho = g.pool ? H / 2 : H; g.Wo = g.pool ? W / 2 : W;
+        e->flops += 2.0 * 9.0 * cin * g.cout * H * W;
+        H = g.Ho; W = g.Wo; cin = g.cout;
+        if (H < 1 || W < 1) { delete e; set_error("input too small for four 2x2 pools"); return ASR_ERR_ARG; }
+        ASR_CHECK_ARG(g.coutp <= 128, "at most 128 channels per layer");
+    }
+    e->head_c = cin; e->head_h = H; e->head_w = W;
+    e->flops += 2.0 * cin * 32 * H * W;
+    ASR_CHECK_ARG(e->head_c <= 128, "head supports at most 128 input channels");
+
+    const size_t B = (size_t)max_batch;
+#define E_CUDA(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess) {                                                                       \
+            set_error(std::string("asr_encoder_create: " #expr " -> ") + cudaGetErrorString(_e));      \
+            asr_encoder_destroy(e);                                                                    \
+            return ASR_ERR_CUDA;                                                                       \
+        }                                                                                              \
+    } while (0)
+
+    // ---- fold BN, pack weights ----
+    std::vector<float> scale, bias;
+    for (int l = 0; l < 8; ++l) {
+        const LayerGeom &g = e->g[l];
+        scale.assign(g.cout, 0.f); bias.assign(g.cout, 0.f);
+        for (int c = 0; c < g.cout; ++c) {
+            scale[c] = d->gamma[l][c] * d->inv_std[l][c];
+            bias[c] = d->beta[l][c] - d->mean[l][c] * scale[c];
+        }
+        // fp32 path: raw (optionally flipped) weights + bn vectors
+        std::vector<float> wr((size_t)g.cout * g.cin * 9);
+        for (int co = 0; co < g.cout; ++co)
+            for (int ci = 0; ci < g.cin; ++ci)
+                for (int t = 0; t < 9; ++t)
+                    wr[((size_t)co * g.cin + ci) * 9 + t] = d->W[l][((size_t)co * g.cin + ci) * 9 + (d->flip_filters ? 8 - t : t)];
+        std::vector<float> bn(4 * (size_t)g.cout);
+        for (int c = 0; c < g.cout; ++c) {
+            bn[c] = d->beta[l][c]; bn[g.cout + c] = d->gamma[l][c];
+            bn[2 * g.cout + c] = d->mean[l][c]; bn[3 * g.cout + c] = d->inv_std[l][c];
+        }
+        E_CUDA(cudaMalloc(&e->ref_w[l], wr.size() * 4));
+        E_CUDA(cudaMemcpy(e->ref_w[l], wr.data(), wr.size() * 4, cudaMemcpyHostToDevice));
+        E_CUDA(cudaMalloc(&e->ref_bn[l], bn.size() * 4));
+        E_CUDA(cudaMemcpy(e->ref_bn[l], bn.data(), bn.size() * 4, cudaMemcpyHostToDevice));
+        if (l == 0) {
+            std::vector<float> w0((size_t)g.cout * 10);
+            for (int c = 0; c < g.cout; ++c) {
+                for (int t = 0; t < 9; ++t) w0[c * 9 + t] = wr[(size_t)c * 9 + t] * scale[c];
+                w0[(size_t)g.cout * 9 + c] = bias[c];
+            }
+            E_CUDA(cudaMalloc(&e->l0_w, w0.size() * 4));
+            E_CUDA(cudaMemcpy(e->l0_w, w0.data(), w0.size() * 4, cudaMemcpyHostToDevice));
+        } else {
+            if (!plan_conv(g, e->plan[l])) {
+                set_error("asr_encoder_create: layer " + std::to_string(l) + " does not fit in shared memory");
+                asr_encoder_destroy(e);
+                return ASR_ERR_UNSUPPORTED;
+            }
+            const int KC = g.cinp / 8, NP = g.coutp;
+            std::vector<uint8_t> blob((size_t)9 * KC * NP * 16 + NP * 4, 0);
+            bf16 *wb = reinterpret_cast<bf16 *>(blob.data());
+            for (int t = 0; t < 9; ++t)
+                for (int ci = 0; ci < g.cin; ++ci)
+                    for (int co = 0; co < g.cout; ++co) {
+                        float v = wr[((size_t)co * g.cin + ci) * 9 + t] * scale[co];
+                        wb[(((size_t)t * KC + ci / 8) * NP + co) * 8 + (ci & 7)] = __float2bfloat16_rn(v);
+                    }
+            float *bb = reinterpret_cast<float *>(blob.data() + (size_t)9 * KC * NP * 16);
+            for (int co = 0; co < g.cout; ++co) bb[co] = bias[co];
+            E_CUDA(cudaMalloc(&e->wblob[l], blob.size()));
+            E_CUDA(cudaMemcpy(e->wblob[l], blob.data(), blob.size(), cudaMemcpyHostToDevice));
+        }
+        // activations of both paths
+        e->act_plane[l] = (long long)(g.Ho + 2) * (g.Wo + 2) * 16;
+        e->act_sample[l] = e->act_plane[l] * (g.coutp / 8);
+        E_CUDA(cudaMalloc(&e->act[l], (size_t)e->act_sample[l] * B));
+        E_CUDA(cudaMemset(e->act[l], 0, (size_t)e->act_sample[l] * B));
+    }
+    {   // head: A[j][c] = W8[j][c] * scale8[j]; b[j] = beta8 - mean8*scale8
+        const int C = e->head_c;
+        std::vector<float> A((size_t)32 * C + 32);
+        for (int j = 0; j < 32; ++j) {
+            float s = d->gamma[8][j] * d->inv_std[8][j];
+            for (int c = 0; c < C; ++c) A[(size_t)j * C + c] = d->W[8][(size_t)j * C + c] * s;
+            A[(size_t)32 * C + j] = d->beta[8][j] - d->mean[8][j] * s;
+        }
+        E_CUDA(cudaMalloc(&e->head_A, A.size() * 4));
+        E_CUDA(cudaMemcpy(e->head_A, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+        E_CUDA(cudaMalloc(&e->cca_mean, 32 * 4));
+        E_CUDA(cudaMalloc(&e->cca_proj, 1024 * 4));
+        E_CUDA(cudaMemcpy(e->cca_mean, d->cca_mean, 32 * 4, cudaMemcpyHostToDevice));
+        E_CUDA(cudaMemcpy(e->cca_proj, d->cca_proj, 1024 * 4, cudaMemcpyHostToDevice));
+    }
+    static bool attr_done = false;
+    if (!attr_done) {
+        E_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        attr_done = true;
+    }
+#undef E_CUDA
+    *out = e;
+    return ASR_OK;
+}
+
+double asr_encoder_flops_per_sample(const asr_encoder_t *e) { return e ? e->flops : 0.0; }
+
+static int ensure_ref_buffers(asr_encoder *e) {
+    if (e->ref_in) return ASR_OK;
+    const size_t B = (size_t)e->max_batch;
+    ASR_CUDA(cudaMalloc(&e->ref_in, B * e->H0 * e->W0 * 4));
+    size_t tmp = 0;
+    for (int l = 0; l < 8; ++l) {
+        const LayerGeom &g = e->g[l];
+        ASR_CUDA(cudaMalloc(&e->ref_act[l], B * g.cout * g.Ho * g.Wo * 4));
+        if (g.pool) tmp = std::max(tmp, B * g.cout * g.H * g.W * 4);
+    }
+    ASR_CUDA(cudaMalloc(&e->ref_tmp, tmp));
+    return ASR_OK;
+}
+
+int asr_encoder_embed(asr_encoder_t *e, const void *x_dev, int x_dtype, int64_t n, float *codes_dev, float *latents_dev,
+                      int path, void *stream) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    ASR_CHECK_ARG(e && x_dev, "NULL argument");
+    ASR_CHECK_ARG(n >= 0 && n <= e->max_batch, "n exceeds max_batch");
+    ASR_CHECK_ARG(x_dtype == ASR_IN_F32 || x_dtype == ASR_IN_U8, "bad x_dtype");
+    ASR_CHECK_ARG(path == ASR_PATH_TCGEN05 || path == ASR_PATH_FP32, "bad path");
+    if (n == 0) return ASR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const asr_encoder_desc &d = e->d;
+    HeadParams hp;
+    hp.C = e->head_c; hp.H = e->head_h; hp.W = e->head_w; hp.Wp = e->head_w + 2;
+    hp.A = e->head_A; hp.cca_mean = e->cca_mean; hp.cca_proj = e->cca_proj;
+    hp.codes = codes_dev; hp.latents = latents_dev;
+    e->last_path = path;
+    if (path == ASR_PATH_TCGEN05) {
+        {
+            const LayerGeom &g = e->g[0];
+            L0Params p;
+            p.x = x_dev; p.x_u8 = x_dtype == ASR_IN_U8; p.prepare = d.prepare;
+            p.Hin = d.in_h; p.Win = d.in_w; p.H = g.H; p.W = g.W; p.Wp = g.W + 2; p.Hp = g.H + 2;
+            p.C = g.cout; p.NCH = g.coutp / 8; p.w = e->l0_w; p.out = e->act[0];
+            p.out_plane = e->act_plane[0]; p.out_sample = e->act_sample[0]; p.n = (int)n;
+            dim3 grid((g.H * g.W + 255) / 256, (unsigned)n);
+            l0_conv_kernel<<<grid, 256, 0, st>>>(p);
+            ASR_LAUNCH_CHECK();
+        }
+        for (int l = 1; l < 8; ++l) {
+            const LayerGeom &g = e->g[l];
+            const ConvPlan &pl = e->plan[l];
+            ConvParams p;
+            p.in = e->act[l - 1]; p.out = e->act[l]; p.wblob = e->wblob[l]; p.n_samples = (int)n;
+            p.H = g.H; p.W = g.W; p.Wp = g.W + 2; p.Hp = g.H + 2; p.KC = g.cinp / 8; p.NP = g.coutp; p.NCH = g.coutp / 8;
+            p.TH = pl.TH; p.bands = pl.bands; p.MT = pl.MT; p.pool = g.pool;
+            p.Ho = g.Ho; p.Wo = g.Wo; p.Wpo = g.Wo + 2;
+            p.in_plane = e->act_plane[l - 1]; p.in_sample = e->act_sample[l - 1];
+            p.out_plane = e->act_plane[l]; p.out_sample = e->act_sample[l];
+            p.sps = pl.sps; p.stage_bytes = pl.stage_bytes; p.n_stages = pl.n_stages; p.slot_cols = pl.slot_cols;
+            p.n_slots = pl.n_slots; p.tmem_cols = pl.tmem_cols; p.wbytes = pl.wbytes;
+            p.off_bias = pl.off_bias; p.off_stage = pl.off_stage; p.off_staging = pl.off_staging; p.off_bar = pl.off_bar;
+            const int items = (int)n * pl.bands;
+            const int grid = std::min(items, sm_count());
+            conv3x3_tc_kernel<<<grid, CONV_THREADS, pl.smem_bytes, st>>>(p);
+            ASR_LAUNCH_CHECK();
+        }
+        hp.in = e->act[7]; hp.is_p8 = 1; hp.plane = e->act_plane[7]; hp.sample = e->act_sample[7];
+    } else {
+        rc = ensure_ref_buffers(e);
+        if (rc) return rc;
+        const size_t tot0 = (size_t)n * e->H0 * e->W0;
+        ref_prepare_kernel<<<(unsigned)((tot0 + 255) / 256), 256, 0, st>>>(x_dev, x_dtype == ASR_IN_U8, d.prepare, d.in_h,
+                                                                          d.in_w, e->H0, e->W0, (int)n, e->ref_in);
+        ASR_LAUNCH_CHECK();
+        const float *cur = e->ref_in;
+        for (int l = 0; l < 8; ++l) {
+            const LayerGeom &g = e->g[l];
+            const size_t tot = (size_t)n * g.cout * g.H * g.W;
+            float *dst = g.pool ? e->ref_tmp : e->ref_act[l];
+            ref_conv3x3_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(cur, e->ref_w[l], e->ref_bn[l], (int)n, g.cin,
+                                                                             g.cout, g.H, g.W, 1, dst);
+            ASR_LAUNCH_CHECK();
+            if (g.pool) {
+                const size_t totp = (size_t)n * g.cout * g.Ho * g.Wo;
+                ref_pool_kernel<<<(unsigned)((totp + 255) / 256), 256, 0, st>>>(dst, (int)n * g.cout, g.H, g.W, e->ref_act[l]);
+                ASR_LAUNCH_CHECK();
+            }
+            cur = e->ref_act[l];
+        }
+        hp.in = e->ref_act[7]; hp.is_p8 = 0; hp.plane = (long long)e->head_h * e->head_w * 4;
+        hp.sample = hp.plane * e->head_c;
+    }
+    head_kernel<<<(unsigned)n, 128, 0, st>>>(hp);
+    ASR_LAUNCH_CHECK();
+    return ASR_OK;
+}
+
+int asr_encoder_debug_activation(asr_encoder_t *e, int layer, int path, int64_t n, float *out_host, int *c, int *h, int *w) {
+    ASR_CHECK_ARG(e && layer >= 0 && layer < 8 && n >= 1 && n <= e->max_batch, "bad argument");
+    const LayerGeom &g = e->g[layer];
+    if (c) *c = g.cout;
+    if (h) *h = g.Ho;
+    if (w) *w = g.Wo;
+    if (!out_host) return ASR_OK;
+    ASR_CUDA(cudaDeviceSynchronize());
+    if (path == ASR_PATH_FP32) {
+        ASR_CHECK_ARG(e->ref_act[layer] != nullptr, "fp32 path has not run");
+        ASR_CUDA(cudaMemcpy(out_host, e->ref_act[layer], (size_t)n * g.cout * g.Ho * g.Wo * 4, cudaMemcpyDeviceToHost));
+        return ASR_OK;
+    }
+    std::vector<uint16_t> raw((size_t)e->act_sample[layer] / 2 * n);
+    ASR_CUDA(cudaMemcpy(raw.data(), e->act[layer], raw.size() * 2, cudaMemcpyDeviceToHost));
+    const int Wp = g.Wo + 2;
+    for (int64_t s = 0; s < n; ++s)
+        for (int ch = 0; ch < g.cout; ++ch)
+            for (int y = 0; y < g.Ho; ++y)
+                for (int x = 0; x < g.Wo; ++x) {
+                    size_t idx = (size_t)s * (e->act_sample[layer] / 2) + (size_t)(ch >> 3) * (e->act_plane[layer] / 2) +
+                                 ((size_t)(y + 1) * Wp + x + 1) * 8 + (ch & 7);
+                    uint32_t bits = (uint32_t)raw[idx] << 16;
+                    float f;
+                    memcpy(&f, &bits, 4);
+                    out_host[(((size_t)s * g.cout + ch) * g.Ho + y) * g.Wo + x] = f;
+                }
+    return ASR_OK;
+}
+
+int asr_encoder_embed_host(asr_encoder_t *e, const void *x_host, int x_dtype, int64_t n, float *codes_host,
+                           float *latents_host, int path) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    ASR_CHECK_ARG(e && x_host, "NULL argument");
+    ASR_CHECK_ARG(x_dtype == ASR_IN_F32 || x_dtype == ASR_IN_U8, "bad x_dtype");
+    if (n == 0) return ASR_OK;
+    const size_t esz = x_dtype == ASR_IN_U8 ? 1 : 4;
+    const size_t sample_bytes = (size_t)e->d.in_h * e->d.in_w * esz;
+    const size_t max_bytes = (size_t)e->d.in_h * e->d.in_w * 4 * e->max_batch;
+    if (!e->s_copy) {
+        ASR_CUDA(cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking));
+        ASR_CUDA(cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            ASR_CUDA(cudaEventCreateWithFlags(&e->ev_copied[b], cudaEventDisableTiming));
+            ASR_CUDA(cudaEventCreateWithFlags(&e->ev_done[b], cudaEventDisableTiming));
+            ASR_CUDA(cudaMalloc(&e->dev_in[b], max_bytes));
+        }
+    }
+    if (e->out_cap < n) {
+        cudaFree(e->dev_codes); cudaFree(e->dev_lat);
+        e->dev_codes = e->dev_lat = nullptr;
+        ASR_CUDA(cudaMalloc(&e->dev_codes, (size_t)n * 32 * 4));
+        ASR_CUDA(cudaMalloc(&e->dev_lat, (size_t)n * 32 * 4));
+        e->out_cap = n;
+    }
+    cudaPointerAttributes pa;
+    bool pinned = cudaPointerGetAttributes(&pa, x_host) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (!pinned && !e->pin_in[0])
+        for (int b = 0; b < 2; ++b) ASR_CUDA(cudaMallocHost(&e->pin_in[b], max_bytes));
+    int64_t ci = 0;
+    for (int64_t s0 = 0; s0 < n; s0 += e->max_batch, ++ci) {
+        const int b = (int)(ci & 1);
+        const int64_t nb = std::min<int64_t>(e->max_batch, n - s0);
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(x_host) + (size_t)s0 * sample_bytes;
+        if (ci >= 2) ASR_CUDA(cudaStreamWaitEvent(e->s_copy, e->ev_done[b], 0));
+        if (!pinned) {
+            if (ci >= 2) ASR_CUDA(cudaEventSynchronize(e->ev_copied[b]));
+            memcpy(e->pin_in[b], src, (size_t)nb * sample_bytes);
+            src = reinterpret_cast<const uint8_t *>(e->pin_in[b]);
+        }
+        ASR_CUDA(cudaMemcpyAsync(e->dev_in[b], src, (size_t)nb * sample_bytes, cudaMemcpyHostToDevice, e->s_copy));
+        ASR_CUDA(cudaEventRecord(e->ev_copied[b], e->s_copy));
+        ASR_CUDA(cudaStreamWaitEvent(e->s_comp, e->ev_copied[b], 0));
+        rc = asr_encoder_embed(e, e->dev_in[b], x_dtype, nb, e->dev_codes + s0 * 32, e->dev_lat + s0 * 32, path, e->s_comp);
+        if (rc) return rc;
+        ASR_CUDA(cudaEventRecord(e->ev_done[b], e->s_comp));
+    }
+    if (codes_host)
+        ASR_CUDA(cudaMemcpyAsync(codes_host, e->dev_codes, (size_t)n * 32 * 4, cudaMemcpyDeviceToHost, e->s_comp));
+    if (latents_host)
+        ASR_CUDA(cudaMemcpyAsync(latents_host, e->dev_lat, (size_t)n * 32 * 4, cudaMemcpyDeviceToHost, e->s_comp));
+    ASR_CUDA(cudaStreamSynchronize(e->s_comp));
+    return ASR_OK;
+}
+
+}  // extern "C"

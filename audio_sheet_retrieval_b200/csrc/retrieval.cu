@@ -1,0 +1,721 @@
+// Fused L2-normalise + 32-dim dot + per-query top-k over a resident embedding DB, the
+// rank-of-target variant for eval_retrieval, the candidate-list merge and the piece vote.
+//
+// Replaces (reference, paths relative to its root):
+//   audio_sheet_retrieval/audio_sheet_server.py:530-563  cdist(DB, q, 'cosine') + argsort[:n]
+//   audio_sheet_retrieval/audio_sheet_server.py:230-240  per-window loop + np.unique vote
+//   audio_sheet_retrieval/utils/train_dcca_pool.py:39-74 N x N cdist + per-row argsort
+//
+// Data movement: the DB (n,32) fp32 row-major is streamed once per query tile with 2-D TMA
+// tensor loads (128-byte rows, SWIZZLE_128B so that "one thread = one row" reads are
+// bank-conflict free) through a 3-stage mbarrier ring; scores follow the pinned-order fp32
+// definition of oracle/search.py (separately rounded * and +, k = 0..31) so the returned
+// indices are bit-exact; candidates live in registers / shared memory; the distance matrix
+// is never written anywhere.
+#include <cuda.h>
+#include <math_constants.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace asr {
+
+constexpr int TK_THREADS = 256;
+constexpr int TK_ROWS = 256;                 // DB rows per stage = 32 KB
+constexpr int TK_STAGES = 3;
+constexpr int TK_QT = 16;                    // queries per pass
+constexpr int TK_QCAP = 512;                 // candidate queue entries per query
+constexpr int TK_STAGE_BYTES = TK_ROWS * 128;
+constexpr size_t TK_SCRATCH_BYTES = 64u << 20;
+
+struct TkSmem {
+    // stage buffers must be 1024-byte aligned for SWIZZLE_128B
+    float stage[TK_STAGES][TK_ROWS * 32];
+    float q[TK_QT][32];
+    float qs[TK_QT][TK_QCAP];                // candidate queue: score
+    uint32_t qi[TK_QT][TK_QCAP];             //                  local row
+    float ls[2][TK_QT][ASR_MAX_K];           // sorted lists (double buffered for the rank merge)
+    uint32_t li[2][TK_QT][ASR_MAX_K];
+    int qcount[TK_QT];
+    int llen[TK_QT];
+    int lbuf[TK_QT];
+    float thr_s[TK_QT];
+    uint32_t thr_i[TK_QT];
+    uint64_t full[TK_STAGES];
+    int flush_flag;
+};
+
+__device__ __forceinline__ bool beats(float sa, uint32_t ia, float sb, uint32_t ib) {
+    return (sa > sb) || (sa == sb && ia < ib);
+}
+
+// Pinned-order helpers (oracle/search.py): no FMA contraction anywhere.
+__device__ __forceinline__ void normalise32(float *d) {
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) ss = __fadd_rn(ss, __fmul_rn(d[k], d[k]));
+    float inv = __fdiv_rn(1.0f, __fsqrt_rn(ss));
+#pragma unroll
+    for (int k = 0; k < 32; ++k) d[k] = __fmul_rn(d[k], inv);
+}
+__device__ __forceinline__ float score32(const float *q, const float *d) {
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc = __fadd_rn(acc, __fmul_rn(q[k], d[k]));
+    return (acc != acc) ? -CUDART_INF_F : acc;
+}
+
+// One warp merges up to 32 candidates (one per lane; dead lanes carry alive=false) into
+// query q's sorted list by rank counting: final position = number of elements that beat you.
+// List entries are held in registers (ceil(len/32) rounds) so every shuffle is warp-uniform.
+__device__ void warp_merge_batch_uniform(TkSmem &sm, int q, int k, float cs, uint32_t ci, bool alive, int lane) {
+    const int len = sm.llen[q];
+    const int cur = sm.lbuf[q];
+    const float *ls = sm.ls[cur][q];
+    const uint32_t *li = sm.li[cur][q];
+    float *ns = sm.ls[cur ^ 1][q];
+    uint32_t *ni = sm.li[cur ^ 1][q];
+    const unsigned alive_mask = __ballot_sync(0xffffffffu, alive);
+    if (alive_mask == 0u) return;
+    int pos = 0;
+    for (int j = 0; j < len; ++j) pos += beats(ls[j], li[j], cs, ci) ? 1 : 0;   // broadcast reads
+    const int rounds = (len + 31) >> 5;
+    float es[ASR_MAX_K / 32];
+    uint32_t ei[ASR_MAX_K / 32];
+    int shift[ASR_MAX_K / 32];
+#pragma unroll
+    for (int r = 0; r < ASR_MAX_K / 32; ++r) {
+        int j = r * 32 + lane;
+        bool v = r < rounds && j < len;
+        es[r] = v ? ls[j] : -CUDART_INF_F;
+        ei[r] = v ? li[j] : 0xffffffffu;
+        shift[r] = 0;
+    }
+    for (int l = 0; l < 32; ++l) {
+        if (!((alive_mask >> l) & 1u)) continue;          // warp-uniform
+        float os = __shfl_sync(0xffffffffu, cs, l);
+        uint32_t oi = __shfl_sync(0xffffffffu, ci, l);
+        if (l != lane) pos += beats(os, oi, cs, ci) ? 1 : 0;
+#pragma unroll
+        for (int r = 0; r < ASR_MAX_K / 32; ++r) shift[r] += beats(os, oi, es[r], ei[r]) ? 1 : 0;
+    }
+#pragma unroll
+    for (int r = 0; r < ASR_MAX_K / 32; ++r) {
+        int j = r * 32 + lane;
+        if (r < rounds && j < len) {
+            int np = j + shift[r];
+            if (np < k) { ns[np] = es[r]; ni[np] = ei[r]; }
+        }
+    }
+    if (alive && pos < k) { ns[pos] = cs; ni[pos] = ci; }
+    __syncwarp();
+    if (lane == 0) {
+        int nl = len + __popc(alive_mask);
+        nl = nl < k ? nl : k;
+        sm.llen[q] = nl;
+        sm.lbuf[q] = cur ^ 1;
+        if (nl == k) { sm.thr_s[q] = ns[k - 1]; sm.thr_i[q] = ni[k - 1]; }
+    }
+    __syncwarp();
+}
+
+// Drain the candidate queues into the sorted lists.  Warp w owns queries w, w+8, ...
+__device__ void flush_queues(TkSmem &sm, int nq_tile, int k, int warp, int lane) {
+    for (int q = warp; q < nq_tile; q += TK_THREADS / 32) {
+        int n = sm.qcount[q];
+        n = n < TK_QCAP ? n : TK_QCAP;
+        for (int base = 0; base < n; base += 32) {
+            int c = base + lane;
+            bool alive = c < n;
+            float cs = alive ? sm.qs[q][c] : -CUDART_INF_F;
+            uint32_t ci = alive ? sm.qi[q][c] : 0xffffffffu;
+            if (alive && sm.llen[q] == k) alive = beats(cs, ci, sm.thr_s[q], sm.thr_i[q]);
+            warp_merge_batch_uniform(sm, q, k, cs, ci, alive, lane);
+        }
+        __syncwarp();
+        if (lane == 0) sm.qcount[q] = 0;
+    }
+}
+
+// grid: (n_slices, n_qgroups).  part_s/part_i: (nq, n_slices, k).
+__global__ void __launch_bounds__(TK_THREADS, 1)
+topk_stream_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles_per_slice, const float *__restrict__ q,
+                   int nq, int k, int normalise, float *__restrict__ part_s, uint32_t *__restrict__ part_i) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    TkSmem &sm = *reinterpret_cast<TkSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int slice = blockIdx.x, n_slices = gridDim.x;
+    const int64_t n_tiles = (n_db + TK_ROWS - 1) / TK_ROWS;
+    const int64_t tile0 = (int64_t)slice * tiles_per_slice;
+    int64_t my_tiles = n_tiles - tile0;
+    if (my_tiles > tiles_per_slice) my_tiles = tiles_per_slice;
+    if (my_tiles < 0) my_tiles = 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < TK_STAGES; ++s) mbar_init(&sm.full[s], 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&tmap);
+    }
+    __syncthreads();
+
+    const int n_qt = (nq + TK_QT - 1) / TK_QT;
+    int64_t it_global = 0;   // running tile counter across query tiles (barrier phases continue)
+    for (int qt = blockIdx.y; qt < n_qt; qt += gridDim.y) {
+        const int q0 = qt * TK_QT;
+        const int nq_tile = min(TK_QT, nq - q0);
+        // stage the query tile (normalised with the pinned definition)
+        if (tid < nq_tile) {
+            float v[32];
+#pragma unroll
+            for (int kk = 0; kk < 32; ++kk) v[kk] = q[(int64_t)(q0 + tid) * 32 + kk];
+            if (normalise) normalise32(v);
+#pragma unroll
+            for (int kk = 0; kk < 32; ++kk) sm.q[tid][kk] = v[kk];
+            sm.qcount[tid] = 0;
+            sm.llen[tid] = 0;
+            sm.lbuf[tid] = 0;
+            sm.thr_s[tid] = -CUDART_INF_F;
+            sm.thr_i[tid] = 0xffffffffu;
+        }
+        if (tid == 0) {
+            sm.flush_flag = 0;
+            // prologue: fill the ring
+            for (int s = 0; s < TK_STAGES && s < my_tiles; ++s) {
+                int slot = (int)((it_global + s) % TK_STAGES);
+                mbar_expect_tx(&sm.full[slot], TK_STAGE_BYTES);
+                tma_load_2d(sm.stage[slot], &tmap, 0, (int)((tile0 + s) * TK_ROWS), &sm.full[slot]);
+            }
+        }
+        __syncthreads();
+
+        for (int64_t it = 0; it < my_tiles; ++it, ++it_global) {
+            const int slot = (int)(it_global % TK_STAGES);
+            const uint32_t parity = (uint32_t)((it_global / TK_STAGES) & 1);
+            mbar_wait(&sm.full[slot], parity);
+            // my row: chunk c of row r sits at r*128 + ((c ^ (r & 7)) << 4)   (SWIZZLE_128B)
+            float d[32];
+            const float4 *rowp = reinterpret_cast<const float4 *>(sm.stage[slot] + tid * 32);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float4 v = rowp[c ^ (tid & 7)];
+                d[4 * c + 0] = v.x; d[4 * c + 1] = v.y; d[4 * c + 2] = v.z; d[4 * c + 3] = v.w;
+            }
+            __syncthreads();   // everyone has its row in registers: the slot can be refilled
+            if (tid == 0 && it + TK_STAGES < my_tiles) {
+                mbar_expect_tx(&sm.full[slot], TK_STAGE_BYTES);
+                tma_load_2d(sm.stage[slot], &tmap, 0, (int)((tile0 + it + TK_STAGES) * TK_ROWS), &sm.full[slot]);
+            }
+            const int64_t row = (tile0 + it) * TK_ROWS + tid;
+            const bool valid = row < n_db;
+            if (normalise) normalise32(d);
+            int overflow = 0;
+            for (int qq = 0; qq < nq_tile; ++qq) {
+                float s = score32(sm.q[qq], d);
+                bool pass = valid && (sm.llen[qq] < k || beats(s, (uint32_t)row, sm.thr_s[qq], sm.thr_i[qq]));
+                if (pass) {
+                    int p = atomicAdd(&sm.qcount[qq], 1);
+                    if (p < TK_QCAP) { sm.qs[qq][p] = s; sm.qi[qq][p] = (uint32_t)row; }
+                    if (p >= TK_QCAP - TK_ROWS) overflow = 1;
+                }
+            }
+            if (overflow) sm.flush_flag = 1;
+            __syncthreads();
+            if (sm.flush_flag) {      // uniform: read after the barrier
+                flush_queues(sm, nq_tile, k, warp, lane);
+                __syncthreads();
+                if (tid == 0) sm.flush_flag = 0;
+                __syncthreads();
+            }
+        }
+        flush_queues(sm, nq_tile, k, warp, lane);
+        __syncthreads();
+        // write this slice's lists
+        for (int e = tid; e < nq_tile * k; e += TK_THREADS) {
+            int qq = e / k, j = e % k;
+            int cur = sm.lbuf[qq];
+            bool v = j < sm.llen[qq];
+            size_t o = ((size_t)(q0 + qq) * n_slices + slice) * k + j;
+            part_s[o] = v ? sm.ls[cur][qq][j] : -CUDART_INF_F;
+            part_i[o] = v ? sm.li[cur][qq][j] : 0xffffffffu;
+        }
+        __syncthreads();
+    }
+}
+
+// One warp per query merges n_lists sorted lists (each k long) into the final top-k.
+// Input either (uint32 local rows + idx_base) or int64 global indices.
+struct MergeSmem {
+    float ls[2][ASR_MAX_K];
+    uint64_t li[2][ASR_MAX_K];
+};
+
+__device__ __forceinline__ bool beats64(float sa, int64_t ia, float sb, int64_t ib) {
+    return (sa > sb) || (sa == sb && ia < ib);
+}
+
+__global__ void __launch_bounds__(32)
+topk_merge_kernel(const float *__restrict__ in_s, const uint32_t *__restrict__ in_i32, const int64_t *__restrict__ in_i64,
+                  int64_t idx_base, int n_lists, int k, float *__restrict__ out_s, int64_t *__restrict__ out_i) {
+    __shared__ float ls[2][ASR_MAX_K];
+    __shared__ int64_t li[2][ASR_MAX_K];
+    const int lane = threadIdx.x;
+    const int64_t qi = blockIdx.x;
+    const size_t base = (size_t)qi * n_lists * k;
+    int len = 0, cur = 0;
+    float thr_s = -CUDART_INF_F;
+    int64_t thr_i = INT64_MAX;
+    const int total = n_lists * k;
+    for (int b = 0; b < total; b += 32) {
+        int c = b + lane;
+        bool alive = c < total;
+        float cs = -CUDART_INF_F;
+        int64_t ci = INT64_MAX;
+        if (alive) {
+            cs = in_s[base + c];
+            if (in_i32) {
+                uint32_t r = in_i32[base + c];
+                alive = r != 0xffffffffu;
+                ci = (int64_t)r + idx_base;
+            } else {
+                ci = in_i64[base + c];
+                alive = ci >= 0;
+                if (!alive) ci = INT64_MAX;
+            }
+        }
+        if (alive && len == k) alive = beats64(cs, ci, thr_s, thr_i);
+        unsigned mask = __ballot_sync(0xffffffffu, alive);
+        if (mask == 0u) continue;
+        const float *s0 = ls[cur];
+        const int64_t *i0 = li[cur];
+        float *s1 = ls[cur ^ 1];
+        int64_t *i1 = li[cur ^ 1];
+        int pos = 0;
+        for (int j = 0; j < len; ++j) pos += beats64(s0[j], i0[j], cs, ci) ? 1 : 0;
+        float es[ASR_MAX_K / 32];
+        int64_t ei[ASR_MAX_K / 32];
+        int shift[ASR_MAX_K / 32];
+#pragma unroll
+        for (int r = 0; r < ASR_MAX_K / 32; ++r) {
+            int j = r * 32 + lane;
+            bool v = j < len;
+            es[r] = v ? s0[j] : -CUDART_INF_F;
+            ei[r] = v ? i0[j] : INT64_MAX;
+            shift[r] = 0;
+        }
+        for (int l = 0; l < 32; ++l) {
+            if (!((mask >> l) & 1u)) continue;
+            float os = __shfl_sync(0xffffffffu, cs, l);
+            int64_t oi = __shfl_sync(0xffffffffu, ci, l);
+            if (l != lane) pos += beats64(os, oi, cs, ci) ? 1 : 0;
+#pragma unroll
+            for (int r = 0; r < ASR_MAX_K / 32; ++r) shift[r] += beats64(os, oi, es[r], ei[r]) ? 1 : 0;
+        }
+#pragma unroll
+        for (int r = 0; r < ASR_MAX_K / 32; ++r) {
+            int j = r * 32 + lane;
+            if (j < len) {
+                int np = j + shift[r];
+                if (np < k) { s1[np] = es[r]; i1[np] = ei[r]; }
+            }
+        }
+        if (alive && pos < k) { s1[pos] = cs; i1[pos] = ci; }
+        __syncwarp();
+        len = min(k, len + __popc(mask));
+        cur ^= 1;
+        if (len == k) { thr_s = ls[cur][k - 1]; thr_i = li[cur][k - 1]; }
+        __syncwarp();
+    }
+    for (int j = lane; j < k; j += 32) {
+        bool v = j < len;
+        out_s[(size_t)qi * k + j] = v ? ls[cur][j] : -CUDART_INF_F;
+        out_i[(size_t)qi * k + j] = v ? li[cur][j] : -1;
+    }
+}
+
+// ---- rank of target ---------------------------------------------------------------
+// phase 0: best correct item per query among this shard's rows (thread per query).
+__global__ void rank_target_kernel(const float *__restrict__ db, int64_t n_db, int64_t idx_base, const float *__restrict__ q,
+                                   int nq, int64_t q_base, int64_t kg, int64_t hg, int normalise,
+                                   float *__restrict__ tscore, int64_t *__restrict__ tidx) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    float qv[32];
+#pragma unroll
+    for (int kk = 0; kk < 32; ++kk) qv[kk] = q[(int64_t)i * 32 + kk];
+    if (normalise) normalise32(qv);
+    const int64_t g = (q_base + i) / hg;
+    float best = -CUDART_INF_F;
+    int64_t bj = -1;
+    for (int64_t j = g * kg; j < (g + 1) * kg; ++j) {
+        int64_t r = j - idx_base;
+        if (r < 0 || r >= n_db) continue;
+        float d[32];
+#pragma unroll
+        for (int kk = 0; kk < 32; ++kk) d[kk] = db[r * 32 + kk];
+        if (normalise) normalise32(d);
+        float s = score32(qv, d);
+        if (bj < 0 || s > best) { best = s; bj = j; }
+    }
+    tscore[i] = best;
+    tidx[i] = bj;
+}
+
+struct RkSmem {
+    float stage[TK_STAGES][TK_ROWS * 32];
+    float q[TK_QT][32];
+    float ts[TK_QT];
+    int64_t ti[TK_QT];
+    unsigned long long cnt[TK_QT];
+    uint64_t full[TK_STAGES];
+};
+
+// phase 1: count rows ranked before the target.  grid (n_slices, n_qgroups).
+__global__ void __launch_bounds__(TK_THREADS, 1)
+rank_count_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int64_t idx_base, int tiles_per_slice,
+                  const float *__restrict__ q, int nq, int normalise, const float *__restrict__ tscore,
+                  const int64_t *__restrict__ tidx, unsigned long long *__restrict__ better) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    RkSmem &sm = *reinterpret_cast<RkSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int slice = blockIdx.x;
+    const int64_t n_tiles = (n_db + TK_ROWS - 1) / TK_ROWS;
+    const int64_t tile0 = (int64_t)slice * tiles_per_slice;
+    int64_t my_tiles = n_tiles - tile0;
+    if (my_tiles > tiles_per_slice) my_tiles = tiles_per_slice;
+    if (my_tiles < 0) my_tiles = 0;
+    if (tid == 0) {
+        for (int s = 0; s < TK_STAGES; ++s) mbar_init(&sm.full[s], 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&tmap);
+    }
+    __syncthreads();
+    const int n_qt = (nq + TK_QT - 1) / TK_QT;
+    int64_t it_global = 0;
+    for (int qt = blockIdx.y; qt < n_qt; qt += gridDim.y) {
+        const int q0 = qt * TK_QT;
+        const int nq_tile = min(TK_QT, nq - q0);
+        if (tid < nq_tile) {
+            float v[32];
+#pragma unroll
+            for (int kk = 0; kk < 32; ++kk) v[kk] = q[(int64_t)(q0 + tid) * 32 + kk];
+            if (normalise) normalise32(v);
+#pragma unroll
+            for (int kk = 0; kk < 32; ++kk) sm.q[tid][kk] = v[kk];
+            sm.ts[tid] = tscore[q0 + tid];
+            sm.ti[tid] = tidx[q0 + tid];
+            sm.cnt[tid] = 0ull;
+        }
+        if (tid == 0) {
+            for (int s = 0; s < TK_STAGES && s < my_tiles; ++s) {
+                int slot = (int)((it_global + s) % TK_STAGES);
+                mbar_expect_tx(&sm.full[slot], TK_STAGE_BYTES);
+                tma_load_2d(sm.stage[slot], &tmap, 0, (int)((tile0 + s) * TK_ROWS), &sm.full[slot]);
+            }
+        }
+        __syncthreads();
+        unsigned cnt[TK_QT];
+#pragma unroll
+        for (int qq = 0; qq < TK_QT; ++qq) cnt[qq] = 0;
+        for (int64_t it = 0; it < my_tiles; ++it, ++it_global) {
+            const int slot = (int)(it_global % TK_STAGES);
+            const uint32_t parity = (uint32_t)((it_global / TK_STAGES) & 1);
+            mbar_wait(&sm.full[slot], parity);
+            float d[32];
+            const float4 *rowp = reinterpret_cast<const float4 *>(sm.stage[slot] + tid * 32);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float4 v = rowp[c ^ (tid & 7)];
+                d[4 * c + 0] = v.x; d[4 * c + 1] = v.y; d[4 * c + 2] = v.z; d[4 * c + 3] = v.w;
+            }
+            __syncthreads();
+            if (tid == 0 && it + TK_STAGES < my_tiles) {
+                mbar_expect_tx(&sm.full[slot], TK_STAGE_BYTES);
+                tma_load_2d(sm.stage[slot], &tmap, 0, (int)((tile0 + it + TK_STAGES) * TK_ROWS), &sm.full[slot]);
+            }
+            const int64_t row = (tile0 + it) * TK_ROWS + tid;
+            const bool valid = row < n_db;
+            const int64_t grow = row + idx_base;
+            if (normalise) normalise32(d);
+#pragma unroll
+            for (int qq = 0; qq < TK_QT; ++qq) {
+                if (qq < nq_tile) {
+                    float s = score32(sm.q[qq], d);
+                    float t = sm.ts[qq];
+                    bool b = valid && ((s > t) || (s == t && grow < sm.ti[qq]));
+                    cnt[qq] += b ? 1u : 0u;
+                }
+            }
+        }
+#pragma unroll
+        for (int qq = 0; qq < TK_QT; ++qq) {
+            unsigned c = cnt[qq];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (lane == 0 && qq < nq_tile && c) atomicAdd(&sm.cnt[qq], (unsigned long long)c);
+        }
+        __syncthreads();
+        if (tid < nq_tile && sm.cnt[tid]) atomicAdd(&better[q0 + tid], sm.cnt[tid]);
+        __syncthreads();
+    }
+}
+
+// ---- vote -------------------------------------------------------------------------
+constexpr int VOTE_MAX = 8192;
+constexpr int VOTE_THREADS = 256;
+
+template <typename T, bool DESC>
+__device__ void bitonic_sort_smem(T *a, int n, int tid, int nthreads) {   // n power of two
+    for (int size = 2; size <= n; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int i = tid; i < n / 2; i += nthreads) {
+                int lo = 2 * i - (i & (stride - 1));
+                int hi = lo + stride;
+                bool up = ((lo & size) == 0);
+                T x = a[lo], y = a[hi];
+                bool sw = DESC ? (up ? (x < y) : (x > y)) : (up ? (x > y) : (x < y));
+                if (sw) { a[lo] = y; a[hi] = x; }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// one CTA per recording
+__global__ void __launch_bounds__(VOTE_THREADS)
+vote_kernel(const int64_t *__restrict__ cand, const int32_t *__restrict__ row_ids, int64_t n_rows, int m, int m_pow2,
+            int top_k, int32_t *__restrict__ out_ids, int32_t *__restrict__ out_counts) {
+    extern __shared__ unsigned long long vsm[];     // m_pow2 entries
+    const int tid = threadIdx.x;
+    const int rec = blockIdx.x;
+    // keys = piece id (ascending sort); empty = ~0
+    for (int i = tid; i < m_pow2; i += VOTE_THREADS) {
+        unsigned long long key = ~0ull;
+        if (i < m) {
+            int64_t r = cand[(size_t)rec * m + i];
+            if (r >= 0 && r < n_rows) key = (unsigned long long)(uint32_t)row_ids[r];
+        }
+        vsm[i] = key;
+    }
+    bitonic_sort_smem<unsigned long long, false>(vsm, m_pow2, tid, VOTE_THREADS);
+    // run lengths: at each run start, count = (next run start) - i.  Two passes through registers.
+    unsigned long long newkey[VOTE_MAX / VOTE_THREADS];
+    int nn = 0;
+    for (int i = tid; i < m_pow2; i += VOTE_THREADS, ++nn) {
+        unsigned long long key = vsm[i];
+        unsigned long long out = 0ull;
+        if (key != ~0ull && (i == 0 || vsm[i - 1] != key)) {
+            int j = i + 1;
+            while (j < m_pow2 && vsm[j] == key) ++j;
+            out = ((unsigned long long)(j - i) << 32) | (key & 0xffffffffull);
+        }
+        newkey[nn] = out;
+    }
+    __syncthreads();
+    nn = 0;
+    for (int i = tid; i < m_pow2; i += VOTE_THREADS, ++nn) vsm[i] = newkey[nn];
+    bitonic_sort_smem<unsigned long long, true>(vsm, m_pow2, tid, VOTE_THREADS);
+    for (int j = tid; j < top_k; j += VOTE_THREADS) {
+        unsigned long long key = j < m_pow2 ? vsm[j] : 0ull;
+        bool v = key != 0ull;
+        out_ids[(size_t)rec * top_k + j] = v ? (int32_t)(key & 0xffffffffull) : -1;
+        out_counts[(size_t)rec * top_k + j] = v ? (int32_t)(key >> 32) : 0;
+    }
+}
+
+// ---- host side --------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+}  // namespace asr
+
+struct asr_db {
+    const float *codes;
+    int64_t n;
+    int64_t idx_base;
+    CUtensorMap tmap;
+    void *scratch;          // TK_SCRATCH_BYTES: per-slice partial lists
+    int sms;
+};
+
+using namespace asr;
+
+extern "C" {
+
+int asr_db_create(asr_db_t **out, const float *codes_dev, int64_t n, int64_t idx_base) {
+    ASR_CHECK_ARG(out != nullptr, "out is NULL");
+    int rc = ensure_device();
+    if (rc) return rc;
+    ASR_CHECK_ARG(codes_dev != nullptr && n > 0, "empty database");
+    ASR_CHECK_ARG((reinterpret_cast<uintptr_t>(codes_dev) & 127) == 0, "codes_dev must be 128-byte aligned");
+    ASR_CHECK_ARG(n < ((int64_t)1 << 31), "at most 2^31-1 rows per shard");
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return ASR_ERR_CUDA; }
+    asr_db *db = new asr_db();
+    db->codes = codes_dev;
+    db->n = n;
+    db->idx_base = idx_base;
+    db->sms = sm_count();
+    cuuint64_t gdim[2] = {32, (cuuint64_t)n};
+    cuuint64_t gstr[1] = {128};
+    cuuint32_t box[2] = {32, (cuuint32_t)TK_ROWS};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&db->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(codes_dev), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        delete db;
+        set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+        return ASR_ERR_CUDA;
+    }
+    if (cudaMalloc(&db->scratch, TK_SCRATCH_BYTES) != cudaSuccess) {
+        delete db;
+        set_error("cudaMalloc of the top-k scratch failed");
+        return ASR_ERR_CUDA;
+    }
+    static bool attr_done = false;
+    if (!attr_done) {
+        ASR_CUDA(cudaFuncSetAttribute(topk_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(TkSmem) + 1024));
+        ASR_CUDA(cudaFuncSetAttribute(rank_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(RkSmem) + 1024));
+        attr_done = true;
+    }
+    *out = db;
+    return ASR_OK;
+}
+
+int asr_db_destroy(asr_db_t *db) {
+    if (!db) return ASR_OK;
+    cudaFree(db->scratch);
+    delete db;
+    return ASR_OK;
+}
+
+static void plan_grid(const asr_db *db, int64_t nq, int *n_slices, int *tiles_per_slice, int *n_qgroups) {
+    const int64_t n_tiles = (db->n + TK_ROWS - 1) / TK_ROWS;
+    const int64_t n_qt = (nq + TK_QT - 1) / TK_QT;
+    const int sms = db->sms;
+    // few query tiles: slice the DB over all SMs.  Many query tiles: keep slices long
+    // (>= 64k rows) so per-slice list maintenance stays negligible and spread queries instead.
+    int64_t want = sms;
+    if (n_qt >= 2 * sms) want = std::max<int64_t>(1, std::min<int64_t>(sms, db->n / 65536));
+    else if (n_qt > 1) want = std::max<int64_t>(1, sms / n_qt);
+    int64_t tps = (n_tiles + want - 1) / want;
+    if (tps < 1) tps = 1;
+    int64_t ns = (n_tiles + tps - 1) / tps;
+    int64_t qg = std::min<int64_t>(n_qt, std::max<int64_t>(1, (2 * sms + ns - 1) / ns));
+    *n_slices = (int)ns;
+    *tiles_per_slice = (int)tps;
+    *n_qgroups = (int)qg;
+}
+
+int asr_topk(asr_db_t *db, const float *q_dev, int64_t nq, int k, int normalise, float *out_score_dev,
+             int64_t *out_idx_dev, void *stream) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    ASR_CHECK_ARG(db != nullptr, "db is NULL");
+    ASR_CHECK_ARG(k >= 1 && k <= ASR_MAX_K, "k must be in [1, ASR_MAX_K]");
+    ASR_CHECK_ARG(nq >= 0, "nq < 0");
+    if (nq == 0) return ASR_OK;
+    ASR_CHECK_ARG(q_dev && out_score_dev && out_idx_dev, "NULL buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    int n_slices, tps, dummy;
+    plan_grid(db, nq, &n_slices, &tps, &dummy);
+    // queries per launch bounded by the scratch: (score f32 + row u32) per (query, slice, k)
+    int64_t per_q = (int64_t)n_slices * k * 8;
+    int64_t q_chunk = std::max<int64_t>(TK_QT, (int64_t)(TK_SCRATCH_BYTES / per_q) / TK_QT * TK_QT);
+    for (int64_t q0 = 0; q0 < nq; q0 += q_chunk) {
+        int64_t nqc = std::min<int64_t>(q_chunk, nq - q0);
+        int ns, t2, qg;
+        plan_grid(db, nqc, &ns, &t2, &qg);
+        if (ns != n_slices) { ns = n_slices; t2 = tps; }   // keep the scratch layout of the plan
+        float *ps = reinterpret_cast<float *>(db->scratch);
+        uint32_t *pi = reinterpret_cast<uint32_t *>(ps + (size_t)nqc * ns * k);
+        dim3 grid(ns, qg);
+        topk_stream_kernel<<<grid, TK_THREADS, sizeof(TkSmem) + 1024, st>>>(db->tmap, db->n, t2, q_dev + q0 * 32, (int)nqc,
+                                                                            k, normalise, ps, pi);
+        ASR_LAUNCH_CHECK();
+        topk_merge_kernel<<<(unsigned)nqc, 32, 0, st>>>(ps, pi, nullptr, db->idx_base, ns, k, out_score_dev + q0 * k,
+                                                       out_idx_dev + q0 * k);
+        ASR_LAUNCH_CHECK();
+    }
+    return ASR_OK;
+}
+
+int asr_topk_merge(const float *score_dev, const int64_t *idx_dev, int64_t nq, int n_lists, int k, float *out_score_dev,
+                   int64_t *out_idx_dev, void *stream) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    ASR_CHECK_ARG(k >= 1 && k <= ASR_MAX_K && n_lists >= 1, "bad k / n_lists");
+    if (nq == 0) return ASR_OK;
+    ASR_CHECK_ARG(score_dev && idx_dev && out_score_dev && out_idx_dev, "NULL buffer");
+    topk_merge_kernel<<<(unsigned)nq, 32, 0, (cudaStream_t)stream>>>(score_dev, nullptr, idx_dev, 0, n_lists, k,
+                                                                    out_score_dev, out_idx_dev);
+    ASR_LAUNCH_CHECK();
+    return ASR_OK;
+}
+
+int asr_rank_of_target(asr_db_t *db, const float *q_dev, int64_t nq, int64_t q_base, int64_t kg, int64_t hg,
+                       int normalise, int phase, float *tscore_dev, int64_t *tidx_dev, int64_t *better_dev,
+                       void *stream) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    ASR_CHECK_ARG(db != nullptr && q_dev && tscore_dev && tidx_dev, "NULL argument");
+    ASR_CHECK_ARG(kg >= 1 && hg >= 1, "kg, hg must be >= 1");
+    if (nq == 0) return ASR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (phase == 0) {
+        rank_target_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(db->codes, db->n, db->idx_base, q_dev, (int)nq,
+                                                                        q_base, kg, hg, normalise, tscore_dev, tidx_dev);
+        ASR_LAUNCH_CHECK();
+        return ASR_OK;
+    }
+    ASR_CHECK_ARG(better_dev != nullptr, "better_dev is NULL");
+    int ns, tps, qg;
+    plan_grid(db, nq, &ns, &tps, &qg);
+    dim3 grid(ns, qg);
+    rank_count_kernel<<<grid, TK_THREADS, sizeof(RkSmem) + 1024, st>>>(db->tmap, db->n, db->idx_base, tps, q_dev, (int)nq,
+                                                                       normalise, tscore_dev, tidx_dev,
+                                                                       reinterpret_cast<unsigned long long *>(better_dev));
+    ASR_LAUNCH_CHECK();
+    return ASR_OK;
+}
+
+int asr_vote(const int64_t *cand_idx_dev, const int32_t *row_ids_dev, int64_t n_rows, int n_rec, int m, int top_k,
+             int32_t *out_ids_dev, int32_t *out_counts_dev, void *stream) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    ASR_CHECK_ARG(cand_idx_dev && row_ids_dev && out_ids_dev && out_counts_dev, "NULL buffer");
+    ASR_CHECK_ARG(m >= 1 && m <= VOTE_MAX, "m must be in [1, 8192]");
+    ASR_CHECK_ARG(top_k >= 1, "top_k < 1");
+    if (n_rec == 0) return ASR_OK;
+    int p2 = 32;
+    while (p2 < m) p2 <<= 1;
+    static bool attr_done = false;
+    if (!attr_done) {
+        ASR_CUDA(cudaFuncSetAttribute(vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VOTE_MAX * 8));
+        attr_done = true;
+    }
+    vote_kernel<<<n_rec, VOTE_THREADS, p2 * 8, (cudaStream_t)stream>>>(cand_idx_dev, row_ids_dev, n_rows, m, p2, top_k,
+                                                                       out_ids_dev, out_counts_dev);
+    ASR_LAUNCH_CHECK();
+    return ASR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,158 @@
+/* asr_b200.h - C ABI of the B200-native audio-sheet retrieval hot path.
+ *
+ * The reference (CPJKU/audio_sheet_retrieval) is pure Python on Theano/Lasagne and
+ * has NO FFI of its own; these entry points sit *behind* its Python interface
+ * (RetrievalWrapper / eval_retrieval / CCA / AudioSheetServer).  Every entry point
+ * cites the reference interface it replaces (paths relative to the reference
+ * root; asr/ = audio_sheet_retrieval/).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; asr_last_error() returns a
+ *     thread-local message for the last failing call.
+ *   - `*_dev` pointers are CUDA device pointers owned by the caller; `stream` is a
+ *     cudaStream_t passed as void* (NULL = legacy default stream).  No call
+ *     synchronises the host unless its name ends in `_host`.
+ *   - opaque handles own only what they allocate at create time (weights,
+ *     activation arena, per-CTA scratch); nothing is allocated on the hot path.
+ *   - sm_100a only.  There is no CPU fallback: without a CUDA device every compute
+ *     entry point fails with ASR_ERR_CUDA.
+ */
+#ifndef ASR_B200_H
+#define ASR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASR_OK 0
+#define ASR_ERR_ARG (-1)
+#define ASR_ERR_CUDA (-2)
+#define ASR_ERR_UNSUPPORTED (-3)
+
+#define ASR_DIM 32        /* DIM_LATENT, asr/models/mutopia_ccal_cont.py:36 */
+#define ASR_N_LAYERS 9    /* 8 conv3x3+BN+ELU and the 1x1 conv+BN head per view */
+#define ASR_MAX_K 128     /* largest n_candidates / top-k supported by asr_topk */
+
+/* input element types for the encoders */
+#define ASR_IN_F32 0      /* float32, the dtype the reference pools hand out (data_pools.py:203-228) */
+#define ASR_IN_U8 1       /* uint8 sheet images (what the float32 arrays hold: 0..255) */
+
+/* prepare modes (model.prepare) */
+#define ASR_PREP_NONE 0     /* view 2 is never prepared (retrieval_wrapper.py:74-77) */
+#define ASR_PREP_SCALE 1    /* x/255                     asr/models/mutopia_ccal_cont.py:170-190 */
+#define ASR_PREP_SCALE_HALF 2 /* x/255 then resize to half (2x2 box mean)  ..._rsz.py:170-190 */
+
+/* which kernels run the 3x3 layers */
+#define ASR_PATH_TCGEN05 0  /* bf16 implicit GEMM on tcgen05/TMEM, TMA-fed (product path) */
+#define ASR_PATH_FP32 1     /* fp32 CUDA-core kernels (on-device debug reference) */
+
+const char *asr_last_error(void);
+int asr_abi_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t asr_launch_count(void);
+
+/* ------------------------------------------------------------------------- *
+ * Encoders.  Replaces the compiled Theano functions of one branch:
+ *   asr/retrieval_wrapper.py:33-38 (compute_v1_latent / compute_v2_latent),
+ *   graph asr/models/mutopia_ccal_cont{,_rsz}.py:64-145,
+ *   CCALayer deterministic branch + LengthNormLayer (layers/cca.py:184-203, 39-40),
+ *   and the pre-CCA latent functions of asr/refine_cca.py:86-89.
+ * ------------------------------------------------------------------------- */
+typedef struct asr_encoder asr_encoder_t;
+
+typedef struct {
+    int in_h, in_w;                 /* raw input size, e.g. 160x200 (view 1) or 92x42 (view 2) */
+    int prepare;                    /* ASR_PREP_* */
+    int flip_filters;               /* 0 = cross-correlation (cuDNN layer, shipped weights), 1 = true convolution */
+    int channels[ASR_N_LAYERS];     /* output channels per layer; last must be ASR_DIM */
+    /* host pointers, Lasagne get_all_param_values order (pickle layout, SURVEY.md 8b face 3) */
+    const float *W[ASR_N_LAYERS];       /* (cout, cin, k, k), k = 3 for layers 0..7, 1 for layer 8 */
+    const float *beta[ASR_N_LAYERS];
+    const float *gamma[ASR_N_LAYERS];
+    const float *mean[ASR_N_LAYERS];
+    const float *inv_std[ASR_N_LAYERS];
+    const float *cca_mean;          /* (32,)   mean1 or mean2 */
+    const float *cca_proj;          /* (32,32) U or V, row-major (in, out) */
+} asr_encoder_desc;
+
+/* max_batch = largest number of samples one asr_encoder_embed call may carry */
+int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *desc, int max_batch);
+int asr_encoder_destroy(asr_encoder_t *enc);
+/* overwrite the CCA projection after a refit (asr/refine_cca.py:104-107) */
+int asr_encoder_set_cca(asr_encoder_t *enc, const float *cca_mean, const float *cca_proj);
+
+/* x_dev: (n, 1, in_h, in_w) of x_dtype.  codes_dev (n,32): unit-norm CCA codes (may be NULL).
+ * latents_dev (n,32): pre-CCA latents (may be NULL).  n <= max_batch. */
+int asr_encoder_embed(asr_encoder_t *enc, const void *x_dev, int x_dtype, int64_t n,
+                      float *codes_dev, float *latents_dev, int path, void *stream);
+/* Host buffers in, host buffers out (what RetrievalWrapper.compute_view_k does,
+ * asr/retrieval_wrapper.py:47-77): chunks of max_batch, pinned staging, copy/compute overlap.
+ * Blocks until the results are in codes_host / latents_host. */
+int asr_encoder_embed_host(asr_encoder_t *enc, const void *x_host, int x_dtype, int64_t n,
+                           float *codes_host, float *latents_host, int path);
+/* debug: copy layer `layer`'s activation (after ELU/pool) of the last embed call to host as
+ * NCHW float32 (n, c, h, w); returns c,h,w through the out params. */
+int asr_encoder_debug_activation(asr_encoder_t *enc, int layer, int path, int64_t n, float *out_host,
+                                 int *c, int *h, int *w);
+/* algorithmic FLOPs per sample of this branch (2*MACs of the nine convolutions) */
+double asr_encoder_flops_per_sample(const asr_encoder_t *enc);
+
+/* ------------------------------------------------------------------------- *
+ * Retrieval.  Replaces cdist(...,'cosine') + argsort of
+ *   asr/audio_sheet_server.py:530-563 (_retrieve_*_ids), the loop at :230-234,
+ *   and asr/utils/train_dcca_pool.py:39-74 (eval_retrieval ranking).
+ * Scores follow the pinned-order fp32 definition in oracle/search.py; order is
+ * (score desc, index asc); the distance matrix is never written to memory.
+ * ------------------------------------------------------------------------- */
+typedef struct asr_db asr_db_t;
+
+/* codes_dev: (n, 32) float32 row-major, 128-byte aligned, caller-owned and kept alive.
+ * idx_base: global index of row 0 (this shard's offset in a sharded DB). */
+int asr_db_create(asr_db_t **out, const float *codes_dev, int64_t n, int64_t idx_base);
+int asr_db_destroy(asr_db_t *db);
+
+/* q_dev (nq,32).  out_score_dev (nq,k) float32, out_idx_dev (nq,k) int64; slots beyond the
+ * DB size hold (-inf, -1).  normalise != 0 L2-normalises queries and DB rows in-kernel. */
+int asr_topk(asr_db_t *db, const float *q_dev, int64_t nq, int k, int normalise,
+             float *out_score_dev, int64_t *out_idx_dev, void *stream);
+/* merge n_lists candidate lists per query, laid out (nq, n_lists*k) - the step after the
+ * all-gather of per-GPU top-k. */
+int asr_topk_merge(const float *score_dev, const int64_t *idx_dev, int64_t nq, int n_lists, int k,
+                   float *out_score_dev, int64_t *out_idx_dev, void *stream);
+/* eval_retrieval ranking: query i's correct items are DB rows j with j/kg == (q_base+i)/hg
+ * (global j).  tscore_dev (nq) in/out: pass 1 (phase=0) computes the best correct score/index
+ * on the shard that owns them (others leave -inf); after a max-allreduce, phase=1 adds to
+ * better_dev (nq, int64) the number of local rows ranked before the best correct item. */
+int asr_rank_of_target(asr_db_t *db, const float *q_dev, int64_t nq, int64_t q_base, int64_t kg,
+                       int64_t hg, int normalise, int phase, float *tscore_dev, int64_t *tidx_dev,
+                       int64_t *better_dev, void *stream);
+/* per-recording vote (asr/audio_sheet_server.py:237-251): cand_idx_dev (n_rec, m) DB row indices
+ * (-1 = empty), row_ids_dev maps DB row -> piece id.  out_ids/out_counts (n_rec, top_k), filled with
+ * -1/0 beyond the number of distinct pieces.  Order: count desc, then piece id desc. */
+int asr_vote(const int64_t *cand_idx_dev, const int32_t *row_ids_dev, int64_t n_rows, int n_rec, int m,
+             int top_k, int32_t *out_ids_dev, int32_t *out_counts_dev, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * CCA statistics and solve.  Replaces asr/utils/cca.py:25-53,199-211 (CCA.fit 'svd')
+ * and the forward of layers/cca.py:91-182.
+ * ------------------------------------------------------------------------- */
+#define ASR_CCA_NSUMS 3136   /* sum x (32) | sum y (32) | sum x x^T | sum y y^T | sum x y^T (3 x 1024) */
+
+/* adds this shard's sufficient statistics of (h1,h2) (n,32) to sums_dev (fp64, ASR_CCA_NSUMS);
+ * shift1/shift2 (32, fp32, device, may be NULL) are subtracted from every row first. */
+int asr_cca_accumulate(const float *h1_dev, const float *h2_dev, int64_t n, const float *shift1_dev,
+                       const float *shift2_dev, double *sums_dev, void *stream);
+/* 'svd' fit from (all-reduced) sums.  mode 0 = CCA.fit('svd') (sigma descending);
+ * mode 1 = CCALayer train forward (eigh of TT'+rT, ascending, sign fix).
+ * Outputs (device): m1,m2 (32) U,V (32x32 row-major) as fp64, sigma (32) fp64. */
+int asr_cca_solve(const double *sums_dev, int64_t n_total, const float *shift1_dev, const float *shift2_dev,
+                  double r1, double r2, double rT, int mode, double *m1_dev, double *m2_dev,
+                  double *U_dev, double *V_dev, double *sigma_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASR_B200_H */

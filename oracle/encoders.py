@@ -270,7 +270,7 @@ def synth_params(model_name, seed=23, calib_n=16):
 
     def proj():
         Q, _ = np.linalg.qr(rng.normal(size=(32, 32)))
-        s = np.linspace(14.0, 4.0, 32)
+        s = np.linspace(10.0, 6.0, 32)
         return (Q * s).astype(np.float32)
 
     U, V = proj(), proj()

@@ -1,0 +1,164 @@
+"""Encoders through the C ABI vs the CPU oracle.
+
+Tolerances (BASELINE.json north_star): codes cosine >= 0.999 per row vs the fp32 oracle for the
+tcgen05/bf16 path; the fp32 CUDA-core path must agree to fp32 round-off.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.encoders import OracleNet, load_param_list, synth_inputs
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+PKL = {"mutopia_ccal_cont_rsz": os.path.join(GOLDEN, "params_all_split_mutopia_full_aug.pkl"),
+       "mutopia_ccal_cont": os.path.join(GOLDEN, "params_synth_mutopia_ccal_cont.pkl")}
+COS_TOL = 0.999
+
+
+def _cos(a, b):
+    return (a * b).sum(1) / np.linalg.norm(a, axis=1) / np.linalg.norm(b, axis=1)
+
+
+def _net(model_name, max_batch=64):
+    import importlib
+    from audio_sheet_retrieval_b200 import network
+    from audio_sheet_retrieval_b200.params import load_params
+    model = importlib.import_module("audio_sheet_retrieval_b200.models." + model_name)
+    layers = model.build_model(show_model=False)
+    net = layers[0].net
+    net.max_batch = max_batch
+    network.set_all_param_values(layers, load_params(PKL[model_name]))
+    return model, net
+
+
+@pytest.mark.parametrize("model_name", ["mutopia_ccal_cont_rsz", "mutopia_ccal_cont"])
+@pytest.mark.parametrize("view", [1, 2])
+def test_fp32_path_matches_oracle_per_layer(model_name, view):
+    from audio_sheet_retrieval_b200 import _lib
+    model, net = _net(model_name)
+    onet = OracleNet(model_name, load_param_list(PKL[model_name]))
+    X1, X2 = synth_inputs(6, seed=3)
+    X = X1 if view == 1 else X2
+    mode = model.prepare.asr_prepare_mode if view == 1 else _lib.PREP_NONE
+    enc = net.encoder(view, mode)
+    codes, lats = enc.embed_host(X, want="both", path=_lib.PATH_FP32)
+    Xp = onet.prepare(X) if view == 1 else X
+    ref_c = onet.code(view, Xp).numpy()
+    ref_l = onet.latent(view, Xp).numpy()
+    np.testing.assert_allclose(lats, ref_l, atol=2e-5, rtol=1e-4)
+    assert _cos(codes, ref_c).min() > 0.99999
+    # per-layer activations
+    import torch.nn.functional as F
+    from oracle.encoders import _elu
+    h = torch.as_tensor(Xp)
+    for l in range(8):
+        L = onet.views[view - 1][l]
+        y = F.conv2d(h, torch.as_tensor(L["W"]), padding=1)
+        y = (y - torch.as_tensor(L["mean"]).view(1, -1, 1, 1)) * torch.as_tensor(L["gamma"] * L["inv_std"]).view(1, -1, 1, 1) \
+            + torch.as_tensor(L["beta"]).view(1, -1, 1, 1)
+        y = _elu(y)
+        if l % 2:
+            y = F.max_pool2d(y, 2)
+        got = enc.debug_activation(l, 6, path=_lib.PATH_FP32)
+        assert got.shape == tuple(y.shape)
+        np.testing.assert_allclose(got, y.numpy(), atol=5e-4, rtol=1e-3, err_msg="layer %d" % l)
+        h = y
+
+
+@pytest.mark.parametrize("model_name", ["mutopia_ccal_cont_rsz", "mutopia_ccal_cont"])
+@pytest.mark.parametrize("view", [1, 2])
+def test_tcgen05_path_per_layer_vs_fp32_path(model_name, view):
+    """Layer by layer: bf16 tensor-core activations vs the fp32 kernels on the same device."""
+    from audio_sheet_retrieval_b200 import _lib
+    model, net = _net(model_name)
+    X1, X2 = synth_inputs(5, seed=4)
+    X = X1 if view == 1 else X2
+    mode = model.prepare.asr_prepare_mode if view == 1 else _lib.PREP_NONE
+    enc = net.encoder(view, mode)
+    c_tc, l_tc = enc.embed_host(X, want="both", path=_lib.PATH_TCGEN05)
+    acts_tc = [enc.debug_activation(l, 5, path=_lib.PATH_TCGEN05) for l in range(8)]
+    c_fp, l_fp = enc.embed_host(X, want="both", path=_lib.PATH_FP32)
+    for l in range(8):
+        ref = enc.debug_activation(l, 5, path=_lib.PATH_FP32)
+        err = np.abs(acts_tc[l] - ref).max()
+        scale = np.abs(ref).max()
+        assert err <= 0.05 * scale + 0.02, "layer %d: max err %.4g (scale %.3g)" % (l, err, scale)
+    assert _cos(c_tc, c_fp).min() >= COS_TOL
+
+
+@pytest.mark.parametrize("model_name,n", [("mutopia_ccal_cont_rsz", 150), ("mutopia_ccal_cont", 70)])
+def test_codes_cosine_vs_oracle(model_name, n):
+    """The headline parity number: per-row cosine >= 0.999 vs the fp32 oracle, both views, u8 and
+    f32 sheet inputs, n > max_batch so the chunked host path is exercised."""
+    from audio_sheet_retrieval_b200 import _lib
+    model, net = _net(model_name, max_batch=64)
+    onet = OracleNet(model_name, load_param_list(PKL[model_name]))
+    X1, X2 = synth_inputs(n, seed=5)
+    ref1, ref2 = onet.compute_view_1(X1), onet.compute_view_2(X2)
+    e1 = net.encoder(1, model.prepare.asr_prepare_mode)
+    e2 = net.encoder(2, _lib.PREP_NONE)
+    c1 = e1.embed_host(X1)
+    c1_u8 = e1.embed_host(X1.astype(np.uint8))
+    c2 = e2.embed_host(X2)
+    assert (c1 == c1_u8).all(), "uint8 and float32 sheet inputs must give identical codes"
+    np.testing.assert_allclose(np.linalg.norm(c1, axis=1), 1.0, atol=1e-5)
+    assert _cos(c1, ref1).min() >= COS_TOL, _cos(c1, ref1).min()
+    assert _cos(c2, ref2).min() >= COS_TOL, _cos(c2, ref2).min()
+    # prepared input + PREP_NONE handle == raw input + fused prepare
+    c1_prep = net.encoder(1, _lib.PREP_NONE).embed_host(model.prepare(X1))
+    assert _cos(c1_prep, c1).min() > 0.99999
+
+
+def test_real_sheet_windows_shipped_weights():
+    """Non-degenerate case from shipped data: windows of tutorials/sheet_image.png."""
+    import cv2
+    from audio_sheet_retrieval_b200 import _lib
+    model, net = _net("mutopia_ccal_cont_rsz")
+    onet = OracleNet("mutopia_ccal_cont_rsz", load_param_list(PKL["mutopia_ccal_cont_rsz"]))
+    im = cv2.imread(os.path.join(GOLDEN, "sheet_image.png"), 0).astype(np.float32)
+    wins = np.stack([im[y:y + 160, x:x + 200] for y in range(60, 1000, 97) for x in range(0, 600, 61)])[:, None]
+    ref = onet.compute_view_1(wins)
+    got = net.encoder(1, model.prepare.asr_prepare_mode).embed_host(wins)
+    assert _cos(got, ref).min() >= COS_TOL
+    # shifting a window by 4 px keeps it the nearest neighbour of its origin among all windows
+    shifted = np.stack([im[y:y + 160, x + 4:x + 204] for y in range(60, 1000, 97) for x in range(0, 600, 61)])[:, None]
+    got_s = net.encoder(1, model.prepare.asr_prepare_mode).embed_host(shifted)
+    ref_s = onet.compute_view_1(shifted)
+    assert ((got_s @ got.T).argmax(1) == (ref_s @ ref.T).argmax(1)).mean() >= 0.98
+
+
+def test_embed_device_and_edge_sizes():
+    from audio_sheet_retrieval_b200 import _lib
+    model, net = _net("mutopia_ccal_cont_rsz", max_batch=8)
+    X1, X2 = synth_inputs(9, seed=6)
+    e2 = net.encoder(2, _lib.PREP_NONE)
+    full = e2.embed_host(X2)
+    one = e2.embed_host(X2[:1])
+    assert (one == full[:1]).all()
+    x = torch.as_tensor(X2[:8]).cuda()
+    codes = torch.empty((8, 32), device="cuda")
+    e2.embed_device(x, codes=codes)
+    torch.cuda.synchronize()
+    assert (codes.cpu().numpy() == full[:8]).all()
+    with pytest.raises(Exception):
+        e2.embed_device(torch.as_tensor(X2).cuda(), codes=torch.empty((9, 32), device="cuda"))   # n > max_batch
+    with pytest.raises(ValueError):
+        e2.embed_host(X1)                                                                         # wrong shape
+    assert e2.embed_host(X2[:0]).shape == (0, 32)
+
+
+def test_flip_filters_switch_changes_result():
+    from audio_sheet_retrieval_b200 import _lib
+    model, net = _net("mutopia_ccal_cont_rsz")
+    X1, X2 = synth_inputs(4, seed=7)
+    a = net.encoder(2, _lib.PREP_NONE).embed_host(X2)
+    model2, net2 = _net("mutopia_ccal_cont_rsz")
+    net2.flip_filters = True
+    b = net2.encoder(2, _lib.PREP_NONE).embed_host(X2)
+    onet = OracleNet("mutopia_ccal_cont_rsz", load_param_list(PKL["mutopia_ccal_cont_rsz"]), flip_filters=True)
+    assert _cos(b, onet.compute_view_2(X2)).min() >= COS_TOL
+    assert _cos(a, b).min() < 0.999

@@ -1,0 +1,159 @@
+"""Parity of the fused retrieval kernels (through the C ABI) with the pinned-order oracle.
+Bit-exact: indices AND scores."""
+import numpy as np
+import pytest
+
+from oracle import clib, metrics, search
+
+pytestmark = pytest.mark.gpu
+
+
+def _db(n, seed=0, unit=True):
+    rng = np.random.RandomState(seed)
+    d = rng.normal(size=(n, 32)).astype(np.float32)
+    if unit:
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return d
+
+
+@pytest.mark.parametrize("n,nq,k", [(1, 1, 1), (5, 3, 8), (255, 2, 25), (256, 17, 25), (257, 16, 1), (3001, 33, 25),
+                                    (20000, 100, 25), (70000, 7, 128), (300000, 1, 25)])
+def test_topk_bit_exact(n, nq, k):
+    from audio_sheet_retrieval_b200.retrieval import EmbeddingDB
+    D, Q = _db(n, 1), _db(nq, 2, unit=False)
+    s_ref, i_ref = clib.topk(Q, D, k)
+    db = EmbeddingDB(D)
+    s, i = db.topk(Q, k)
+    assert (i == i_ref).all(), "indices differ"
+    assert (s.view(np.uint32) == s_ref.view(np.uint32)).all() or (s == s_ref).all()
+
+
+def test_topk_ties_zero_rows_and_base():
+    from audio_sheet_retrieval_b200.retrieval import EmbeddingDB
+    D = _db(5000, 3)
+    D[10] = D[2000] = D[4999] = D[77]          # exact duplicates -> ties resolve by index
+    D[5] = 0                                   # zero row -> NaN -> -inf, never selected
+    Q = np.concatenate([D[70:80], _db(6, 4)])
+    s_ref, i_ref = search.pinned_topk(Q, D, 25, idx_base=12345)
+    db = EmbeddingDB(D, idx_base=12345)
+    s, i = db.topk(Q, 25)
+    assert (i == i_ref).all() and (s == s_ref).all()
+    assert list(i[7, :4] - 12345) == [10, 77, 2000, 4999]
+    assert not (i - 12345 == 5).any()
+
+
+def test_topk_unnormalised_inputs_and_no_normalise():
+    from audio_sheet_retrieval_b200.retrieval import EmbeddingDB
+    D, Q = _db(4000, 5, unit=False) * 3.7, _db(9, 6, unit=False) * 0.01
+    db = EmbeddingDB(D)
+    for norm in (True, False):
+        s_ref, i_ref = clib.topk(Q, D, 10, normalise=norm)
+        s, i = db.topk(Q, 10, normalise=norm)
+        assert (i == i_ref).all() and (s == s_ref).all()
+
+
+def test_topk_clipped_dims_match_oracle():
+    """--max_dim clipping (run_eval.py:160-162): zero padding adds exactly nothing."""
+    from audio_sheet_retrieval_b200.retrieval import EmbeddingDB
+    D, Q = _db(3000, 7), _db(11, 8)
+    s_ref, i_ref = clib.topk(Q[:, :8], D[:, :8], 5)
+    s, i = EmbeddingDB(D[:, :8]).topk(Q[:, :8], 5)
+    assert (i == i_ref).all() and (s == s_ref).all()
+
+
+def test_topk_matches_reference_rows(golden):
+    """Same rows as the reference's own cdist+argsort on the golden server fixture."""
+    from audio_sheet_retrieval_b200.retrieval import EmbeddingDB
+    db = EmbeddingDB(golden["srv_db"])
+    _, i = db.topk(golden["srv_q"][3:4], 25)
+    assert (i[0] == golden["srv_sidx"]).all()
+
+
+def test_sharded_topk_merge_equals_global():
+    import torch
+    from audio_sheet_retrieval_b200.retrieval import EmbeddingDB, merge_topk_device
+    D, Q = _db(10007, 9), _db(40, 10)
+    D[9000] = D[100]
+    k, world = 25, 4
+    s_ref, i_ref = clib.topk(Q, D, k)
+    ss, ii = [], []
+    q = torch.as_tensor(Q).cuda()
+    for r in range(world):
+        lo, hi = len(D) * r // world, len(D) * (r + 1) // world
+        s, i = EmbeddingDB(D[lo:hi], idx_base=lo).topk_device(q, k)
+        ss.append(s); ii.append(i)
+    S = torch.stack(ss, 1).reshape(len(Q), world * k)
+    I = torch.stack(ii, 1).reshape(len(Q), world * k)
+    s, i = merge_topk_device(S, I, world, k)
+    assert (i.cpu().numpy() == i_ref).all() and (s.cpu().numpy() == s_ref).all()
+
+
+@pytest.mark.parametrize("n1,n2", [(300, 300), (100, 300), (300, 100), (2000, 2000), (1, 1)])
+def test_ranks_bit_exact(n1, n2):
+    from audio_sheet_retrieval_b200.utils.train_dcca_pool import retrieval_ranks
+    base = np.random.RandomState(11).normal(size=(max(n1, n2), 32))
+    a = (base[:n1] if n1 <= n2 else base) + 0.8 * np.random.RandomState(12).normal(size=(n1, 32))
+    b = (np.repeat(base[:n1], n2 // n1, axis=0) if n2 > n1 else base[:n2]) + 0.8 * np.random.RandomState(13).normal(size=(n2, 32))
+    a, b = a.astype(np.float32), b.astype(np.float32)
+    r_ref, t_ref = clib.rank(a, b)
+    r, t = retrieval_ranks(a, b)
+    assert (r == r_ref).all() and (t == t_ref).all()
+
+
+def test_eval_retrieval_matches_reference_golden(golden):
+    """R@k / MRR / mean+median rank equal the reference's own eval_retrieval on its golden data."""
+    from audio_sheet_retrieval_b200.utils.train_dcca_pool import eval_retrieval
+    for a, b, key in (("er_lv1", "er_lv2", "er_res"), ("er_g_lv1", "er_g_lv2", "er_g_res")):
+        mr, med, md, hr, mrr = eval_retrieval(golden[a], golden[b])
+        ref = golden[key]
+        assert mr == ref[0] and med == ref[1] and mrr == pytest.approx(ref[7], abs=1e-12)
+        assert [hr[1], hr[5], hr[10], hr[25]] == list(ref[3:7])
+        if key == "er_res":
+            assert md == pytest.approx(ref[2], abs=1e-6)
+    mr, med, md, hr, mrr = eval_retrieval(golden["er_lv1"][:, :8], golden["er_lv2"][:, :8])
+    ref = golden["er_c_res"]
+    assert mr == ref[0] and med == ref[1] and [hr[1], hr[5], hr[10], hr[25]] == list(ref[3:7])
+
+
+def test_vote_matches_oracle_and_reference(golden):
+    import torch
+    from audio_sheet_retrieval_b200.audio_sheet_server import AudioSheetServer
+    srv = AudioSheetServer()
+    n_pieces = int(golden["srv_ids"].max()) + 1
+    names = dict((i, "piece_%02d" % i) for i in range(n_pieces))
+    srv.set_sheet_db(golden["srv_db"], golden["srv_ids"], names)
+    srv.set_audio_db(golden["srv_db"], golden["srv_ids"], names)
+    pid, sidx = srv._retrieve_sheet_snippet_ids(golden["srv_q"][3:4], 25)
+    assert (pid == golden["srv_pid"]).all() and (sidx == golden["srv_sidx"]).all()
+    res, votes = srv._vote(srv._sheet_db, golden["srv_q"], names, 5, 25, False)
+    assert [int(r.split("_")[1]) for r in res] == list(golden["srv_names"])
+    np.testing.assert_allclose(votes, golden["srv_votes"], atol=1e-15)
+    res, votes = srv._vote(srv._audio_db, golden["srv_q"], names, 5, 10, False)
+    assert [int(r.split("_")[1]) for r in res] == list(golden["srv_p_names"])
+    np.testing.assert_allclose(votes, golden["srv_p_votes"], atol=1e-15)
+
+
+def test_piece_identification_batched_equals_oracle():
+    from audio_sheet_retrieval_b200.audio_sheet_server import AudioSheetServer
+    db, ids, q, true_piece = search.synth_piece_db(200, 50, 12, 100, sigma=0.25)
+    srv = AudioSheetServer()
+    srv.set_sheet_db(db, ids, dict((i, str(i)) for i in range(200)))
+    got_ids, got_cnt = srv.identify_from_codes(q, 12, top_k=5, n_candidates=25)
+    for r in range(12):
+        ref_ids, ref_votes, _ = search.detect_pinned(q[r * 100:(r + 1) * 100], db, ids, top_k=5, n_candidates=25)
+        assert list(got_ids[r][:len(ref_ids)]) == list(ref_ids)
+        assert list(got_cnt[r][:len(ref_ids)]) == list(ref_votes)
+    assert (got_ids[:, 0] == true_piece).mean() >= 0.9
+
+
+def test_large_db_roundtrip_property():
+    """Full-size style check without the oracle: every DB row queried against the DB returns itself first."""
+    import torch
+    from audio_sheet_retrieval_b200.retrieval import EmbeddingDB
+    g = torch.Generator(device="cuda").manual_seed(1)
+    D = torch.randn((1000000, 32), generator=g, device="cuda")
+    db = EmbeddingDB(D)
+    rows = torch.arange(0, 1000000, 9973, device="cuda")
+    s, i = db.topk_device(D[rows].contiguous(), 4)
+    assert (i[:, 0] == rows).all()
+    assert (s[:, 0] > 0.9999).all() and (s[:, :-1] >= s[:, 1:]).all()

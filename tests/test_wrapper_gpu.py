@@ -1,0 +1,124 @@
+"""The reference-facing interface end to end: RetrievalWrapper, run_eval, refine_cca, server."""
+import os
+
+import numpy as np
+import pytest
+import yaml
+
+from oracle import cca as occa
+from oracle import metrics
+from oracle.encoders import OracleNet, load_param_list, synth_inputs
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+PKL = os.path.join(GOLDEN, "params_all_split_mutopia_full_aug.pkl")
+
+
+def _cos(a, b):
+    return (a * b).sum(1) / np.linalg.norm(a, axis=1) / np.linalg.norm(b, axis=1)
+
+
+def test_retrieval_wrapper_tutorial_contract():
+    """Embedding Tutorial.ipynb cells 20-33: shapes, dtypes, attributes."""
+    from audio_sheet_retrieval_b200.models import mutopia_ccal_cont_rsz as model
+    from audio_sheet_retrieval_b200.retrieval_wrapper import RetrievalWrapper
+    w = RetrievalWrapper(model, PKL, prepare_view_1=model.prepare, prepare_view_2=None)
+    assert w.code_dim == 32 and tuple(w.shape_view1) == (1, 80, 100) and tuple(w.shape_view2) == (1, 92, 42)
+    assert model.INPUT_SHAPE_1[1:] == [160, 200] and model.INPUT_SHAPE_2[1:] == [92, 42]
+    X1, X2 = synth_inputs(100, seed=8)
+    c1, c2 = w.compute_view_1(X1), w.compute_view_2(X2)
+    assert c1.shape == (100, 32) and c2.shape == (100, 32) and c1.dtype == np.float32
+    onet = OracleNet("mutopia_ccal_cont_rsz", load_param_list(PKL))
+    assert _cos(c1, onet.compute_view_1(X1)).min() >= 0.999
+    assert _cos(c2, onet.compute_view_2(X2)).min() >= 0.999
+    # audio-to-audio tutorial: both prepare_* None, view-1 input already prepared
+    w2 = RetrievalWrapper(model, PKL)
+    c1b = w2.compute_view_1(model.prepare(X1))
+    assert _cos(c1b, c1).min() > 0.99999
+    # a custom host-side prepare callable goes through the generic batch loop
+    w3 = RetrievalWrapper(model, PKL, prepare_view_1=lambda x: model.prepare(x))
+    assert _cos(w3.compute_view_1(X1[:23]), c1[:23]).min() > 0.99999
+    # two-input compiled functions (run_eval.py:91-95)
+    r = w.compute_v2_latent(w.dummy_in_v1, X2[:5])
+    assert (r == c2[:5]).all()
+
+
+def test_run_eval_metrics_vs_oracle(tmp_path, capsys):
+    """Config 1 (reduced n): R@k / MRR / MR within 0.5 % absolute of the oracle's eval on oracle codes."""
+    from audio_sheet_retrieval_b200 import run_eval
+    from audio_sheet_retrieval_b200.utils.mutopia_data import SyntheticPairPool
+    n = 300
+    res = run_eval.main(["--model", "mutopia_ccal_cont_rsz", "--data", "mutopia", "--n_test", str(n),
+                         "--param_file", PKL])
+    out = capsys.readouterr().out
+    assert "Median Rank" in out and "MAP" in out
+    pool = SyntheticPairPool(2000, seed=25)
+    idx = np.linspace(0, 1999, n).astype(int)
+    X1, X2 = pool[idx]
+    onet = OracleNet("mutopia_ccal_cont_rsz", load_param_list(PKL))
+    mr, med, md, hr, mrr = metrics.eval_retrieval_ref(onet.compute_view_1(X1), onet.compute_view_2(X2))
+    assert abs(res["map"] - mrr) <= 0.005
+    assert abs(res["med_rank"] - med) <= max(1.0, 0.005 * n)
+    for k in (1, 5, 10, 25):
+        assert abs(res["recall_at_k"]["%d" % k] - 100.0 * hr[k] / n) <= 0.5 + 100.0 / n
+
+
+def test_run_eval_yaml_schema(tmp_path):
+    from audio_sheet_retrieval_b200 import run_eval
+    import shutil
+    pf = tmp_path / "params_all_split_mutopia_full_aug.pkl"
+    shutil.copy(PKL, pf)
+    run_eval.main(["--model", "mutopia_ccal_cont_rsz", "--data", "mutopia", "--n_test", "40", "--param_file", str(pf),
+                   "--dump_results", "--V2_to_V1", "--max_dim", "16"])
+    res = yaml.safe_load(open(tmp_path / "eval_all_split_mutopia_full_aug_A2S.yaml"))
+    assert set(res) == {"map", "med_rank", "recall_at_k"} and set(res["recall_at_k"]) == {"1", "5", "10", "25"}
+
+
+def test_refine_cca_roundtrip(tmp_path):
+    """refine_cca: pickle in -> pickle out, entries 90-93 replaced, fit equals the oracle's fit on
+    the same latents, invariants hold on the library's own latents."""
+    from audio_sheet_retrieval_b200 import network, refine_cca
+    from audio_sheet_retrieval_b200.params import load_params
+    out = tmp_path / "out" / "params.pkl"
+    refine_cca.main(["--model", "mutopia_ccal_cont_rsz", "--data", "mutopia", "--n_train", "400", "--param_file", PKL,
+                     "--out_file", str(out)])
+    old, new = load_params(PKL), load_params(str(out))
+    assert len(new) == 97
+    for i in range(97):
+        same = (old[i] == new[i]).all()
+        assert same == (i not in (90, 91, 92, 93)), i
+    # oracle fit on the library's latents
+    from audio_sheet_retrieval_b200.models import mutopia_ccal_cont_rsz as model
+    from audio_sheet_retrieval_b200.utils.mutopia_data import SyntheticPairPool
+    layers = model.build_model(False)
+    network.set_all_param_values(layers, old)
+    net = layers[0].net
+    X1, X2 = SyntheticPairPool(25000, seed=23)[0:400]
+    l1 = net.encoder(1, model.prepare.asr_prepare_mode).embed_host(X1, want="latents")
+    l2 = net.encoder(2, 0).embed_host(X2, want="latents")
+    o = occa.CCA()
+    sig = o.fit(l1, l2)
+    U, V = new[90].astype(np.float64), new[91].astype(np.float64)
+    np.testing.assert_allclose(new[92], o.m1, atol=1e-6)
+    np.testing.assert_allclose(np.abs(np.diag(U.T @ o.S12 @ V)), sig, atol=5e-4)
+    np.testing.assert_allclose(U.T @ o.S11 @ U, np.eye(32), atol=5e-3)
+
+
+def test_detect_score_end_to_end():
+    """detect_score on a synthetic recording whose windows were put into the DB: the true piece wins."""
+    from audio_sheet_retrieval_b200.audio_sheet_server import AudioSheetServer
+    from audio_sheet_retrieval_b200.models import mutopia_ccal_cont_rsz as model
+    rng = np.random.RandomState(0)
+    srv = AudioSheetServer()
+    srv.initialize_embedding_network(model, PKL)
+    specs = [np.abs(rng.normal(0, 0.3, (92, 300))).astype(np.float32) * (rng.rand(92, 1) > 0.7) for _ in range(4)]
+    codes, ids = [], []
+    for pid, sp in enumerate(specs):
+        ex = np.stack([sp[None, :, s:s + 42] for s in range(0, 300 - 42, 5)])
+        codes.append(srv.embed_network.compute_view_2(ex))
+        ids += [pid] * len(ex)
+    # audio -> audio DB: identify recording 2 from its own spectrogram
+    srv.set_sheet_db(np.concatenate(codes), np.array(ids), dict((i, "rec%d" % i) for i in range(4)))
+    names, votes = srv.detect_score(specs[2], top_k=3, n_candidates=5)
+    assert names[0] == "rec2" and votes[0] > 0.5 and abs(votes.sum() - 1.0) < 1e-12
