@@ -52,6 +52,9 @@ def _load():
     lib.asr_encoder_embed_host.argtypes = [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int]
     lib.asr_encoder_debug_activation.argtypes = [c_void_p, c_int, c_int, c_int64, c_void_p,
                                                  POINTER(c_int), POINTER(c_int), POINTER(c_int)]
+    lib.asr_encoder_set_timing.argtypes = [c_void_p, c_int]
+    lib.asr_encoder_get_timing.argtypes = [c_void_p, POINTER(c_double), POINTER(c_double), POINTER(c_double),
+                                           POINTER(c_int64)]
     lib.asr_encoder_flops_per_sample.argtypes = [c_void_p]
     lib.asr_encoder_flops_per_sample.restype = c_double
     lib.asr_db_create.argtypes = [POINTER(c_void_p), c_void_p, c_int64, c_int64]
@@ -65,7 +68,8 @@ def _load():
     lib.asr_cca_solve.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_double, c_double, c_double, c_int,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     for name in ("asr_encoder_create", "asr_encoder_destroy", "asr_encoder_set_cca", "asr_encoder_embed",
-                 "asr_encoder_embed_host", "asr_encoder_debug_activation", "asr_db_create", "asr_db_destroy",
+                 "asr_encoder_embed_host", "asr_encoder_debug_activation", "asr_encoder_set_timing",
+                 "asr_encoder_get_timing", "asr_db_create", "asr_db_destroy",
                  "asr_topk", "asr_topk_merge", "asr_rank_of_target", "asr_vote", "asr_cca_accumulate",
                  "asr_cca_solve"):
         getattr(lib, name).restype = c_int

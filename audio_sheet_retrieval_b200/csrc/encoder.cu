@@ -462,6 +462,10 @@ struct asr_encoder {
     float *ref_w[8] = {nullptr}, *ref_bn[8] = {nullptr};
     float *ref_in = nullptr, *ref_act[8] = {nullptr}, *ref_tmp = nullptr;
     int last_path = -1;
+    // optional per-group device timing (bench.py roofline): events around [layer 0], [layers 1..7], [head]
+    bool timing = false;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
     // host-buffer entry
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
@@ -513,6 +517,16 @@ static bool plan_conv(const LayerGeom &g, ConvPlan &pl) {
 
 static int pad16(int c) { return (c + 15) / 16 * 16; }
 
+static void mark(asr_encoder *e, cudaStream_t st) {
+    if (!e->timing) return;
+    if (e->ev_used == e->ev_pool.size()) {
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        e->ev_pool.push_back(ev);
+    }
+    cudaEventRecord(e->ev_pool[e->ev_used++], st);
+}
+
 extern "C" {
 
 int asr_encoder_destroy(asr_encoder_t *e) {
@@ -529,6 +543,7 @@ int asr_encoder_destroy(asr_encoder_t *e) {
         if (e->ev_done[b]) cudaEventDestroy(e->ev_done[b]);
     }
     cudaFree(e->dev_codes); cudaFree(e->dev_lat);
+    for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     if (e->s_copy) cudaStreamDestroy(e->s_copy);
     if (e->s_comp) cudaStreamDestroy(e->s_comp);
     delete e;
@@ -701,6 +716,7 @@ int asr_encoder_embed(asr_encoder_t *e, const void *x_dev, int x_dtype, int64_t 
     hp.codes = codes_dev; hp.latents = latents_dev;
     e->last_path = path;
     if (path == ASR_PATH_TCGEN05) {
+        mark(e, st);
         {
             const LayerGeom &g = e->g[0];
             L0Params p;
@@ -712,6 +728,7 @@ int asr_encoder_embed(asr_encoder_t *e, const void *x_dev, int x_dtype, int64_t 
             l0_conv_kernel<<<grid, 256, 0, st>>>(p);
             ASR_LAUNCH_CHECK();
         }
+        mark(e, st);
         for (int l = 1; l < 8; ++l) {
             const LayerGeom &g = e->g[l];
             const ConvPlan &pl = e->plan[l];
@@ -730,6 +747,7 @@ int asr_encoder_embed(asr_encoder_t *e, const void *x_dev, int x_dtype, int64_t 
             conv3x3_tc_kernel<<<grid, CONV_THREADS, pl.smem_bytes, st>>>(p);
             ASR_LAUNCH_CHECK();
         }
+        mark(e, st);
         hp.in = e->act[7]; hp.is_p8 = 1; hp.plane = e->act_plane[7]; hp.sample = e->act_sample[7];
     } else {
         rc = ensure_ref_buffers(e);
@@ -758,6 +776,34 @@ int asr_encoder_embed(asr_encoder_t *e, const void *x_dev, int x_dtype, int64_t 
     }
     head_kernel<<<(unsigned)n, 128, 0, st>>>(hp);
     ASR_LAUNCH_CHECK();
+    if (path == ASR_PATH_TCGEN05) mark(e, st);
+    return ASR_OK;
+}
+
+int asr_encoder_set_timing(asr_encoder_t *e, int enable) {
+    ASR_CHECK_ARG(e != nullptr, "NULL handle");
+    e->timing = enable != 0;
+    e->ev_used = 0;
+    return ASR_OK;
+}
+
+int asr_encoder_get_timing(asr_encoder_t *e, double *ms_layer0, double *ms_conv_tc, double *ms_head, int64_t *n_calls) {
+    ASR_CHECK_ARG(e != nullptr, "NULL handle");
+    double a = 0, b = 0, c = 0;
+    const size_t calls = e->ev_used / 4;
+    if (calls) ASR_CUDA(cudaEventSynchronize(e->ev_pool[e->ev_used - 1]));
+    for (size_t i = 0; i < calls; ++i) {
+        float t0 = 0, t1 = 0, t2 = 0;
+        ASR_CUDA(cudaEventElapsedTime(&t0, e->ev_pool[4 * i], e->ev_pool[4 * i + 1]));
+        ASR_CUDA(cudaEventElapsedTime(&t1, e->ev_pool[4 * i + 1], e->ev_pool[4 * i + 2]));
+        ASR_CUDA(cudaEventElapsedTime(&t2, e->ev_pool[4 * i + 2], e->ev_pool[4 * i + 3]));
+        a += t0; b += t1; c += t2;
+    }
+    if (ms_layer0) *ms_layer0 = a;
+    if (ms_conv_tc) *ms_conv_tc = b;
+    if (ms_head) *ms_head = c;
+    if (n_calls) *n_calls = (int64_t)calls;
+    e->ev_used = 0;
     return ASR_OK;
 }
 

@@ -146,6 +146,16 @@ class Encoder(object):
                                               _lib.dptr(latents), path, _lib.stream_ptr(stream)))
         return codes, latents
 
+    def set_timing(self, enable):
+        _lib.check(_lib.lib.asr_encoder_set_timing(self.handle, int(bool(enable))))
+
+    def get_timing(self):
+        """-> dict(ms_layer0, ms_conv_tc, ms_head, calls) summed since the last call."""
+        a, b, c, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+        _lib.check(_lib.lib.asr_encoder_get_timing(self.handle, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c),
+                                                   ctypes.byref(n)))
+        return dict(ms_layer0=a.value, ms_conv_tc=b.value, ms_head=c.value, calls=n.value)
+
     def debug_activation(self, layer, n, path=_lib.PATH_TCGEN05):
         c, h, w = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         _lib.check(_lib.lib.asr_encoder_debug_activation(self.handle, layer, path, n, None, ctypes.byref(c),

@@ -97,6 +97,11 @@ int asr_encoder_embed_host(asr_encoder_t *enc, const void *x_host, int x_dtype, 
  * NCHW float32 (n, c, h, w); returns c,h,w through the out params. */
 int asr_encoder_debug_activation(asr_encoder_t *enc, int layer, int path, int64_t n, float *out_host,
                                  int *c, int *h, int *w);
+/* Device timing for the roofline report: when enabled, every asr_encoder_embed on the tcgen05 path
+ * records CUDA events on its stream around [layer 0] [layers 1..7 = the tcgen05 kernel] [head];
+ * get_timing synchronises on the last event, returns the summed milliseconds and resets. */
+int asr_encoder_set_timing(asr_encoder_t *enc, int enable);
+int asr_encoder_get_timing(asr_encoder_t *enc, double *ms_layer0, double *ms_conv_tc, double *ms_head, int64_t *n_calls);
 /* algorithmic FLOPs per sample of this branch (2*MACs of the nine convolutions) */
 double asr_encoder_flops_per_sample(const asr_encoder_t *enc);
 
