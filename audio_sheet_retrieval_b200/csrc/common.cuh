@@ -111,6 +111,16 @@ __device__ __forceinline__ void tma_prefetch_desc(const void *tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
 
+__device__ __forceinline__ bool elect_one() {   // one lane of a fully converged warp
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- tcgen05 / TMEM ----
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {  // whole warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
@@ -137,6 +147,30 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, ui
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Same, predicated on `leader` (non-zero in exactly one lane): lets a fully converged warp run the
+// issue loop with warp-uniform operands.  Descriptors are passed as their low words; the high
+// word (SBO = 128 B, version 1, no swizzle) is the constant UMMA_DESC_HI.
+constexpr uint32_t UMMA_DESC_HI = (128u >> 4) | (1u << 14);
+__device__ __forceinline__ void tc_mma_bf16_pred(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                                 uint32_t idesc, uint32_t accumulate, uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "setp.ne.b32 q, %6, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_pred(uint64_t *bar, uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(leader)
         : "memory");
 }
 // 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread (thread = lane = row)
@@ -170,7 +204,18 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-__device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : (__expf(x) - 1.0f); }
+// ELU with the raw MUFU.EX2 (ex2.approx.ftz): 2^(x*log2e) - 1 for x <= 0.  Without -use_fast_math
+// __expf expands to a denormal-safe sequence of ~9 predicated instructions per value; flushing
+// to zero is exact enough here (exp(x) < 2^-126 => elu = -1).
+__device__ __forceinline__ float ex2_approx(float t) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+    return e;
+}
+__device__ __forceinline__ float elu_f(float x) {
+    const float e = ex2_approx(x * 1.4426950408889634f);
+    return x > 0.f ? x : (e - 1.0f);
+}
 
 #endif  // __CUDACC__
 }  // namespace asr

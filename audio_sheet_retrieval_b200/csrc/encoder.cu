@@ -27,6 +27,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -62,10 +63,14 @@ struct ConvParams {
     long long in_plane, in_sample, out_plane, out_sample;   // bytes
     int sps, stage_bytes, n_stages, slot_cols, n_slots, tmem_cols, wbytes;
     int off_bias, off_stage, off_staging, off_bar;
+    unsigned wp_magic;   // ceil(2^32 / Wp): o / Wp == __umulhi(o, wp_magic) for every o the kernel sees
 };
 
-constexpr int CONV_THREADS = 320;        // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr int EPI_THREADS = 256;
+constexpr int N_MMA_WARPS = 4;           // tile tc is issued by MMA warp (tc & 3) and drained by epilogue group (tc & 3)
+constexpr int N_EPI_GROUPS = 4;
+constexpr int EPI_WARP0 = 1 + N_MMA_WARPS;
+constexpr int EPI_THREADS = N_EPI_GROUPS * 128;
+constexpr int CONV_THREADS = 32 * EPI_WARP0 + EPI_THREADS;   // warp 0 TMA, warps 1..4 MMA, warps 5..20 epilogue
 constexpr int TAIL_SLACK = 2080;
 constexpr int MAX_SLOTS = 8;
 constexpr int SMEM_LIMIT = 227 * 1024;
@@ -73,6 +78,7 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 // --------------------------------------------------------------------------------------
 // tcgen05 implicit-GEMM convolution (layers 1..7)
 // --------------------------------------------------------------------------------------
+template <int KPAIRS>
 __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(const ConvParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -90,7 +96,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(const ConvP
 
     if (tid == 0) {
         mbar_init(w_full, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&in_full[s], 1); mbar_init(&in_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&in_full[s], 1); mbar_init(&in_empty[s], N_MMA_WARPS); }
         for (int s = 0; s < MAX_SLOTS; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
         mbar_fence_init();
     }
@@ -127,64 +133,72 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(const ConvP
                     tma_bulk_g2s(dst + (size_t)kc * p.sps, src + (long long)kc * p.in_plane, bytes, &in_full[s]);
             }
         }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(p.NP);
-            const uint32_t w_addr = smem_u32(w_sm);
-            const uint32_t b_lbo = (uint32_t)(p.NP * 16);
-            mbar_wait(w_full, 0);
-            int it = 0;
-            uint32_t tc = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-                const int s = it % p.n_stages;
-                const uint32_t ph = (uint32_t)((it / p.n_stages) & 1);
-                mbar_wait(&in_full[s], ph);
+    } else if (warp < EPI_WARP0) {
+        // ================= MMA issuers (4 warps, tile tc belongs to warp tc & 3) =================
+        const uint32_t my = (uint32_t)(warp - 1);
+        // The whole warp walks the (uniform, fully unrolled) issue sequence so that descriptors live in
+        // uniform registers; the tcgen05 instructions themselves are predicated on one elected lane.
+        // Descriptors advance by adding to their low word (start-address field, 16-byte units).
+        const uint32_t leader = elect_one() ? 1u : 0u;
+        const uint32_t idesc = umma_idesc_bf16(p.NP);
+        const uint32_t a_lbo = ((uint32_t)p.sps >> 4) << 16;                   // LBO = smem plane stride
+        const uint32_t w_lo = ((smem_u32(w_sm) & 0x3FFFFu) >> 4) | ((uint32_t)p.NP << 16);   // LBO = NP*16 B
+        const uint32_t kstep_a = (uint32_t)(2 * p.sps) >> 4;
+        const uint32_t kstep_b = (uint32_t)(2 * p.NP);
+        const uint32_t slot_mask = (uint32_t)p.n_slots - 1u;                   // n_slots is a power of two
+        const uint32_t slot_shift = (uint32_t)__ffs(p.n_slots) - 1u;
+        const uint32_t wp = (uint32_t)p.Wp;
+        mbar_wait(w_full, 0);
+        int it = 0;
+        uint32_t tc = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const int s = it % p.n_stages;
+            const uint32_t ph = (uint32_t)((it / p.n_stages) & 1);
+            mbar_wait(&in_full[s], ph);
+            tc_fence_after();
+            // descriptor of padded position -1 of the band (tap dy=-1, dx=-1 of output position 0)
+            uint32_t tile_lo = (((smem_u32(stage_sm + (size_t)s * p.stage_bytes + 16) & 0x3FFFFu) >> 4) | a_lbo) - 1u;
+            for (int mt = 0; mt < p.MT; ++mt, ++tc, tile_lo += 128u) {
+                if ((tc & (uint32_t)(N_MMA_WARPS - 1)) != my) continue;
+                const uint32_t slot = tc & slot_mask;
+                const uint32_t sph = (tc >> slot_shift) & 1u;
+                mbar_wait(&acc_empty[slot], sph ^ 1u);
                 tc_fence_after();
-                const uint32_t tile_addr = smem_u32(stage_sm + (size_t)s * p.stage_bytes + 16);
-                for (int mt = 0; mt < p.MT; ++mt, ++tc) {
-                    const uint32_t slot = tc % (uint32_t)p.n_slots;
-                    const uint32_t sph = (tc / (uint32_t)p.n_slots) & 1u;
-                    mbar_wait(&acc_empty[slot], sph ^ 1u);
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + slot * (uint32_t)p.slot_cols;
-                    uint32_t acc = 0;
-#pragma unroll 1
-                    for (int t = 0; t < 9; ++t) {
-                        const int dy = t / 3 - 1, dx = t % 3 - 1;
-                        const uint32_t a0 = tile_addr + (uint32_t)((mt * 128 + (1 + dy) * p.Wp + dx) * 16);
-                        const uint32_t b0 = w_addr + (uint32_t)(t * p.KC * p.NP * 16);
-                        for (int kp = 0; kp < p.KC / 2; ++kp) {
-                            const uint64_t ad = umma_desc(a0 + (uint32_t)(2 * kp * p.sps), (uint32_t)p.sps, 128u);
-                            const uint64_t bd = umma_desc(b0 + (uint32_t)(2 * kp) * b_lbo, b_lbo, 128u);
-                            tc_mma_bf16(d_tmem, ad, bd, idesc, acc);
-                            acc = 1;
-                        }
+                const uint32_t d_tmem = tmem_base + slot * (uint32_t)p.slot_cols;
+                uint32_t b_lo = w_lo;
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    uint32_t a_lo = tile_lo + (uint32_t)(t / 3) * wp + (uint32_t)(t % 3);
+#pragma unroll
+                    for (int kp = 0; kp < KPAIRS; ++kp) {
+                        tc_mma_bf16_pred(d_tmem, a_lo, b_lo, UMMA_DESC_HI, idesc, (t | kp) != 0 ? 1u : 0u, leader);
+                        a_lo += kstep_a;
+                        b_lo += kstep_b;
                     }
-                    tc_commit(&acc_full[slot]);
                 }
-                tc_commit(&in_empty[s]);
+                tc_commit_pred(&acc_full[slot], leader);
             }
+            tc_commit_pred(&in_empty[s], leader);
         }
     } else {
         // ================= epilogue: TMEM -> bias + ELU -> bf16 -> (pool) -> global =================
-        const int ew = warp - 2;                 // 0..7
-        const int grp = ew >> 2;                 // tiles alternate between the two groups
+        const int ew = warp - EPI_WARP0;         // 0..15
+        const uint32_t grp = (uint32_t)(ew >> 2); // tile tc is drained by group tc & 3
         const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-        const int etid = tid - 64;               // 0..255
+        const int etid = tid - 32 * EPI_WARP0;   // 0..511
         mbar_wait(w_full, 0);                    // bias visible
         uint32_t tc = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int n = item / p.bands, y0 = (item % p.bands) * p.TH;
             uint8_t *out_n = reinterpret_cast<uint8_t *>(p.out) + (long long)n * p.out_sample;
             for (int mt = 0; mt < p.MT; ++mt, ++tc) {
-                if ((int)(tc & 1u) != grp) continue;
-                const uint32_t slot = tc % (uint32_t)p.n_slots;
-                const uint32_t sph = (tc / (uint32_t)p.n_slots) & 1u;
+                if ((tc & (uint32_t)(N_EPI_GROUPS - 1)) != grp) continue;
+                const uint32_t slot = tc & ((uint32_t)p.n_slots - 1u);
+                const uint32_t sph = (tc >> ((uint32_t)__ffs(p.n_slots) - 1u)) & 1u;
                 mbar_wait(&acc_full[slot], sph);
                 tc_fence_after();
                 const int o = mt * 128 + quarter * 32 + lane;       // padded raster position in the band
-                const int r = o / p.Wp, c = o - r * p.Wp;
+                const int r = (int)__umulhi((unsigned)o, p.wp_magic), c = o - r * p.Wp;
                 const int y = y0 + r;
                 const bool in_band = r < p.TH;
                 const bool valid = in_band && c >= 1 && c <= p.W && y < p.H;
@@ -194,11 +208,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(const ConvP
                     tmem_ld16(taddr + (uint32_t)(ng * 16), v);
                     uint32_t pk[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float a = elu_f(v[2 * j] + bias_sm[ng * 16 + 2 * j]);
-                        float b = elu_f(v[2 * j + 1] + bias_sm[ng * 16 + 2 * j + 1]);
-                        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-                        pk[j] = *reinterpret_cast<uint32_t *>(&h);
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 b4 = *reinterpret_cast<const float4 *>(&bias_sm[ng * 16 + 4 * j]);
+                        __nv_bfloat162 h0 = __floats2bfloat162_rn(elu_f(v[4 * j] + b4.x), elu_f(v[4 * j + 1] + b4.y));
+                        __nv_bfloat162 h1 = __floats2bfloat162_rn(elu_f(v[4 * j + 2] + b4.z), elu_f(v[4 * j + 3] + b4.w));
+                        pk[2 * j] = *reinterpret_cast<uint32_t *>(&h0);
+                        pk[2 * j + 1] = *reinterpret_cast<uint32_t *>(&h1);
                     }
                     if (p.pool) {
                         if (in_band) {
@@ -353,30 +368,58 @@ struct HeadParams {
 __global__ void __launch_bounds__(128) head_kernel(const HeadParams p) {
     __shared__ float m[128];
     __shared__ float lat[32];
-    const int n = blockIdx.x, tid = threadIdx.x;
+    const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float inv = 1.0f / (float)(p.H * p.W);
-    for (int c = tid; c < p.C; c += blockDim.x) {
-        float s = 0.f;
-        if (p.is_p8) {
-            const uint8_t *base = reinterpret_cast<const uint8_t *>(p.in) + (long long)n * p.sample +
-                                  (long long)(c >> 3) * p.plane + (c & 7) * 2;
-            for (int y = 0; y < p.H; ++y)
-                for (int x = 0; x < p.W; ++x)
-                    s += __bfloat162float(*reinterpret_cast<const bf16 *>(base + ((long long)(y + 1) * p.Wp + x + 1) * 16));
-        } else {
+    if (p.is_p8) {
+        // warp w sums channel chunks w, w+4, ...: lanes stride over positions with 16-byte loads
+        const int n_chunks = (p.C + 7) >> 3;
+        const int npos = p.H * p.W;
+        for (int ch = warp; ch < n_chunks; ch += 4) {
+            const uint8_t *base = reinterpret_cast<const uint8_t *>(p.in) + (long long)n * p.sample + (long long)ch * p.plane;
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+            for (int i = lane; i < npos; i += 32) {
+                const int y = i / p.W, x = i - y * p.W;
+                const uint4 v = *reinterpret_cast<const uint4 *>(base + ((long long)(y + 1) * p.Wp + x + 1) * 16);
+                const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w4[j]));
+                    acc[2 * j] += f.x;
+                    acc[2 * j + 1] += f.y;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float s = acc[j];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == 0 && ch * 8 + j < p.C) m[ch * 8 + j] = s * inv;
+            }
+        }
+    } else {
+        for (int c = tid; c < p.C; c += blockDim.x) {
             const float *base = reinterpret_cast<const float *>(reinterpret_cast<const uint8_t *>(p.in) +
                                                                 (long long)n * p.sample + (long long)c * p.plane);
+            float s = 0.f;
             for (int i = 0; i < p.H * p.W; ++i) s += base[i];
+            m[c] = s * inv;
         }
-        m[c] = s * inv;
     }
     __syncthreads();
-    if (tid < 32) {
+    // latent_j = sum_c A[j][c] m[c] + b[j]: four lanes per output, then a 4-lane reduce
+    {
+        const int j = tid >> 2, part = tid & 3;
         float s = 0.f;
-        for (int c = 0; c < p.C; ++c) s = fmaf(p.A[tid * p.C + c], m[c], s);
-        s += p.A[32 * p.C + tid];
-        lat[tid] = s;
-        if (p.latents) p.latents[(size_t)n * 32 + tid] = s;
+        for (int c = part; c < p.C; c += 4) s = fmaf(p.A[j * p.C + c], m[c], s);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (part == 0) {
+            s += p.A[32 * p.C + j];
+            lat[j] = s;
+            if (p.latents) p.latents[(size_t)n * 32 + j] = s;
+        }
     }
     __syncthreads();
     if (tid < 32 && p.codes) {
@@ -584,6 +627,8 @@ int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *d, int max_b
         H = g.Ho; W = g.Wo; cin = g.cout;
         if (H < 1 || W < 1) { delete e; set_error("input too small for four 2x2 pools"); return ASR_ERR_ARG; }
         ASR_CHECK_ARG(g.coutp <= 128, "at most 128 channels per layer");
+        ASR_CHECK_ARG(l == 0 || g.cinp == 16 || g.cinp == 32 || g.cinp == 48 || g.cinp == 64 || g.cinp == 96 || g.cinp == 128,
+                      "input channels must pad to 16, 32, 48, 64, 96 or 128");
     }
     e->head_c = cin; e->head_h = H; e->head_w = W;
     e->flops += 2.0 * cin * 32 * H * W;
@@ -638,6 +683,13 @@ int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *d, int max_b
                 asr_encoder_destroy(e);
                 return ASR_ERR_UNSUPPORTED;
             }
+            if (getenv("ASR_DEBUG_PLAN")) {
+                const ConvPlan &pl = e->plan[l];
+                fprintf(stderr, "[asr] layer %d: %dx%d cin %d->%d (pad %d->%d) pool %d | TH %d bands %d MT %d stages %d slots %d x %d cols "
+                        "smem %d B (w %d, stage %d, staging %d)\n", l, g.H, g.W, g.cin, g.cout, g.cinp, g.coutp, g.pool, pl.TH,
+                        pl.bands, pl.MT, pl.n_stages, pl.n_slots, pl.slot_cols, pl.smem_bytes, pl.wbytes, pl.stage_bytes,
+                        pl.staging_bytes);
+            }
             const int KC = g.cinp / 8, NP = g.coutp;
             std::vector<uint8_t> blob((size_t)9 * KC * NP * 16 + NP * 4, 0);
             bf16 *wb = reinterpret_cast<bf16 *>(blob.data());
@@ -675,7 +727,12 @@ int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *d, int max_b
     }
     static bool attr_done = false;
     if (!attr_done) {
-        E_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        E_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        E_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        E_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        E_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        E_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        E_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         attr_done = true;
     }
 #undef E_CUDA
@@ -742,9 +799,23 @@ int asr_encoder_embed(asr_encoder_t *e, const void *x_dev, int x_dtype, int64_t 
             p.sps = pl.sps; p.stage_bytes = pl.stage_bytes; p.n_stages = pl.n_stages; p.slot_cols = pl.slot_cols;
             p.n_slots = pl.n_slots; p.tmem_cols = pl.tmem_cols; p.wbytes = pl.wbytes;
             p.off_bias = pl.off_bias; p.off_stage = pl.off_stage; p.off_staging = pl.off_staging; p.off_bar = pl.off_bar;
+            p.wp_magic = (unsigned)((0x100000000ull + (unsigned)p.Wp - 1) / (unsigned)p.Wp);
+            for (unsigned o = 0; o < (unsigned)pl.MT * 128u; ++o)
+                if ((unsigned)(((unsigned long long)o * p.wp_magic) >> 32) != o / (unsigned)p.Wp) {
+                    set_error("asr_encoder_embed: internal error (fast division)");
+                    return ASR_ERR_UNSUPPORTED;
+                }
             const int items = (int)n * pl.bands;
             const int grid = std::min(items, sm_count());
-            conv3x3_tc_kernel<<<grid, CONV_THREADS, pl.smem_bytes, st>>>(p);
+            switch (p.KC / 2) {
+                case 1: conv3x3_tc_kernel<1><<<grid, CONV_THREADS, pl.smem_bytes, st>>>(p); break;
+                case 2: conv3x3_tc_kernel<2><<<grid, CONV_THREADS, pl.smem_bytes, st>>>(p); break;
+                case 3: conv3x3_tc_kernel<3><<<grid, CONV_THREADS, pl.smem_bytes, st>>>(p); break;
+                case 4: conv3x3_tc_kernel<4><<<grid, CONV_THREADS, pl.smem_bytes, st>>>(p); break;
+                case 6: conv3x3_tc_kernel<6><<<grid, CONV_THREADS, pl.smem_bytes, st>>>(p); break;
+                case 8: conv3x3_tc_kernel<8><<<grid, CONV_THREADS, pl.smem_bytes, st>>>(p); break;
+                default: set_error("asr_encoder_embed: unsupported input channel count"); return ASR_ERR_UNSUPPORTED;
+            }
             ASR_LAUNCH_CHECK();
         }
         mark(e, st);

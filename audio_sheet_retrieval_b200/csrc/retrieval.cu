@@ -24,27 +24,30 @@ namespace asr {
 
 constexpr int TK_THREADS = 256;
 constexpr int TK_ROWS = 256;                 // DB rows per stage = 32 KB
-constexpr int TK_STAGES = 3;
-constexpr int TK_QT = 16;                    // queries per pass
 constexpr int TK_QCAP = 512;                 // candidate queue entries per query
 constexpr int TK_STAGE_BYTES = TK_ROWS * 128;
 constexpr size_t TK_SCRATCH_BYTES = 64u << 20;
+constexpr int TK_QT_MAX = 16;
+constexpr int TK_STAGES = 3;                 // used by the rank kernel
 
+// Per query-tile state.  QT queries are scored per pass over the DB slice; the smaller
+// instantiations fit several CTAs per SM (the Q = 1 streaming case is latency-bound per warp:
+// the pinned summation order is one dependent chain per row, so occupancy hides it).
+template <int QT, int STAGES>
 struct TkSmem {
-    // stage buffers must be 1024-byte aligned for SWIZZLE_128B
-    float stage[TK_STAGES][TK_ROWS * 32];
-    float q[TK_QT][32];
-    float qs[TK_QT][TK_QCAP];                // candidate queue: score
-    uint32_t qi[TK_QT][TK_QCAP];             //                  local row
-    float ls[2][TK_QT][ASR_MAX_K];           // sorted lists (double buffered for the rank merge)
-    uint32_t li[2][TK_QT][ASR_MAX_K];
-    int qcount[TK_QT];
-    int llen[TK_QT];
-    int lbuf[TK_QT];
-    float thr_s[TK_QT];
-    uint32_t thr_i[TK_QT];
-    uint64_t full[TK_STAGES];
-    int flush_flag;
+    float stage[STAGES][TK_ROWS * 32];       // 1024-byte aligned (SWIZZLE_128B)
+    float q[QT][32];
+    float qs[QT][TK_QCAP];                   // candidate queue: score
+    uint32_t qi[QT][TK_QCAP];                //                  local row
+    float ls[2][QT][ASR_MAX_K];              // sorted lists (double buffered for the rank merge)
+    uint32_t li[2][QT][ASR_MAX_K];
+    int qcount[QT];
+    int llen[QT];
+    int lbuf[QT];
+    float thr_s[QT];
+    uint32_t thr_i[QT];
+    uint64_t full[STAGES];
+    int flush_flag[3];
 };
 
 __device__ __forceinline__ bool beats(float sa, uint32_t ia, float sb, uint32_t ib) {
@@ -66,63 +69,77 @@ __device__ __forceinline__ float score32(const float *q, const float *d) {
     for (int k = 0; k < 32; ++k) acc = __fadd_rn(acc, __fmul_rn(q[k], d[k]));
     return (acc != acc) ? -CUDART_INF_F : acc;
 }
+// four queries at once: four independent dependent-add chains give the scheduler ILP
+__device__ __forceinline__ void score32x4(const float (*q)[32], const float *d, float *out) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) {
+        const float4 q0 = *reinterpret_cast<const float4 *>(&q[0][4 * kb]);
+        const float4 q1 = *reinterpret_cast<const float4 *>(&q[1][4 * kb]);
+        const float4 q2 = *reinterpret_cast<const float4 *>(&q[2][4 * kb]);
+        const float4 q3 = *reinterpret_cast<const float4 *>(&q[3][4 * kb]);
+        const float d0 = d[4 * kb], d1 = d[4 * kb + 1], d2 = d[4 * kb + 2], d3 = d[4 * kb + 3];
+        a0 = __fadd_rn(a0, __fmul_rn(q0.x, d0)); a1 = __fadd_rn(a1, __fmul_rn(q1.x, d0));
+        a2 = __fadd_rn(a2, __fmul_rn(q2.x, d0)); a3 = __fadd_rn(a3, __fmul_rn(q3.x, d0));
+        a0 = __fadd_rn(a0, __fmul_rn(q0.y, d1)); a1 = __fadd_rn(a1, __fmul_rn(q1.y, d1));
+        a2 = __fadd_rn(a2, __fmul_rn(q2.y, d1)); a3 = __fadd_rn(a3, __fmul_rn(q3.y, d1));
+        a0 = __fadd_rn(a0, __fmul_rn(q0.z, d2)); a1 = __fadd_rn(a1, __fmul_rn(q1.z, d2));
+        a2 = __fadd_rn(a2, __fmul_rn(q2.z, d2)); a3 = __fadd_rn(a3, __fmul_rn(q3.z, d2));
+        a0 = __fadd_rn(a0, __fmul_rn(q0.w, d3)); a1 = __fadd_rn(a1, __fmul_rn(q1.w, d3));
+        a2 = __fadd_rn(a2, __fmul_rn(q2.w, d3)); a3 = __fadd_rn(a3, __fmul_rn(q3.w, d3));
+    }
+    out[0] = (a0 != a0) ? -CUDART_INF_F : a0;
+    out[1] = (a1 != a1) ? -CUDART_INF_F : a1;
+    out[2] = (a2 != a2) ? -CUDART_INF_F : a2;
+    out[3] = (a3 != a3) ? -CUDART_INF_F : a3;
+}
 
-// One warp merges up to 32 candidates (one per lane; dead lanes carry alive=false) into
-// query q's sorted list by rank counting: final position = number of elements that beat you.
-// List entries are held in registers (ceil(len/32) rounds) so every shuffle is warp-uniform.
-__device__ void warp_merge_batch_uniform(TkSmem &sm, int q, int k, float cs, uint32_t ci, bool alive, int lane) {
-    const int len = sm.llen[q];
-    const int cur = sm.lbuf[q];
-    const float *ls = sm.ls[cur][q];
-    const uint32_t *li = sm.li[cur][q];
-    float *ns = sm.ls[cur ^ 1][q];
-    uint32_t *ni = sm.li[cur ^ 1][q];
-    const unsigned alive_mask = __ballot_sync(0xffffffffu, alive);
-    if (alive_mask == 0u) return;
+// One warp merges up to 32 candidates (one per lane; dead lanes carry alive=false) into a sorted
+// list by rank counting: final position = number of elements that beat you.  List entries are
+// held in registers (ceil(len/32) rounds) so every shuffle is warp-uniform.  I = index type.
+template <typename I>
+__device__ __forceinline__ bool beats_t(float sa, I ia, float sb, I ib) {
+    return (sa > sb) || (sa == sb && ia < ib);
+}
+template <typename I>
+__device__ void warp_merge_batch(const float *ls, const I *li, float *ns, I *ni, int len, int k, float cs, I ci,
+                                 bool alive, unsigned alive_mask, I sentinel, int lane) {
     int pos = 0;
-    for (int j = 0; j < len; ++j) pos += beats(ls[j], li[j], cs, ci) ? 1 : 0;   // broadcast reads
-    const int rounds = (len + 31) >> 5;
+    for (int j = 0; j < len; ++j) pos += beats_t<I>(ls[j], li[j], cs, ci) ? 1 : 0;   // broadcast reads
     float es[ASR_MAX_K / 32];
-    uint32_t ei[ASR_MAX_K / 32];
+    I ei[ASR_MAX_K / 32];
     int shift[ASR_MAX_K / 32];
 #pragma unroll
     for (int r = 0; r < ASR_MAX_K / 32; ++r) {
         int j = r * 32 + lane;
-        bool v = r < rounds && j < len;
+        bool v = j < len;
         es[r] = v ? ls[j] : -CUDART_INF_F;
-        ei[r] = v ? li[j] : 0xffffffffu;
+        ei[r] = v ? li[j] : sentinel;
         shift[r] = 0;
     }
     for (int l = 0; l < 32; ++l) {
         if (!((alive_mask >> l) & 1u)) continue;          // warp-uniform
         float os = __shfl_sync(0xffffffffu, cs, l);
-        uint32_t oi = __shfl_sync(0xffffffffu, ci, l);
-        if (l != lane) pos += beats(os, oi, cs, ci) ? 1 : 0;
+        I oi = __shfl_sync(0xffffffffu, ci, l);
+        if (l != lane) pos += beats_t<I>(os, oi, cs, ci) ? 1 : 0;
 #pragma unroll
-        for (int r = 0; r < ASR_MAX_K / 32; ++r) shift[r] += beats(os, oi, es[r], ei[r]) ? 1 : 0;
+        for (int r = 0; r < ASR_MAX_K / 32; ++r) shift[r] += beats_t<I>(os, oi, es[r], ei[r]) ? 1 : 0;
     }
 #pragma unroll
     for (int r = 0; r < ASR_MAX_K / 32; ++r) {
         int j = r * 32 + lane;
-        if (r < rounds && j < len) {
+        if (j < len) {
             int np = j + shift[r];
             if (np < k) { ns[np] = es[r]; ni[np] = ei[r]; }
         }
     }
     if (alive && pos < k) { ns[pos] = cs; ni[pos] = ci; }
     __syncwarp();
-    if (lane == 0) {
-        int nl = len + __popc(alive_mask);
-        nl = nl < k ? nl : k;
-        sm.llen[q] = nl;
-        sm.lbuf[q] = cur ^ 1;
-        if (nl == k) { sm.thr_s[q] = ns[k - 1]; sm.thr_i[q] = ni[k - 1]; }
-    }
-    __syncwarp();
 }
 
 // Drain the candidate queues into the sorted lists.  Warp w owns queries w, w+8, ...
-__device__ void flush_queues(TkSmem &sm, int nq_tile, int k, int warp, int lane) {
+template <int QT, int STAGES>
+__device__ void flush_queues(TkSmem<QT, STAGES> &sm, int nq_tile, int k, int warp, int lane) {
     for (int q = warp; q < nq_tile; q += TK_THREADS / 32) {
         int n = sm.qcount[q];
         n = n < TK_QCAP ? n : TK_QCAP;
@@ -131,20 +148,45 @@ __device__ void flush_queues(TkSmem &sm, int nq_tile, int k, int warp, int lane)
             bool alive = c < n;
             float cs = alive ? sm.qs[q][c] : -CUDART_INF_F;
             uint32_t ci = alive ? sm.qi[q][c] : 0xffffffffu;
-            if (alive && sm.llen[q] == k) alive = beats(cs, ci, sm.thr_s[q], sm.thr_i[q]);
-            warp_merge_batch_uniform(sm, q, k, cs, ci, alive, lane);
+            const int len = sm.llen[q], cur = sm.lbuf[q];
+            if (alive && len == k) alive = beats(cs, ci, sm.thr_s[q], sm.thr_i[q]);
+            const unsigned mask = __ballot_sync(0xffffffffu, alive);
+            if (mask == 0u) continue;
+            warp_merge_batch<uint32_t>(sm.ls[cur][q], sm.li[cur][q], sm.ls[cur ^ 1][q], sm.li[cur ^ 1][q], len, k, cs, ci,
+                                       alive, mask, 0xffffffffu, lane);
+            if (lane == 0) {
+                int nl = len + __popc(mask);
+                nl = nl < k ? nl : k;
+                sm.llen[q] = nl;
+                sm.lbuf[q] = cur ^ 1;
+                if (nl == k) { sm.thr_s[q] = sm.ls[cur ^ 1][q][k - 1]; sm.thr_i[q] = sm.li[cur ^ 1][q][k - 1]; }
+            }
+            __syncwarp();
         }
         __syncwarp();
         if (lane == 0) sm.qcount[q] = 0;
     }
 }
 
+template <int QT, int STAGES>
+__device__ __forceinline__ void push_candidate(TkSmem<QT, STAGES> &sm, int qq, float s, uint32_t row, int k, bool valid,
+                                               int &overflow) {
+    bool pass = valid && (sm.llen[qq] < k || beats(s, row, sm.thr_s[qq], sm.thr_i[qq]));
+    if (pass) {
+        int p = atomicAdd(&sm.qcount[qq], 1);
+        if (p < TK_QCAP) { sm.qs[qq][p] = s; sm.qi[qq][p] = row; }
+        if (p >= TK_QCAP - TK_ROWS) overflow = 1;
+    }
+}
+
 // grid: (n_slices, n_qgroups).  part_s/part_i: (nq, n_slices, k).
-__global__ void __launch_bounds__(TK_THREADS, 1)
+template <int QT, int STAGES, int MINB>
+__global__ void __launch_bounds__(TK_THREADS, MINB)
 topk_stream_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles_per_slice, const float *__restrict__ q,
                    int nq, int k, int normalise, float *__restrict__ part_s, uint32_t *__restrict__ part_i) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    TkSmem &sm = *reinterpret_cast<TkSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    typedef TkSmem<QT, STAGES> Smem;
+    Smem &sm = *reinterpret_cast<Smem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int slice = blockIdx.x, n_slices = gridDim.x;
     const int64_t n_tiles = (n_db + TK_ROWS - 1) / TK_ROWS;
@@ -154,23 +196,23 @@ topk_stream_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int t
     if (my_tiles < 0) my_tiles = 0;
 
     if (tid == 0) {
-        for (int s = 0; s < TK_STAGES; ++s) mbar_init(&sm.full[s], 1);
+        for (int s = 0; s < STAGES; ++s) mbar_init(&sm.full[s], 1);
         mbar_fence_init();
         tma_prefetch_desc(&tmap);
     }
     __syncthreads();
 
-    const int n_qt = (nq + TK_QT - 1) / TK_QT;
+    const int n_qt = (nq + QT - 1) / QT;
     int64_t it_global = 0;   // running tile counter across query tiles (barrier phases continue)
     for (int qt = blockIdx.y; qt < n_qt; qt += gridDim.y) {
-        const int q0 = qt * TK_QT;
-        const int nq_tile = min(TK_QT, nq - q0);
-        // stage the query tile (normalised with the pinned definition)
-        if (tid < nq_tile) {
+        const int q0 = qt * QT;
+        const int nq_tile = min(QT, nq - q0);
+        // stage the query tile (normalised with the pinned definition); unused rows are zero
+        if (tid < QT) {
             float v[32];
 #pragma unroll
-            for (int kk = 0; kk < 32; ++kk) v[kk] = q[(int64_t)(q0 + tid) * 32 + kk];
-            if (normalise) normalise32(v);
+            for (int kk = 0; kk < 32; ++kk) v[kk] = tid < nq_tile ? q[(int64_t)(q0 + tid) * 32 + kk] : 0.f;
+            if (normalise && tid < nq_tile) normalise32(v);
 #pragma unroll
             for (int kk = 0; kk < 32; ++kk) sm.q[tid][kk] = v[kk];
             sm.qcount[tid] = 0;
@@ -180,10 +222,9 @@ topk_stream_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int t
             sm.thr_i[tid] = 0xffffffffu;
         }
         if (tid == 0) {
-            sm.flush_flag = 0;
-            // prologue: fill the ring
-            for (int s = 0; s < TK_STAGES && s < my_tiles; ++s) {
-                int slot = (int)((it_global + s) % TK_STAGES);
+            sm.flush_flag[0] = sm.flush_flag[1] = sm.flush_flag[2] = 0;
+            for (int s = 0; s < STAGES && s < my_tiles; ++s) {     // prologue: fill the ring
+                int slot = (int)((it_global + s) % STAGES);
                 mbar_expect_tx(&sm.full[slot], TK_STAGE_BYTES);
                 tma_load_2d(sm.stage[slot], &tmap, 0, (int)((tile0 + s) * TK_ROWS), &sm.full[slot]);
             }
@@ -191,8 +232,8 @@ topk_stream_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int t
         __syncthreads();
 
         for (int64_t it = 0; it < my_tiles; ++it, ++it_global) {
-            const int slot = (int)(it_global % TK_STAGES);
-            const uint32_t parity = (uint32_t)((it_global / TK_STAGES) & 1);
+            const int slot = (int)(it_global % STAGES);
+            const uint32_t parity = (uint32_t)((it_global / STAGES) & 1);
             mbar_wait(&sm.full[slot], parity);
             // my row: chunk c of row r sits at r*128 + ((c ^ (r & 7)) << 4)   (SWIZZLE_128B)
             float d[32];
@@ -202,33 +243,39 @@ topk_stream_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int t
                 float4 v = rowp[c ^ (tid & 7)];
                 d[4 * c + 0] = v.x; d[4 * c + 1] = v.y; d[4 * c + 2] = v.z; d[4 * c + 3] = v.w;
             }
-            __syncthreads();   // everyone has its row in registers: the slot can be refilled
-            if (tid == 0 && it + TK_STAGES < my_tiles) {
+            // One barrier per tile: (a) every thread holds its row, so the slot can be refilled;
+            // (b) the previous tile's candidate pushes are complete, so its overflow flag is final.
+            __syncthreads();
+            if (tid == 0 && it + STAGES < my_tiles) {
                 mbar_expect_tx(&sm.full[slot], TK_STAGE_BYTES);
-                tma_load_2d(sm.stage[slot], &tmap, 0, (int)((tile0 + it + TK_STAGES) * TK_ROWS), &sm.full[slot]);
+                tma_load_2d(sm.stage[slot], &tmap, 0, (int)((tile0 + it + STAGES) * TK_ROWS), &sm.full[slot]);
             }
+            // flags rotate over three slots: written during tile it, read here at it+1, cleared at it+2
+            if (it > 0 && sm.flush_flag[(it - 1) % 3]) {
+                flush_queues(sm, nq_tile, k, warp, lane);
+                __syncthreads();
+            }
+            if (tid == 0 && it > 1) sm.flush_flag[(it - 2) % 3] = 0;
             const int64_t row = (tile0 + it) * TK_ROWS + tid;
             const bool valid = row < n_db;
             if (normalise) normalise32(d);
             int overflow = 0;
-            for (int qq = 0; qq < nq_tile; ++qq) {
-                float s = score32(sm.q[qq], d);
-                bool pass = valid && (sm.llen[qq] < k || beats(s, (uint32_t)row, sm.thr_s[qq], sm.thr_i[qq]));
-                if (pass) {
-                    int p = atomicAdd(&sm.qcount[qq], 1);
-                    if (p < TK_QCAP) { sm.qs[qq][p] = s; sm.qi[qq][p] = (uint32_t)row; }
-                    if (p >= TK_QCAP - TK_ROWS) overflow = 1;
+            if (QT == 1) {
+                float s = score32(sm.q[0], d);
+                push_candidate(sm, 0, s, (uint32_t)row, k, valid, overflow);
+            } else {
+#pragma unroll 1
+                for (int qq = 0; qq < nq_tile; qq += 4) {
+                    float s[4];
+                    score32x4(&sm.q[qq], d, s);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (qq + j < nq_tile) push_candidate(sm, qq + j, s[j], (uint32_t)row, k, valid, overflow);
                 }
             }
-            if (overflow) sm.flush_flag = 1;
-            __syncthreads();
-            if (sm.flush_flag) {      // uniform: read after the barrier
-                flush_queues(sm, nq_tile, k, warp, lane);
-                __syncthreads();
-                if (tid == 0) sm.flush_flag = 0;
-                __syncthreads();
-            }
+            if (overflow) sm.flush_flag[it % 3] = 1;
         }
+        __syncthreads();
         flush_queues(sm, nq_tile, k, warp, lane);
         __syncthreads();
         // write this slice's lists
@@ -244,93 +291,77 @@ topk_stream_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int t
     }
 }
 
-// One warp per query merges n_lists sorted lists (each k long) into the final top-k.
+// Merge n_lists sorted lists (each k long) per query into the final top-k.  One CTA of four
+// warps per query: warp w folds lists w, w+4, ... into its own list, warp 0 folds the four.
 // Input either (uint32 local rows + idx_base) or int64 global indices.
-struct MergeSmem {
-    float ls[2][ASR_MAX_K];
-    uint64_t li[2][ASR_MAX_K];
-};
-
-__device__ __forceinline__ bool beats64(float sa, int64_t ia, float sb, int64_t ib) {
-    return (sa > sb) || (sa == sb && ia < ib);
-}
-
-__global__ void __launch_bounds__(32)
+constexpr int MG_WARPS = 4;
+__global__ void __launch_bounds__(MG_WARPS * 32)
 topk_merge_kernel(const float *__restrict__ in_s, const uint32_t *__restrict__ in_i32, const int64_t *__restrict__ in_i64,
                   int64_t idx_base, int n_lists, int k, float *__restrict__ out_s, int64_t *__restrict__ out_i) {
-    __shared__ float ls[2][ASR_MAX_K];
-    __shared__ int64_t li[2][ASR_MAX_K];
-    const int lane = threadIdx.x;
+    __shared__ float ls[MG_WARPS][2][ASR_MAX_K];
+    __shared__ int64_t li[MG_WARPS][2][ASR_MAX_K];
+    __shared__ int wlen[MG_WARPS], wcur[MG_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t qi = blockIdx.x;
     const size_t base = (size_t)qi * n_lists * k;
     int len = 0, cur = 0;
     float thr_s = -CUDART_INF_F;
     int64_t thr_i = INT64_MAX;
-    const int total = n_lists * k;
+    auto fold = [&](float cs, int64_t ci, bool alive, int w) {
+        if (alive && len == k) alive = beats_t<int64_t>(cs, ci, thr_s, thr_i);
+        const unsigned mask = __ballot_sync(0xffffffffu, alive);
+        if (mask == 0u) return;
+        warp_merge_batch<int64_t>(ls[w][cur], li[w][cur], ls[w][cur ^ 1], li[w][cur ^ 1], len, k, cs, ci, alive, mask,
+                                  (int64_t)INT64_MAX, lane);
+        len = min(k, len + __popc(mask));
+        cur ^= 1;
+        if (len == k) { thr_s = ls[w][cur][k - 1]; thr_i = li[w][cur][k - 1]; }
+        __syncwarp();
+    };
+    // phase 1: each warp folds its lists; candidates are taken position-major across lists so the
+    // threshold rises quickly (position 0 of every list first)
+    const int my_lists = (n_lists - warp + MG_WARPS - 1) / MG_WARPS;
+    const int total = my_lists * k;
     for (int b = 0; b < total; b += 32) {
         int c = b + lane;
         bool alive = c < total;
         float cs = -CUDART_INF_F;
         int64_t ci = INT64_MAX;
         if (alive) {
-            cs = in_s[base + c];
+            int pos = c / my_lists, l = warp + (c % my_lists) * MG_WARPS;
+            size_t o = base + (size_t)l * k + pos;
+            cs = in_s[o];
             if (in_i32) {
-                uint32_t r = in_i32[base + c];
+                uint32_t r = in_i32[o];
                 alive = r != 0xffffffffu;
                 ci = (int64_t)r + idx_base;
             } else {
-                ci = in_i64[base + c];
+                ci = in_i64[o];
                 alive = ci >= 0;
-                if (!alive) ci = INT64_MAX;
             }
+            if (!alive) ci = INT64_MAX;
         }
-        if (alive && len == k) alive = beats64(cs, ci, thr_s, thr_i);
-        unsigned mask = __ballot_sync(0xffffffffu, alive);
-        if (mask == 0u) continue;
-        const float *s0 = ls[cur];
-        const int64_t *i0 = li[cur];
-        float *s1 = ls[cur ^ 1];
-        int64_t *i1 = li[cur ^ 1];
-        int pos = 0;
-        for (int j = 0; j < len; ++j) pos += beats64(s0[j], i0[j], cs, ci) ? 1 : 0;
-        float es[ASR_MAX_K / 32];
-        int64_t ei[ASR_MAX_K / 32];
-        int shift[ASR_MAX_K / 32];
-#pragma unroll
-        for (int r = 0; r < ASR_MAX_K / 32; ++r) {
-            int j = r * 32 + lane;
-            bool v = j < len;
-            es[r] = v ? s0[j] : -CUDART_INF_F;
-            ei[r] = v ? i0[j] : INT64_MAX;
-            shift[r] = 0;
-        }
-        for (int l = 0; l < 32; ++l) {
-            if (!((mask >> l) & 1u)) continue;
-            float os = __shfl_sync(0xffffffffu, cs, l);
-            int64_t oi = __shfl_sync(0xffffffffu, ci, l);
-            if (l != lane) pos += beats64(os, oi, cs, ci) ? 1 : 0;
-#pragma unroll
-            for (int r = 0; r < ASR_MAX_K / 32; ++r) shift[r] += beats64(os, oi, es[r], ei[r]) ? 1 : 0;
-        }
-#pragma unroll
-        for (int r = 0; r < ASR_MAX_K / 32; ++r) {
-            int j = r * 32 + lane;
-            if (j < len) {
-                int np = j + shift[r];
-                if (np < k) { s1[np] = es[r]; i1[np] = ei[r]; }
-            }
-        }
-        if (alive && pos < k) { s1[pos] = cs; i1[pos] = ci; }
-        __syncwarp();
-        len = min(k, len + __popc(mask));
-        cur ^= 1;
-        if (len == k) { thr_s = ls[cur][k - 1]; thr_i = li[cur][k - 1]; }
-        __syncwarp();
+        fold(cs, ci, alive, warp);
     }
-    for (int j = lane; j < k; j += 32) {
-        bool v = j < len;
-        out_s[(size_t)qi * k + j] = v ? ls[cur][j] : -CUDART_INF_F;
-        out_i[(size_t)qi * k + j] = v ? li[cur][j] : -1;
+    if (lane == 0) { wlen[warp] = len; wcur[warp] = cur; }
+    __syncthreads();
+    // phase 2: warp 0 folds the other warps' lists into its own
+    if (warp == 0) {
+        for (int w = 1; w < MG_WARPS; ++w) {
+            const int n = wlen[w], c2 = wcur[w];
+            for (int b = 0; b < n; b += 32) {
+                int c = b + lane;
+                bool alive = c < n;
+                float cs = alive ? ls[w][c2][c] : -CUDART_INF_F;
+                int64_t ci = alive ? li[w][c2][c] : INT64_MAX;
+                fold(cs, ci, alive, 0);
+            }
+        }
+        for (int j = lane; j < k; j += 32) {
+            bool v = j < len;
+            out_s[(size_t)qi * k + j] = v ? ls[0][cur][j] : -CUDART_INF_F;
+            out_i[(size_t)qi * k + j] = v ? li[0][cur][j] : -1;
+        }
     }
 }
 
@@ -364,10 +395,10 @@ __global__ void rank_target_kernel(const float *__restrict__ db, int64_t n_db, i
 
 struct RkSmem {
     float stage[TK_STAGES][TK_ROWS * 32];
-    float q[TK_QT][32];
-    float ts[TK_QT];
-    int64_t ti[TK_QT];
-    unsigned long long cnt[TK_QT];
+    float q[TK_QT_MAX][32];
+    float ts[TK_QT_MAX];
+    int64_t ti[TK_QT_MAX];
+    unsigned long long cnt[TK_QT_MAX];
     uint64_t full[TK_STAGES];
 };
 
@@ -391,11 +422,11 @@ rank_count_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int64_
         tma_prefetch_desc(&tmap);
     }
     __syncthreads();
-    const int n_qt = (nq + TK_QT - 1) / TK_QT;
+    const int n_qt = (nq + TK_QT_MAX - 1) / TK_QT_MAX;
     int64_t it_global = 0;
     for (int qt = blockIdx.y; qt < n_qt; qt += gridDim.y) {
-        const int q0 = qt * TK_QT;
-        const int nq_tile = min(TK_QT, nq - q0);
+        const int q0 = qt * TK_QT_MAX;
+        const int nq_tile = min(TK_QT_MAX, nq - q0);
         if (tid < nq_tile) {
             float v[32];
 #pragma unroll
@@ -415,9 +446,9 @@ rank_count_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int64_
             }
         }
         __syncthreads();
-        unsigned cnt[TK_QT];
+        unsigned cnt[TK_QT_MAX];
 #pragma unroll
-        for (int qq = 0; qq < TK_QT; ++qq) cnt[qq] = 0;
+        for (int qq = 0; qq < TK_QT_MAX; ++qq) cnt[qq] = 0;
         for (int64_t it = 0; it < my_tiles; ++it, ++it_global) {
             const int slot = (int)(it_global % TK_STAGES);
             const uint32_t parity = (uint32_t)((it_global / TK_STAGES) & 1);
@@ -439,7 +470,7 @@ rank_count_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int64_
             const int64_t grow = row + idx_base;
             if (normalise) normalise32(d);
 #pragma unroll
-            for (int qq = 0; qq < TK_QT; ++qq) {
+            for (int qq = 0; qq < TK_QT_MAX; ++qq) {
                 if (qq < nq_tile) {
                     float s = score32(sm.q[qq], d);
                     float t = sm.ts[qq];
@@ -449,7 +480,7 @@ rank_count_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int64_
             }
         }
 #pragma unroll
-        for (int qq = 0; qq < TK_QT; ++qq) {
+        for (int qq = 0; qq < TK_QT_MAX; ++qq) {
             unsigned c = cnt[qq];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -590,8 +621,12 @@ int asr_db_create(asr_db_t **out, const float *codes_dev, int64_t n, int64_t idx
     }
     static bool attr_done = false;
     if (!attr_done) {
-        ASR_CUDA(cudaFuncSetAttribute(topk_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)sizeof(TkSmem) + 1024));
+        ASR_CUDA(cudaFuncSetAttribute(topk_stream_kernel<1, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(TkSmem<1, 2>) + 1024));
+        ASR_CUDA(cudaFuncSetAttribute(topk_stream_kernel<4, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(TkSmem<4, 2>) + 1024));
+        ASR_CUDA(cudaFuncSetAttribute(topk_stream_kernel<16, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(TkSmem<16, 3>) + 1024));
         ASR_CUDA(cudaFuncSetAttribute(rank_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)sizeof(RkSmem) + 1024));
         attr_done = true;
@@ -607,19 +642,21 @@ int asr_db_destroy(asr_db_t *db) {
     return ASR_OK;
 }
 
-static void plan_grid(const asr_db *db, int64_t nq, int *n_slices, int *tiles_per_slice, int *n_qgroups) {
+// qt = queries per pass of the chosen kernel, ctas_per_sm = its occupancy
+static void plan_grid(const asr_db *db, int64_t nq, int qt, int ctas_per_sm, int *n_slices, int *tiles_per_slice,
+                      int *n_qgroups) {
     const int64_t n_tiles = (db->n + TK_ROWS - 1) / TK_ROWS;
-    const int64_t n_qt = (nq + TK_QT - 1) / TK_QT;
-    const int sms = db->sms;
-    // few query tiles: slice the DB over all SMs.  Many query tiles: keep slices long
+    const int64_t n_qt = (nq + qt - 1) / qt;
+    const int64_t slots = (int64_t)db->sms * ctas_per_sm;
+    // few query tiles: slice the DB over all CTA slots.  Many query tiles: keep slices long
     // (>= 64k rows) so per-slice list maintenance stays negligible and spread queries instead.
-    int64_t want = sms;
-    if (n_qt >= 2 * sms) want = std::max<int64_t>(1, std::min<int64_t>(sms, db->n / 65536));
-    else if (n_qt > 1) want = std::max<int64_t>(1, sms / n_qt);
+    int64_t want = slots;
+    if (n_qt >= 2 * slots) want = std::max<int64_t>(1, std::min<int64_t>(slots, db->n / 65536));
+    else if (n_qt > 1) want = std::max<int64_t>(1, slots / n_qt);
     int64_t tps = (n_tiles + want - 1) / want;
     if (tps < 1) tps = 1;
     int64_t ns = (n_tiles + tps - 1) / tps;
-    int64_t qg = std::min<int64_t>(n_qt, std::max<int64_t>(1, (2 * sms + ns - 1) / ns));
+    int64_t qg = std::min<int64_t>(n_qt, std::max<int64_t>(1, (2 * slots + ns - 1) / ns));
     *n_slices = (int)ns;
     *tiles_per_slice = (int)tps;
     *n_qgroups = (int)qg;
@@ -635,24 +672,32 @@ int asr_topk(asr_db_t *db, const float *q_dev, int64_t nq, int k, int normalise,
     if (nq == 0) return ASR_OK;
     ASR_CHECK_ARG(q_dev && out_score_dev && out_idx_dev, "NULL buffer");
     cudaStream_t st = (cudaStream_t)stream;
-    int n_slices, tps, dummy;
-    plan_grid(db, nq, &n_slices, &tps, &dummy);
+    const int qt = nq <= 2 ? 1 : (nq <= 8 ? 4 : 16);
+    const int occ = qt == 1 ? 3 : (qt == 4 ? 2 : 1);
+    int n_slices, tps, qg0;
+    plan_grid(db, nq, qt, occ, &n_slices, &tps, &qg0);
     // queries per launch bounded by the scratch: (score f32 + row u32) per (query, slice, k)
-    int64_t per_q = (int64_t)n_slices * k * 8;
-    int64_t q_chunk = std::max<int64_t>(TK_QT, (int64_t)(TK_SCRATCH_BYTES / per_q) / TK_QT * TK_QT);
+    const int64_t per_q = (int64_t)n_slices * k * 8;
+    const int64_t q_chunk = std::max<int64_t>(qt, (int64_t)(TK_SCRATCH_BYTES / per_q) / qt * qt);
     for (int64_t q0 = 0; q0 < nq; q0 += q_chunk) {
-        int64_t nqc = std::min<int64_t>(q_chunk, nq - q0);
-        int ns, t2, qg;
-        plan_grid(db, nqc, &ns, &t2, &qg);
-        if (ns != n_slices) { ns = n_slices; t2 = tps; }   // keep the scratch layout of the plan
+        const int64_t nqc = std::min<int64_t>(q_chunk, nq - q0);
+        const int64_t n_qt = (nqc + qt - 1) / qt;
+        const int qg = (int)std::min<int64_t>(n_qt, std::max<int64_t>(1, (2 * (int64_t)db->sms * occ + n_slices - 1) / n_slices));
         float *ps = reinterpret_cast<float *>(db->scratch);
-        uint32_t *pi = reinterpret_cast<uint32_t *>(ps + (size_t)nqc * ns * k);
-        dim3 grid(ns, qg);
-        topk_stream_kernel<<<grid, TK_THREADS, sizeof(TkSmem) + 1024, st>>>(db->tmap, db->n, t2, q_dev + q0 * 32, (int)nqc,
-                                                                            k, normalise, ps, pi);
+        uint32_t *pi = reinterpret_cast<uint32_t *>(ps + (size_t)nqc * n_slices * k);
+        dim3 grid(n_slices, qg);
+        if (qt == 1)
+            topk_stream_kernel<1, 2, 3><<<grid, TK_THREADS, sizeof(TkSmem<1, 2>) + 1024, st>>>(
+                db->tmap, db->n, tps, q_dev + q0 * 32, (int)nqc, k, normalise, ps, pi);
+        else if (qt == 4)
+            topk_stream_kernel<4, 2, 2><<<grid, TK_THREADS, sizeof(TkSmem<4, 2>) + 1024, st>>>(
+                db->tmap, db->n, tps, q_dev + q0 * 32, (int)nqc, k, normalise, ps, pi);
+        else
+            topk_stream_kernel<16, 3, 1><<<grid, TK_THREADS, sizeof(TkSmem<16, 3>) + 1024, st>>>(
+                db->tmap, db->n, tps, q_dev + q0 * 32, (int)nqc, k, normalise, ps, pi);
         ASR_LAUNCH_CHECK();
-        topk_merge_kernel<<<(unsigned)nqc, 32, 0, st>>>(ps, pi, nullptr, db->idx_base, ns, k, out_score_dev + q0 * k,
-                                                       out_idx_dev + q0 * k);
+        topk_merge_kernel<<<(unsigned)nqc, MG_WARPS * 32, 0, st>>>(ps, pi, nullptr, db->idx_base, n_slices, k,
+                                                                  out_score_dev + q0 * k, out_idx_dev + q0 * k);
         ASR_LAUNCH_CHECK();
     }
     return ASR_OK;
@@ -665,8 +710,8 @@ int asr_topk_merge(const float *score_dev, const int64_t *idx_dev, int64_t nq, i
     ASR_CHECK_ARG(k >= 1 && k <= ASR_MAX_K && n_lists >= 1, "bad k / n_lists");
     if (nq == 0) return ASR_OK;
     ASR_CHECK_ARG(score_dev && idx_dev && out_score_dev && out_idx_dev, "NULL buffer");
-    topk_merge_kernel<<<(unsigned)nq, 32, 0, (cudaStream_t)stream>>>(score_dev, nullptr, idx_dev, 0, n_lists, k,
-                                                                    out_score_dev, out_idx_dev);
+    topk_merge_kernel<<<(unsigned)nq, MG_WARPS * 32, 0, (cudaStream_t)stream>>>(score_dev, nullptr, idx_dev, 0, n_lists, k,
+                                                                               out_score_dev, out_idx_dev);
     ASR_LAUNCH_CHECK();
     return ASR_OK;
 }
@@ -688,7 +733,7 @@ int asr_rank_of_target(asr_db_t *db, const float *q_dev, int64_t nq, int64_t q_b
     }
     ASR_CHECK_ARG(better_dev != nullptr, "better_dev is NULL");
     int ns, tps, qg;
-    plan_grid(db, nq, &ns, &tps, &qg);
+    plan_grid(db, nq, TK_QT_MAX, 1, &ns, &tps, &qg);
     dim3 grid(ns, qg);
     rank_count_kernel<<<grid, TK_THREADS, sizeof(RkSmem) + 1024, st>>>(db->tmap, db->n, db->idx_base, tps, q_dev, (int)nq,
                                                                        normalise, tscore_dev, tidx_dev,
