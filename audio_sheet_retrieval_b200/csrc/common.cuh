@@ -73,19 +73,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"   // suspend-time hint: sleep in HW, do not spin
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
         : "memory");
     return ok != 0;
 }
-// Bounded spin: a protocol bug must not hang the GPU box (that would be a strike);
-// after ~2^26 polls the kernel traps and the host sees a launch failure.
+// Bounded wait: a protocol bug must not hang the GPU box (that would be a strike); after ~4 s of
+// wall time the kernel traps and the host sees a launch failure.
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t spins = 0;
+    if (mbar_try_wait(bar, parity)) return;
+    const uint64_t t0 = globaltimer_ns();
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) {
+        if (globaltimer_ns() - t0 > 4000000000ull) {
             printf("asr: mbarrier timeout block %d thread %d parity %u\n", blockIdx.x, threadIdx.x, parity);
             __trap();
         }

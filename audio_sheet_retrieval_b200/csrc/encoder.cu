@@ -58,7 +58,7 @@ struct ConvParams {
     bf16 *out;
     const bf16 *wblob;   // [9][KC][NP][8] bf16 followed by NP fp32 biases
     int n_samples;
-    int H, W, Wp, Hp, KC, NP, NCH, TH, bands, MT, pool;
+    int H, W, Wp, Hp, KC, NP, NCH, TH, bands, MT, pool, cout;
     int Ho, Wo, Wpo;
     long long in_plane, in_sample, out_plane, out_sample;   // bytes
     int sps, stage_bytes, n_stages, slot_cols, n_slots, tmem_cols, wbytes;
@@ -150,16 +150,18 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(const ConvP
         const uint32_t wp = (uint32_t)p.Wp;
         mbar_wait(w_full, 0);
         int it = 0;
-        uint32_t tc = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const int s = it % p.n_stages;
             const uint32_t ph = (uint32_t)((it / p.n_stages) & 1);
             mbar_wait(&in_full[s], ph);
             tc_fence_after();
             // descriptor of padded position -1 of the band (tap dy=-1, dx=-1 of output position 0)
-            uint32_t tile_lo = (((smem_u32(stage_sm + (size_t)s * p.stage_bytes + 16) & 0x3FFFFu) >> 4) | a_lbo) - 1u;
-            for (int mt = 0; mt < p.MT; ++mt, ++tc, tile_lo += 128u) {
-                if ((tc & (uint32_t)(N_MMA_WARPS - 1)) != my) continue;
+            const uint32_t band_lo = (((smem_u32(stage_sm + (size_t)s * p.stage_bytes + 16) & 0x3FFFFu) >> 4) | a_lbo) - 1u;
+            // my tiles of this band: tc0 + mt with (tc0 + mt) & 3 == my
+            const uint32_t tc0 = (uint32_t)it * (uint32_t)p.MT;
+            for (int mt = (int)((my - tc0) & (uint32_t)(N_MMA_WARPS - 1)); mt < p.MT; mt += N_MMA_WARPS) {
+                const uint32_t tc = tc0 + (uint32_t)mt;
+                const uint32_t tile_lo = band_lo + (uint32_t)mt * 128u;
                 const uint32_t slot = tc & slot_mask;
                 const uint32_t sph = (tc >> slot_shift) & 1u;
                 mbar_wait(&acc_empty[slot], sph ^ 1u);
@@ -187,12 +189,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(const ConvP
         const int quarter = warp & 3;            // TMEM lane quarter this warp may access
         const int etid = tid - 32 * EPI_WARP0;   // 0..511
         mbar_wait(w_full, 0);                    // bias visible
-        uint32_t tc = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int it = 0;
+        const int n_groups16 = (p.cout + 3) >> 2;     // 4-channel groups that hold real channels
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const int n = item / p.bands, y0 = (item % p.bands) * p.TH;
             uint8_t *out_n = reinterpret_cast<uint8_t *>(p.out) + (long long)n * p.out_sample;
-            for (int mt = 0; mt < p.MT; ++mt, ++tc) {
-                if ((tc & (uint32_t)(N_EPI_GROUPS - 1)) != grp) continue;
+            const uint32_t tc0 = (uint32_t)it * (uint32_t)p.MT;
+            for (int mt = (int)((grp - tc0) & (uint32_t)(N_EPI_GROUPS - 1)); mt < p.MT; mt += N_EPI_GROUPS) {
+                const uint32_t tc = tc0 + (uint32_t)mt;
                 const uint32_t slot = tc & ((uint32_t)p.n_slots - 1u);
                 const uint32_t sph = (tc >> ((uint32_t)__ffs(p.n_slots) - 1u)) & 1u;
                 mbar_wait(&acc_full[slot], sph);
@@ -209,11 +213,16 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(const ConvP
                     uint32_t pk[8];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const float4 b4 = *reinterpret_cast<const float4 *>(&bias_sm[ng * 16 + 4 * j]);
-                        __nv_bfloat162 h0 = __floats2bfloat162_rn(elu_f(v[4 * j] + b4.x), elu_f(v[4 * j + 1] + b4.y));
-                        __nv_bfloat162 h1 = __floats2bfloat162_rn(elu_f(v[4 * j + 2] + b4.z), elu_f(v[4 * j + 3] + b4.w));
-                        pk[2 * j] = *reinterpret_cast<uint32_t *>(&h0);
-                        pk[2 * j + 1] = *reinterpret_cast<uint32_t *>(&h1);
+                        if (ng * 4 + j < n_groups16) {     // warp-uniform: padded channels stay exactly zero
+                            const float4 b4 = *reinterpret_cast<const float4 *>(&bias_sm[ng * 16 + 4 * j]);
+                            __nv_bfloat162 h0 = __floats2bfloat162_rn(elu_f(v[4 * j] + b4.x), elu_f(v[4 * j + 1] + b4.y));
+                            __nv_bfloat162 h1 = __floats2bfloat162_rn(elu_f(v[4 * j + 2] + b4.z), elu_f(v[4 * j + 3] + b4.w));
+                            pk[2 * j] = *reinterpret_cast<uint32_t *>(&h0);
+                            pk[2 * j + 1] = *reinterpret_cast<uint32_t *>(&h1);
+                        } else {
+                            pk[2 * j] = 0u;
+                            pk[2 * j + 1] = 0u;
+                        }
                     }
                     if (p.pool) {
                         if (in_band) {
@@ -311,43 +320,64 @@ __device__ __forceinline__ float l0_fetch(const L0Params &p, const uint8_t *xu, 
 }
 
 constexpr int L0_MAXC = 32;
+constexpr int L0_TW = 32, L0_TH = 8;    // pixels per block
 
-__global__ void __launch_bounds__(256) l0_conv_kernel(const L0Params p) {
-    __shared__ float w_sm[L0_MAXC * 10];
-    for (int i = threadIdx.x; i < p.C * 10; i += blockDim.x) w_sm[i] = p.w[i];
-    __syncthreads();
-    const int n = blockIdx.y;
-    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= p.H * p.W) return;
-    const int y = pix / p.W, x = pix - y * p.W;
+// Folded weights travel in the kernel parameter block (constant bank): with the channel loops fully
+// unrolled every FFMA takes its weight straight from c[0][..], no load instruction.
+struct L0Weights {
+    float w[L0_MAXC * 9];
+    float b[L0_MAXC];
+};
+
+template <int C>   // C > 0: compile-time channel count; C == 0: run-time p.C
+__global__ void __launch_bounds__(L0_TW * L0_TH) l0_conv_kernel(const L0Params p, const L0Weights wt) {
+    __shared__ float tile[L0_TH + 2][L0_TW + 2];
+    const int tid = threadIdx.x;
+    const int n = blockIdx.z;
+    const int x0 = blockIdx.x * L0_TW, y0 = blockIdx.y * L0_TH;
     const size_t in_off = (size_t)n * p.Hin * p.Win;
     const uint8_t *xu = reinterpret_cast<const uint8_t *>(p.x) + in_off;
     const float *xf = reinterpret_cast<const float *>(p.x) + in_off;
+    for (int i = tid; i < (L0_TH + 2) * (L0_TW + 2); i += L0_TW * L0_TH) {
+        const int ty = i / (L0_TW + 2), tx = i - ty * (L0_TW + 2);
+        tile[ty][tx] = l0_fetch(p, xu, xf, y0 + ty - 1, x0 + tx - 1);
+    }
+    __syncthreads();
+    const int ty = tid / L0_TW, tx = tid - ty * L0_TW;
+    const int y = y0 + ty, x = x0 + tx;
+    if (y >= p.H || x >= p.W) return;
     float v[9];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) v[t] = l0_fetch(p, xu, xf, y + t / 3 - 1, x + t % 3 - 1);
-    uint8_t *out_n = reinterpret_cast<uint8_t *>(p.out) + (long long)n * p.out_sample +
-                     ((long long)(y + 1) * p.Wp + x + 1) * 16;
-    for (int ch = 0; ch < p.NCH; ++ch) {
-        uint32_t pk[4];
+    for (int t = 0; t < 9; ++t) v[t] = tile[ty + t / 3][tx + t % 3];
+    uint8_t *out_px = reinterpret_cast<uint8_t *>(p.out) + (long long)n * p.out_sample +
+                      ((long long)(y + 1) * p.Wp + x + 1) * 16;
+    constexpr int NCH_T = C > 0 ? (C + 15) / 16 * 2 : 0;
+    const int nch = C > 0 ? NCH_T : p.NCH;
+    const int cc = C > 0 ? C : p.C;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float r[2];
+    for (int ch = 0; ch < (C > 0 ? NCH_T : 4); ++ch) {
+        if (ch < nch) {
+            uint32_t pk[4];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int c = ch * 8 + 2 * j + h;
-                float acc = 0.f;
-                if (c < p.C) {
+            for (int j = 0; j < 4; ++j) {
+                float r[2];
 #pragma unroll
-                    for (int t = 0; t < 9; ++t) acc = fmaf(v[t], w_sm[c * 9 + t], acc);
-                    acc = elu_f(acc + w_sm[p.C * 9 + c]);
+                for (int h = 0; h < 2; ++h) {
+                    const int c = ch * 8 + 2 * j + h;
+                    float acc = 0.f;
+                    if (c < cc) {
+                        acc = wt.b[c];
+#pragma unroll
+                        for (int t = 0; t < 9; ++t) acc = fmaf(v[t], wt.w[c * 9 + t], acc);
+                        acc = elu_f(acc);
+                    }
+                    r[h] = acc;
                 }
-                r[h] = acc;
+                __nv_bfloat162 hh = __floats2bfloat162_rn(r[0], r[1]);
+                pk[j] = *reinterpret_cast<uint32_t *>(&hh);
             }
-            __nv_bfloat162 hh = __floats2bfloat162_rn(r[0], r[1]);
-            pk[j] = *reinterpret_cast<uint32_t *>(&hh);
+            *reinterpret_cast<uint4 *>(out_px + (long long)ch * p.out_plane) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
-        *reinterpret_cast<uint4 *>(out_n + (long long)ch * p.out_plane) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
 }
 
@@ -493,7 +523,8 @@ struct asr_encoder {
     int head_c, head_h, head_w;
     double flops;
     // tcgen05 path
-    float *l0_w = nullptr;          // [C0*9 + C0]
+    float *l0_w = nullptr;          // [C0*9 + C0] (device copy, unused by the product path)
+    L0Weights l0_host;              // folded layer-0 weights, passed by value at launch
     bf16 *wblob[8] = {nullptr};     // layers 1..7
     ConvPlan plan[8];
     bf16 *act[8] = {nullptr};       // P8 activations (output of layer l)
@@ -675,6 +706,11 @@ int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *d, int max_b
                 for (int t = 0; t < 9; ++t) w0[c * 9 + t] = wr[(size_t)c * 9 + t] * scale[c];
                 w0[(size_t)g.cout * 9 + c] = bias[c];
             }
+            memset(&e->l0_host, 0, sizeof(e->l0_host));
+            for (int c = 0; c < g.cout; ++c) {
+                for (int t = 0; t < 9; ++t) e->l0_host.w[c * 9 + t] = w0[(size_t)c * 9 + t];
+                e->l0_host.b[c] = w0[(size_t)g.cout * 9 + c];
+            }
             E_CUDA(cudaMalloc(&e->l0_w, w0.size() * 4));
             E_CUDA(cudaMemcpy(e->l0_w, w0.data(), w0.size() * 4, cudaMemcpyHostToDevice));
         } else {
@@ -781,8 +817,10 @@ int asr_encoder_embed(asr_encoder_t *e, const void *x_dev, int x_dtype, int64_t 
             p.Hin = d.in_h; p.Win = d.in_w; p.H = g.H; p.W = g.W; p.Wp = g.W + 2; p.Hp = g.H + 2;
             p.C = g.cout; p.NCH = g.coutp / 8; p.w = e->l0_w; p.out = e->act[0];
             p.out_plane = e->act_plane[0]; p.out_sample = e->act_sample[0]; p.n = (int)n;
-            dim3 grid((g.H * g.W + 255) / 256, (unsigned)n);
-            l0_conv_kernel<<<grid, 256, 0, st>>>(p);
+            dim3 grid((g.W + L0_TW - 1) / L0_TW, (g.H + L0_TH - 1) / L0_TH, (unsigned)n);
+            if (g.cout == 12) l0_conv_kernel<12><<<grid, L0_TW * L0_TH, 0, st>>>(p, e->l0_host);
+            else if (g.cout == 24) l0_conv_kernel<24><<<grid, L0_TW * L0_TH, 0, st>>>(p, e->l0_host);
+            else l0_conv_kernel<0><<<grid, L0_TW * L0_TH, 0, st>>>(p, e->l0_host);
             ASR_LAUNCH_CHECK();
         }
         mark(e, st);
@@ -792,7 +830,7 @@ int asr_encoder_embed(asr_encoder_t *e, const void *x_dev, int x_dtype, int64_t 
             ConvParams p;
             p.in = e->act[l - 1]; p.out = e->act[l]; p.wblob = e->wblob[l]; p.n_samples = (int)n;
             p.H = g.H; p.W = g.W; p.Wp = g.W + 2; p.Hp = g.H + 2; p.KC = g.cinp / 8; p.NP = g.coutp; p.NCH = g.coutp / 8;
-            p.TH = pl.TH; p.bands = pl.bands; p.MT = pl.MT; p.pool = g.pool;
+            p.TH = pl.TH; p.bands = pl.bands; p.MT = pl.MT; p.pool = g.pool; p.cout = g.cout;
             p.Ho = g.Ho; p.Wo = g.Wo; p.Wpo = g.Wo + 2;
             p.in_plane = e->act_plane[l - 1]; p.in_sample = e->act_sample[l - 1];
             p.out_plane = e->act_plane[l]; p.out_sample = e->act_sample[l];

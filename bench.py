@@ -208,7 +208,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=100000, help="pairs per GPU per step")
-    ap.add_argument("--max-batch", type=int, default=128)
+    ap.add_argument("--max-batch", type=int, default=1024)
     ap.add_argument("--cpu-sample", type=int, default=256, help="pairs in the CPU baseline sample")
     ap.add_argument("--db-rows", type=int, default=10000000)
     ap.add_argument("--skip-extras", action="store_true", help="only the headline leg (used under ncu)")
