@@ -186,8 +186,12 @@ topk_stream_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int t
                    int nq, int k, int normalise, float *__restrict__ part_s, uint32_t *__restrict__ part_i) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     typedef TkSmem<QT, STAGES> Smem;
-    Smem &sm = *reinterpret_cast<Smem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // No integer round-trip on the pointer: the compiler must keep the shared address space (LDS/STS,
+    // not generic LD/ST).  Dynamic shared memory starts at offset 0 of the CTA window (no static
+    // __shared__ in this kernel), which satisfies SWIZZLE_128B's 1024-byte alignment; checked below.
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (smem_u32(smem_raw) & 1023u) __trap();
     const int slice = blockIdx.x, n_slices = gridDim.x;
     const int64_t n_tiles = (n_db + TK_ROWS - 1) / TK_ROWS;
     const int64_t tile0 = (int64_t)slice * tiles_per_slice;
@@ -408,8 +412,9 @@ rank_count_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int64_
                   const float *__restrict__ q, int nq, int normalise, const float *__restrict__ tscore,
                   const int64_t *__restrict__ tidx, unsigned long long *__restrict__ better) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    RkSmem &sm = *reinterpret_cast<RkSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    RkSmem &sm = *reinterpret_cast<RkSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
+    if (smem_u32(smem_raw) & 1023u) __trap();
     const int slice = blockIdx.x;
     const int64_t n_tiles = (n_db + TK_ROWS - 1) / TK_ROWS;
     const int64_t tile0 = (int64_t)slice * tiles_per_slice;

@@ -97,6 +97,7 @@ def cpu_reference_pairs_per_s(n_sample, steps=1, warmup=0):
     CCA projection, length norm; asr/retrieval_wrapper.py + model graph) on all host threads."""
     import torch
     from oracle.encoders import OracleNet, load_param_list, synth_inputs
+    torch.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1; use every host core
     net = OracleNet(MODEL, load_param_list(PKL))
     X1, X2 = synth_inputs(min(n_sample, 64), seed=3)
     reps = (n_sample + len(X1) - 1) // len(X1)
