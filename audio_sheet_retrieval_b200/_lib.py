@@ -60,6 +60,8 @@ def _load():
     lib.asr_db_create.argtypes = [POINTER(c_void_p), c_void_p, c_int64, c_int64]
     lib.asr_db_destroy.argtypes = [c_void_p]
     lib.asr_topk.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]
+    lib.asr_debug_tc_scores.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
+    lib.asr_debug_tc_scores.restype = c_int
     lib.asr_topk_merge.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]
     lib.asr_rank_of_target.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_int,
                                        c_void_p, c_void_p, c_void_p, c_void_p]

@@ -16,6 +16,8 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -497,6 +499,309 @@ rank_count_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int64_
     }
 }
 
+// ---- tensor-core pre-filter + exact re-scoring ------------------------------------------
+// For many queries the pinned-order scoring (64 dependent fp32 instructions per (row, query)) is
+// FP32-issue bound.  This path scores a 128-query x 256-row tile with four tcgen05 tf32 MMAs
+// (fp32 accumulators in TMEM), which is only an APPROXIMATION s~ of the pinned score s, with
+// |s~ - s| <= 2^-9 for unit vectors (each tf32 operand carries <= 2^-10 relative error and
+// sum |q_k d_k| <= 1).  Exactness is kept by filtering, not by trusting s~: a row is re-scored with
+// the pinned fp32 order iff s~ >= tau_q - eps, where tau_q is the query's current k-th best EXACT
+// score and eps = 2^-8.  Every true top-k row satisfies s >= tau_final >= tau_q, hence
+// s~ >= tau_q - eps, so it is always re-scored; lists, thresholds and the final order use exact
+// scores only.  Results are therefore identical to topk_stream_kernel / the oracle.
+// Layout: thread = query (= TMEM lane); each thread keeps its query's sorted top-k list in registers.
+constexpr int TC_QM = 128;
+constexpr int TC_ROWS = 256;
+constexpr int TC_STAGES = 3;
+constexpr int TC_KMAX = 32;
+constexpr int TC_THREADS = 192;      // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue (one query per thread)
+
+struct TcSmem {
+    float stage[TC_STAGES][TC_ROWS * 32];     // normalised DB rows, SWIZZLE_128B (written by TMA)
+    float q[TC_QM * 32];                      // normalised queries, same swizzle (written by threads)
+    unsigned short cand[16][TC_QM];           // pending-candidate masks: [16-column group][query]
+    uint64_t full[TC_STAGES], empty[TC_STAGES], tfull[2], tempty[2];
+    uint32_t tmem_ptr;
+};
+
+__global__ void normalise_rows_kernel(const float *__restrict__ x, int64_t n, float *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v[32];
+    const float4 *src = reinterpret_cast<const float4 *>(x + i * 32);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float4 t = src[c];
+        v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
+    }
+    normalise32(v);
+    float4 *dst = reinterpret_cast<float4 *>(out + i * 32);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) dst[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+}
+
+// K-major, SWIZZLE_128B operand descriptor (128-byte rows, 8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;                       // LBO (unused for swizzled K-major)
+    d |= (uint64_t)(1024u >> 4) << 32;            // SBO
+    d |= (uint64_t)1 << 46;                       // version 1 (Blackwell)
+    d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// order-preserving map float -> uint32 (and back); NaN never reaches it (scores map NaN to -inf)
+__device__ __forceinline__ uint32_t fkey(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__device__ __forceinline__ bool key_gt(uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl) {
+    return (ah > bh) || (ah == bh && al > bl);
+}
+
+// exact pinned-order score of query lane `ql` against row `r` of a swizzled stage
+__device__ __forceinline__ float tc_exact_score(const float *qsm, const float *stage, int ql, int r) {
+    float acc = 0.f;
+    const float4 *qp = reinterpret_cast<const float4 *>(qsm + ql * 32);
+    const float4 *dp = reinterpret_cast<const float4 *>(stage + r * 32);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float4 a = qp[c ^ (ql & 7)];
+        const float4 b = dp[c ^ (r & 7)];
+        acc = __fadd_rn(acc, __fmul_rn(a.x, b.x));
+        acc = __fadd_rn(acc, __fmul_rn(a.y, b.y));
+        acc = __fadd_rn(acc, __fmul_rn(a.z, b.z));
+        acc = __fadd_rn(acc, __fmul_rn(a.w, b.w));
+    }
+    return (acc != acc) ? -CUDART_INF_F : acc;
+}
+
+// grid (n_slices, n_qgroups); qn = normalised queries (nq,32); tmap over the normalised DB copy
+__global__ void __launch_bounds__(TC_THREADS, 1)
+topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles_per_slice, const float *__restrict__ qn,
+               int nq, int k, float eps, float *__restrict__ part_s, uint32_t *__restrict__ part_i, float *dbg) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    TcSmem &sm = *reinterpret_cast<TcSmem *>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (smem_u32(smem_raw) & 1023u) __trap();
+    const int slice = blockIdx.x, n_slices = gridDim.x;
+    const int64_t n_tiles = (n_db + TC_ROWS - 1) / TC_ROWS;
+    const int64_t tile0 = (int64_t)slice * tiles_per_slice;
+    int64_t my_tiles = n_tiles - tile0;
+    if (my_tiles > tiles_per_slice) my_tiles = tiles_per_slice;
+    if (my_tiles < 0) my_tiles = 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&sm.tfull[s], 1); mbar_init(&sm.tempty[s], 4); }
+        mbar_fence_init();
+        tma_prefetch_desc(&tmap);
+    }
+    if (warp == 1) { tmem_alloc(&sm.tmem_ptr, 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sm.tmem_ptr;
+    // kind::tf32: a/b format 2 (TF32), fp32 accumulate, K-major both, M = 128, N = 256
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_ROWS >> 3) << 17) | ((uint32_t)(TC_QM >> 4) << 24);
+
+    const int n_qt = (nq + TC_QM - 1) / TC_QM;
+    int64_t itg = 0;                 // running tile counter (barrier phases continue across query tiles)
+    for (int qt = blockIdx.y; qt < n_qt; qt += gridDim.y) {
+        const int q0 = qt * TC_QM;
+        // stage the query tile, swizzled like a SWIZZLE_128B TMA load; rows beyond nq are zero
+        for (int i = tid; i < TC_QM * 8; i += TC_THREADS) {
+            const int row = i >> 3, c = i & 7;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q0 + row < nq) v = *reinterpret_cast<const float4 *>(qn + (int64_t)(q0 + row) * 32 + c * 4);
+            *reinterpret_cast<float4 *>(sm.q + row * 32 + ((c ^ (row & 7)) << 2)) = v;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA (async proxy)
+        __syncthreads();
+
+        if (warp == 0) {
+            if (lane == 0) {
+                for (int64_t it = 0; it < my_tiles; ++it) {
+                    const int64_t g = itg + it;
+                    const int s = (int)(g % TC_STAGES);
+                    mbar_wait(&sm.empty[s], (uint32_t)(((g / TC_STAGES) & 1) ^ 1));
+                    mbar_expect_tx(&sm.full[s], TC_ROWS * 128);
+                    tma_load_2d(sm.stage[s], &tmap, 0, (int)((tile0 + it) * TC_ROWS), &sm.full[s]);
+                }
+            }
+        } else if (warp == 1) {
+            const uint32_t leader = elect_one() ? 1u : 0u;
+            const uint32_t qaddr = smem_u32(sm.q);
+            for (int64_t it = 0; it < my_tiles; ++it) {
+                const int64_t g = itg + it;
+                const int s = (int)(g % TC_STAGES);
+                const uint32_t slot = (uint32_t)(g & 1);
+                mbar_wait(&sm.full[s], (uint32_t)((g / TC_STAGES) & 1));
+                mbar_wait(&sm.tempty[slot], (uint32_t)(((g >> 1) & 1) ^ 1));
+                tc_fence_after();
+                if (leader) {
+                    const uint32_t baddr = smem_u32(sm.stage[s]);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        tc_mma_tf32(tmem_base + slot * 256u, umma_desc_sw128(qaddr + kk * 32), umma_desc_sw128(baddr + kk * 32),
+                                    idesc, kk ? 1u : 0u);
+                    tc_commit(&sm.tfull[slot]);
+                }
+                __syncwarp();
+            }
+        } else {
+            const int quarter = warp & 3;
+            const int ql = quarter * 32 + lane;
+            const bool qvalid = q0 + ql < nq;
+            // The query's sorted top-k list lives in REGISTERS (k <= 32, all indexing static) as 64-bit
+            // keys (hi = order-preserving map of the exact score, lo = ~row): one unsigned 64-bit compare
+            // is exactly "score desc, index asc".  Empty slots hold the smallest key (-inf, row 0xffffffff),
+            // which loses to every real row (a NaN row scores -inf but has a smaller index).
+            uint32_t kh[TC_KMAX], kl[TC_KMAX];
+            const uint32_t NEG_INF_KEY = 0x007fffffu;     // fkey(-inf)
+#pragma unroll
+            for (int j = 0; j < TC_KMAX; ++j) { kh[j] = NEG_INF_KEY; kl[j] = 0u; }
+            // (thr_h, thr_l): a row must beat this key to enter the list; tau: rows whose APPROXIMATE score
+            // is below tau cannot beat it.  Both start from a floor found on the first tile (below).
+            uint32_t thr_h = NEG_INF_KEY, thr_l = 0u;
+            float tau = -CUDART_INF_F;
+            for (int64_t it = 0; it < my_tiles; ++it) {
+                const int64_t g = itg + it;
+                const int s = (int)(g % TC_STAGES);
+                const uint32_t slot = (uint32_t)(g & 1);
+                mbar_wait(&sm.tfull[slot], (uint32_t)((g >> 1) & 1));
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + slot * 256u + ((uint32_t)(quarter * 32) << 16);
+                const int64_t row0 = (tile0 + it) * TC_ROWS;
+                const float *stage = sm.stage[s];
+                if (it == 0 && row0 + TC_ROWS <= n_db) {
+                    // Threshold floor from the first (full) tile: bisect for a value `lo` such that at least k
+                    // of its 256 approximate scores are >= lo.  Those k rows have exact scores >= lo - eps,
+                    // so the final k-th best is >= lo - eps: a valid floor that removes the warm-up, where
+                    // every row would otherwise be scored exactly and inserted.
+                    float lo = -2.0f, hi = 2.0f;
+#pragma unroll 1
+                    for (int iter = 0; iter < 12; ++iter) {
+                        const float mid = 0.5f * (lo + hi);
+                        int cnt = 0;
+#pragma unroll 1
+                        for (int gq = 0; gq < 16; ++gq) {
+                            float v[16];
+                            tmem_ld16(taddr + (uint32_t)(gq * 16), v);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) cnt += v[j] >= mid ? 1 : 0;
+                        }
+                        if (cnt >= k) lo = mid; else hi = mid;
+                    }
+                    if (lo > -2.0f) {          // found (queries of all-NaN / degenerate tiles keep -inf)
+                        const float floor_s = lo - eps;
+                        thr_h = fkey(floor_s);
+                        thr_l = 0u;            // ties with the floor itself still enter (row index < 0xffffffff)
+                        tau = floor_s - eps;
+                    }
+                }
+                // Pass 1 (cheap, converged): scan the 256 approximate scores, remember which columns pass
+                // the filter as 16-bit masks in shared memory.
+                unsigned pend = 0u;
+#pragma unroll 1
+                for (int gq = 0; gq < 16; ++gq) {
+                    float v[16];
+                    tmem_ld16(taddr + (uint32_t)(gq * 16), v);
+                    if (dbg && slice == 0 && qt == 0 && it == 0) {      // debug: dump the approximate scores of tile 0
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) dbg[ql * TC_ROWS + gq * 16 + j] = v[j];
+                    }
+                    float m = v[0];
+#pragma unroll
+                    for (int j = 1; j < 16; ++j) m = fmaxf(m, v[j]);
+                    bool has_nan = false;       // fmaxf drops NaN (zero rows): they must reach the exact path
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) has_nan |= (v[j] != v[j]);
+                    if (qvalid && (has_nan || !(m < tau))) {
+                        unsigned mask = 0u;        // static indexing keeps v[] in registers
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) mask |= !(v[j] < tau) ? (1u << j) : 0u;
+                        sm.cand[gq][ql] = (unsigned short)mask;
+                        pend |= 1u << gq;
+                    }
+                }
+                // Pass 2 (rare): the lanes that have candidates drain them in lockstep, one candidate per
+                // lane per iteration, so the cost is the maximum (not the sum) over the warp's lanes.
+                while (__any_sync(0xffffffffu, pend != 0u)) {
+                    if (pend) {
+                        const int gq = __ffs(pend) - 1;
+                        unsigned mask = sm.cand[gq][ql];
+                        const int j = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        sm.cand[gq][ql] = (unsigned short)mask;
+                        if (!mask) pend &= ~(1u << gq);
+                        const int r = gq * 16 + j;
+                        const int64_t row = row0 + r;
+                        if (row < n_db) {
+                            uint32_t ch = fkey(tc_exact_score(sm.q, stage, ql, r));
+                            uint32_t cl = ~(uint32_t)row;
+                            if (key_gt(ch, cl, thr_h, thr_l)) {
+                                // bubble the candidate through the sorted list: whoever loses moves on
+#pragma unroll
+                                for (int jj = 0; jj < TC_KMAX; ++jj) {
+                                    if (jj < k) {
+                                        const bool b = key_gt(ch, cl, kh[jj], kl[jj]);
+                                        const uint32_t th = b ? kh[jj] : ch, tl = b ? kl[jj] : cl;
+                                        kh[jj] = b ? ch : kh[jj];
+                                        kl[jj] = b ? cl : kl[jj];
+                                        ch = th;
+                                        cl = tl;
+                                    }
+                                }
+                                uint32_t lh = NEG_INF_KEY, ll = 0u;      // the list's k-th entry
+#pragma unroll
+                                for (int jj = 0; jj < TC_KMAX; ++jj)
+                                    if (jj == k - 1) { lh = kh[jj]; ll = kl[jj]; }
+                                if (key_gt(lh, ll, thr_h, thr_l)) {       // thresholds only ever rise
+                                    thr_h = lh;
+                                    thr_l = ll;
+                                    tau = fkey_inv(lh) - eps;
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&sm.tempty[slot]); mbar_arrive(&sm.empty[s]); }
+            }
+            if (qvalid) {
+                const size_t o = ((size_t)(q0 + ql) * n_slices + slice) * k;
+#pragma unroll
+                for (int j = 0; j < TC_KMAX; ++j)
+                    if (j < k) {
+                        const bool real = !(kh[j] == NEG_INF_KEY && kl[j] == 0u);
+                        part_s[o + j] = real ? fkey_inv(kh[j]) : -CUDART_INF_F;
+                        part_i[o + j] = real ? ~kl[j] : 0xffffffffu;
+                    }
+            }
+        }
+        itg += my_tiles;
+        __syncthreads();     // every role is done with sm.q / the lists before the next query tile
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 // ---- vote -------------------------------------------------------------------------
 constexpr int VOTE_MAX = 8192;
 constexpr int VOTE_THREADS = 256;
@@ -587,6 +892,11 @@ struct asr_db {
     CUtensorMap tmap;
     void *scratch;          // TK_SCRATCH_BYTES: per-slice partial lists
     int sms;
+    // tensor-core pre-filter: pinned-normalised copy of the DB (made lazily on first use) + its tensor map
+    float *codes_n = nullptr;
+    CUtensorMap tmap_n;
+    float *qn = nullptr;    // normalised queries of the current call
+    int64_t qn_cap = 0;
 };
 
 using namespace asr;
@@ -634,6 +944,7 @@ int asr_db_create(asr_db_t **out, const float *codes_dev, int64_t n, int64_t idx
                                       (int)sizeof(TkSmem<16, 3>) + 1024));
         ASR_CUDA(cudaFuncSetAttribute(rank_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)sizeof(RkSmem) + 1024));
+        ASR_CUDA(cudaFuncSetAttribute(topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcSmem)));
         attr_done = true;
     }
     *out = db;
@@ -643,6 +954,8 @@ int asr_db_create(asr_db_t **out, const float *codes_dev, int64_t n, int64_t idx
 int asr_db_destroy(asr_db_t *db) {
     if (!db) return ASR_OK;
     cudaFree(db->scratch);
+    cudaFree(db->codes_n);
+    cudaFree(db->qn);
     delete db;
     return ASR_OK;
 }
@@ -667,6 +980,52 @@ static void plan_grid(const asr_db *db, int64_t nq, int qt, int ctas_per_sm, int
     *n_qgroups = (int)qg;
 }
 
+static float *g_tc_dbg = nullptr;   // set by asr_debug_tc_scores
+
+static int topk_tc(asr_db *db, const float *q_dev, int64_t nq, int k, float *out_score_dev, int64_t *out_idx_dev,
+                   cudaStream_t st) {
+    if (!db->codes_n) {     // first use: pinned-normalised copy + tensor map (not on the steady-state path)
+        ASR_CUDA(cudaMalloc(&db->codes_n, (size_t)db->n * 128));
+        normalise_rows_kernel<<<(unsigned)((db->n + 255) / 256), 256, 0, st>>>(db->codes, db->n, db->codes_n);
+        ASR_LAUNCH_CHECK();
+        cuuint64_t gdim[2] = {32, (cuuint64_t)db->n};
+        cuuint64_t gstr[1] = {128};
+        cuuint32_t box[2] = {32, (cuuint32_t)TC_ROWS};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = get_encode_fn()(&db->tmap_n, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, db->codes_n, gdim, gstr, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (normalised copy) failed"); return ASR_ERR_CUDA; }
+    }
+    if (db->qn_cap < nq) {
+        cudaFree(db->qn);
+        db->qn = nullptr;
+        ASR_CUDA(cudaMalloc(&db->qn, (size_t)nq * 128));
+        db->qn_cap = nq;
+    }
+    normalise_rows_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(q_dev, nq, db->qn);
+    ASR_LAUNCH_CHECK();
+    int n_slices, tps, qg0;
+    plan_grid(db, nq, TC_QM, 1, &n_slices, &tps, &qg0);
+    const int64_t per_q = (int64_t)n_slices * k * 8;
+    const int64_t q_chunk = std::max<int64_t>(TC_QM, (int64_t)(TK_SCRATCH_BYTES / per_q) / TC_QM * TC_QM);
+    for (int64_t q0 = 0; q0 < nq; q0 += q_chunk) {
+        const int64_t nqc = std::min<int64_t>(q_chunk, nq - q0);
+        const int64_t n_qt = (nqc + TC_QM - 1) / TC_QM;
+        const int qg = (int)std::min<int64_t>(n_qt, std::max<int64_t>(1, (2 * (int64_t)db->sms + n_slices - 1) / n_slices));
+        float *ps = reinterpret_cast<float *>(db->scratch);
+        uint32_t *pi = reinterpret_cast<uint32_t *>(ps + (size_t)nqc * n_slices * k);
+        dim3 grid(n_slices, qg);
+        topk_tc_kernel<<<grid, TC_THREADS, sizeof(TcSmem), st>>>(db->tmap_n, db->n, tps, db->qn + q0 * 32, (int)nqc, k,
+                                                                 0.00390625f, ps, pi, g_tc_dbg);
+        ASR_LAUNCH_CHECK();
+        topk_merge_kernel<<<(unsigned)nqc, MG_WARPS * 32, 0, st>>>(ps, pi, nullptr, db->idx_base, n_slices, k,
+                                                                  out_score_dev + q0 * k, out_idx_dev + q0 * k);
+        ASR_LAUNCH_CHECK();
+    }
+    return ASR_OK;
+}
+
 int asr_topk(asr_db_t *db, const float *q_dev, int64_t nq, int k, int normalise, float *out_score_dev,
              int64_t *out_idx_dev, void *stream) {
     int rc = ensure_device();
@@ -677,6 +1036,9 @@ int asr_topk(asr_db_t *db, const float *q_dev, int64_t nq, int k, int normalise,
     if (nq == 0) return ASR_OK;
     ASR_CHECK_ARG(q_dev && out_score_dev && out_idx_dev, "NULL buffer");
     cudaStream_t st = (cudaStream_t)stream;
+    const char *force = getenv("ASR_TOPK_PATH");       // "exact" | "tc" (tests exercise both)
+    const bool want_tc = force ? (strcmp(force, "tc") == 0) : (nq > 2);
+    if (want_tc && normalise && k <= TC_KMAX) return topk_tc(db, q_dev, nq, k, out_score_dev, out_idx_dev, st);
     const int qt = nq <= 2 ? 1 : (nq <= 8 ? 4 : 16);
     const int occ = qt == 1 ? 3 : (qt == 4 ? 2 : 1);
     int n_slices, tps, qg0;
@@ -705,6 +1067,24 @@ int asr_topk(asr_db_t *db, const float *q_dev, int64_t nq, int k, int normalise,
                                                                   out_score_dev + q0 * k, out_idx_dev + q0 * k);
         ASR_LAUNCH_CHECK();
     }
+    return ASR_OK;
+}
+
+// debug/validation: run the tensor-core path once and return the APPROXIMATE scores of the first
+// 128 queries against the first 256 DB rows (out_host: 128 x 256 floats)
+int asr_debug_tc_scores(asr_db_t *db, const float *q_dev, int64_t nq, float *out_host) {
+    float *d = nullptr;
+    ASR_CUDA(cudaMalloc(&d, TC_QM * TC_ROWS * 4));
+    ASR_CUDA(cudaMemset(d, 0, TC_QM * TC_ROWS * 4));
+    float *s = nullptr; int64_t *i = nullptr;
+    ASR_CUDA(cudaMalloc(&s, (size_t)nq * 4)); ASR_CUDA(cudaMalloc(&i, (size_t)nq * 8));
+    g_tc_dbg = d;
+    int rc = topk_tc(db, q_dev, nq, 1, s, i, 0);
+    g_tc_dbg = nullptr;
+    if (rc) return rc;
+    ASR_CUDA(cudaDeviceSynchronize());
+    ASR_CUDA(cudaMemcpy(out_host, d, TC_QM * TC_ROWS * 4, cudaMemcpyDeviceToHost));
+    cudaFree(d); cudaFree(s); cudaFree(i);
     return ASR_OK;
 }
 

@@ -199,7 +199,8 @@ def piece_id_leg(torch, dev, rank, world, quick=False):
     acc = float((pid[:, 0].long() == true_piece).float().mean().item())
     return {"db_rows": n_db, "queries": n_rec * win, "k": 25, "ms": float(ms.item()),
             "queries_per_s": n_rec * win / (float(ms.item()) * 1e-3), "top1_piece_accuracy": acc,
-            "regime": "fp32-pipe bound (separately rounded mul+add for bit-exact scores), DB sharded over %d GPU(s)" % world}
+            "regime": "tcgen05 tf32 pre-filter + exact fp32 re-scoring (bit-exact results); bound by the TMEM read-out of "
+                      "the 128x256 score tiles; DB sharded over %d GPU(s)" % world}
 
 
 def main():

@@ -123,6 +123,9 @@ int asr_db_destroy(asr_db_t *db);
  * DB size hold (-inf, -1).  normalise != 0 L2-normalises queries and DB rows in-kernel. */
 int asr_topk(asr_db_t *db, const float *q_dev, int64_t nq, int k, int normalise,
              float *out_score_dev, int64_t *out_idx_dev, void *stream);
+/* validation hook: approximate (tf32 tensor-core) scores of the first 128 queries x first 256 DB rows as the
+ * pre-filter of asr_topk sees them (out_host: 128*256 floats, row = query) */
+int asr_debug_tc_scores(asr_db_t *db, const float *q_dev, int64_t nq, float *out_host);
 /* merge n_lists candidate lists per query, laid out (nq, n_lists*k) - the step after the
  * all-gather of per-GPU top-k. */
 int asr_topk_merge(const float *score_dev, const int64_t *idx_dev, int64_t nq, int n_lists, int k,

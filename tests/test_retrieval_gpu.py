@@ -157,3 +157,33 @@ def test_large_db_roundtrip_property():
     s, i = db.topk_device(D[rows].contiguous(), 4)
     assert (i[:, 0] == rows).all()
     assert (s[:, 0] > 0.9999).all() and (s[:, :-1] >= s[:, 1:]).all()
+
+
+@pytest.mark.parametrize("path", ["exact", "tc"])
+@pytest.mark.parametrize("n,nq,k", [(300, 5, 7), (5000, 130, 25), (66000, 257, 32), (1000, 3, 1)])
+def test_topk_both_kernel_paths_bit_exact(monkeypatch, path, n, nq, k):
+    """The tensor-core pre-filter path and the streaming fp32 path must both equal the oracle."""
+    from audio_sheet_retrieval_b200.retrieval import EmbeddingDB
+    monkeypatch.setenv("ASR_TOPK_PATH", path)
+    D, Q = _db(n, 21), _db(nq, 22, unit=False)
+    D[n // 2] = D[3]
+    D[7] = 0
+    s_ref, i_ref = clib.topk(Q, D, k)
+    s, i = EmbeddingDB(D, idx_base=77).topk(Q, k)
+    assert (i - 77 == i_ref).all() and (s == s_ref).all()
+
+
+@pytest.mark.parametrize("path", ["exact", "tc"])
+def test_topk_near_ties_within_prefilter_margin(monkeypatch, path):
+    """Adversarial for the approximate pre-filter: thousands of rows whose exact scores differ by far
+    less than the tf32 error (clusters of 1e-5-perturbed copies).  Exact re-scoring must still order them."""
+    from audio_sheet_retrieval_b200.retrieval import EmbeddingDB
+    monkeypatch.setenv("ASR_TOPK_PATH", path)
+    rng = np.random.RandomState(5)
+    centers = _db(40, 31)
+    D = np.repeat(centers, 500, axis=0) + rng.normal(0, 1e-5, (20000, 32)).astype(np.float32)
+    D = np.concatenate([D, _db(30000, 32)]).astype(np.float32)
+    Q = centers + rng.normal(0, 1e-3, centers.shape).astype(np.float32)
+    s_ref, i_ref = clib.topk(Q, D, 25)
+    s, i = EmbeddingDB(D).topk(Q, 25)
+    assert (i == i_ref).all() and (s == s_ref).all()
