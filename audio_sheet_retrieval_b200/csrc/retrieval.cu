@@ -522,6 +522,7 @@ struct TcSmem {
     unsigned short cand[16][TC_QM];           // pending-candidate masks: [16-column group][query]
     uint64_t full[TC_STAGES], empty[TC_STAGES], tfull[2], tempty[2];
     uint32_t tmem_ptr;
+    unsigned item;
 };
 
 __global__ void normalise_rows_kernel(const float *__restrict__ x, int64_t n, float *__restrict__ out) {
@@ -589,20 +590,17 @@ __device__ __forceinline__ float tc_exact_score(const float *qsm, const float *s
     return (acc != acc) ? -CUDART_INF_F : acc;
 }
 
-// grid (n_slices, n_qgroups); qn = normalised queries (nq,32); tmap over the normalised DB copy
+// Persistent 1-D grid; work items (query tile, DB slice) are handed out by an atomic counter so that
+// any (nq, n_db) shape fills all SMs.  qn = normalised queries (nq,32); tmap over the normalised DB copy.
 __global__ void __launch_bounds__(TC_THREADS, 1)
-topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles_per_slice, const float *__restrict__ qn,
-               int nq, int k, float eps, float *__restrict__ part_s, uint32_t *__restrict__ part_i, float *dbg) {
+topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles_per_slice, int n_slices,
+               const float *__restrict__ qn, int nq, int k, float eps, float *__restrict__ part_s,
+               uint32_t *__restrict__ part_i, unsigned *__restrict__ work_counter, float *dbg) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     TcSmem &sm = *reinterpret_cast<TcSmem *>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (smem_u32(smem_raw) & 1023u) __trap();
-    const int slice = blockIdx.x, n_slices = gridDim.x;
     const int64_t n_tiles = (n_db + TC_ROWS - 1) / TC_ROWS;
-    const int64_t tile0 = (int64_t)slice * tiles_per_slice;
-    int64_t my_tiles = n_tiles - tile0;
-    if (my_tiles > tiles_per_slice) my_tiles = tiles_per_slice;
-    if (my_tiles < 0) my_tiles = 0;
 
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 4); }
@@ -619,8 +617,19 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_ROWS >> 3) << 17) | ((uint32_t)(TC_QM >> 4) << 24);
 
     const int n_qt = (nq + TC_QM - 1) / TC_QM;
-    int64_t itg = 0;                 // running tile counter (barrier phases continue across query tiles)
-    for (int qt = blockIdx.y; qt < n_qt; qt += gridDim.y) {
+    const unsigned n_items = (unsigned)n_qt * (unsigned)n_slices;
+    int64_t itg = 0;                 // running tile counter (barrier phases continue across work items)
+    for (;;) {
+        if (tid == 0) sm.item = atomicAdd(work_counter, 1u);
+        __syncthreads();
+        const unsigned item = sm.item;
+        if (item >= n_items) break;
+        // consecutive items share the DB slice (L2 reuse across CTAs), query tile varies fastest
+        const int slice = (int)(item / (unsigned)n_qt), qt = (int)(item % (unsigned)n_qt);
+        const int64_t tile0 = (int64_t)slice * tiles_per_slice;
+        int64_t my_tiles = n_tiles - tile0;
+        if (my_tiles > tiles_per_slice) my_tiles = tiles_per_slice;
+        if (my_tiles < 0) my_tiles = 0;
         const int q0 = qt * TC_QM;
         // stage the query tile, swizzled like a SWIZZLE_128B TMA load; rows beyond nq are zero
         for (int i = tid; i < TC_QM * 8; i += TC_THREADS) {
@@ -698,11 +707,11 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles
                         const float mid = 0.5f * (lo + hi);
                         int cnt = 0;
 #pragma unroll 1
-                        for (int gq = 0; gq < 16; ++gq) {
-                            float v[16];
-                            tmem_ld16(taddr + (uint32_t)(gq * 16), v);
+                        for (int g4 = 0; g4 < 4; ++g4) {
+                            float v[64];
+                            tmem_ld64(taddr + (uint32_t)(g4 * 64), v);
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) cnt += v[j] >= mid ? 1 : 0;
+                            for (int j = 0; j < 64; ++j) cnt += v[j] >= mid ? 1 : 0;
                         }
                         if (cnt >= k) lo = mid; else hi = mid;
                     }
@@ -713,29 +722,38 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles
                         tau = floor_s - eps;
                     }
                 }
-                // Pass 1 (cheap, converged): scan the 256 approximate scores, remember which columns pass
-                // the filter as 16-bit masks in shared memory.
+                // Pass 1 (cheap, converged): scan the 256 approximate scores, 64 columns per TMEM round trip,
+                // and remember which columns pass the filter as 16-bit masks in shared memory.  NaN
+                // approximations (zero DB rows) need no special case: they can only matter while tau is
+                // -inf, and then !(x < tau) is true for every x.
                 unsigned pend = 0u;
 #pragma unroll 1
-                for (int gq = 0; gq < 16; ++gq) {
-                    float v[16];
-                    tmem_ld16(taddr + (uint32_t)(gq * 16), v);
+                for (int g4 = 0; g4 < 4; ++g4) {
+                    float v[64];
+                    tmem_ld64(taddr + (uint32_t)(g4 * 64), v);
                     if (dbg && slice == 0 && qt == 0 && it == 0) {      // debug: dump the approximate scores of tile 0
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) dbg[ql * TC_ROWS + gq * 16 + j] = v[j];
+                        for (int j = 0; j < 64; ++j) dbg[ql * TC_ROWS + g4 * 64 + j] = v[j];
                     }
-                    float m = v[0];
+                    float m[4];
 #pragma unroll
-                    for (int j = 1; j < 16; ++j) m = fmaxf(m, v[j]);
-                    bool has_nan = false;       // fmaxf drops NaN (zero rows): they must reach the exact path
+                    for (int sub = 0; sub < 4; ++sub) {
+                        m[sub] = v[sub * 16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) has_nan |= (v[j] != v[j]);
-                    if (qvalid && (has_nan || !(m < tau))) {
-                        unsigned mask = 0u;        // static indexing keeps v[] in registers
+                        for (int j = 1; j < 16; ++j) m[sub] = fmaxf(m[sub], v[sub * 16 + j]);
+                    }
+                    const float mm = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
+                    if (qvalid && !(mm < tau)) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) mask |= !(v[j] < tau) ? (1u << j) : 0u;
-                        sm.cand[gq][ql] = (unsigned short)mask;
-                        pend |= 1u << gq;
+                        for (int sub = 0; sub < 4; ++sub) {
+                            if (!(m[sub] < tau)) {
+                                unsigned mask = 0u;        // static indexing keeps v[] in registers
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) mask |= !(v[sub * 16 + j] < tau) ? (1u << j) : 0u;
+                                sm.cand[g4 * 4 + sub][ql] = (unsigned short)mask;
+                                pend |= 1u << (g4 * 4 + sub);
+                            }
+                        }
                     }
                 }
                 // Pass 2 (rare): the lanes that have candidates drain them in lockstep, one candidate per
@@ -1005,19 +1023,32 @@ static int topk_tc(asr_db *db, const float *q_dev, int64_t nq, int k, float *out
     }
     normalise_rows_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(q_dev, nq, db->qn);
     ASR_LAUNCH_CHECK();
-    int n_slices, tps, qg0;
-    plan_grid(db, nq, TC_QM, 1, &n_slices, &tps, &qg0);
+    // slices: enough (query tile, slice) items to balance the persistent grid, but never shorter than
+    // 128 tiles (32k rows) so the per-item threshold warm-up stays negligible
+    const int64_t n_tiles = (db->n + TC_ROWS - 1) / TC_ROWS;
+    const int64_t n_qt_all = (nq + TC_QM - 1) / TC_QM;
+    // Every (query tile, slice) item pays a threshold warm-up (about k*ln(rows/256) exact re-scorings per
+    // query), so items should be long.  Many query tiles: slices of >= 1024 tiles, ~2 items per SM
+    // (measured best for 10k queries x 1M rows).  Few query tiles: the DB must be sliced to fill the SMs.
+    const bool many_q = n_qt_all * 2 >= db->sms;
+    const int items_per_sm = getenv("ASR_TC_ITEMS_PER_SM") ? atoi(getenv("ASR_TC_ITEMS_PER_SM")) : (many_q ? 2 : 1);
+    const int min_tiles = getenv("ASR_TC_MIN_TILES") ? atoi(getenv("ASR_TC_MIN_TILES")) : (many_q ? 1024 : 128);
+    int64_t want = std::max<int64_t>(1, (items_per_sm * (int64_t)db->sms + n_qt_all - 1) / n_qt_all);
+    want = std::min<int64_t>(want, std::max<int64_t>(1, n_tiles / min_tiles));
+    const int tps = (int)((n_tiles + want - 1) / want);
+    const int n_slices = (int)((n_tiles + tps - 1) / tps);
     const int64_t per_q = (int64_t)n_slices * k * 8;
-    const int64_t q_chunk = std::max<int64_t>(TC_QM, (int64_t)(TK_SCRATCH_BYTES / per_q) / TC_QM * TC_QM);
+    const int64_t q_chunk = std::max<int64_t>(TC_QM, (int64_t)((TK_SCRATCH_BYTES - 256) / per_q) / TC_QM * TC_QM);
+    unsigned *counter = reinterpret_cast<unsigned *>(reinterpret_cast<uint8_t *>(db->scratch) + TK_SCRATCH_BYTES - 256);
     for (int64_t q0 = 0; q0 < nq; q0 += q_chunk) {
         const int64_t nqc = std::min<int64_t>(q_chunk, nq - q0);
         const int64_t n_qt = (nqc + TC_QM - 1) / TC_QM;
-        const int qg = (int)std::min<int64_t>(n_qt, std::max<int64_t>(1, (2 * (int64_t)db->sms + n_slices - 1) / n_slices));
         float *ps = reinterpret_cast<float *>(db->scratch);
         uint32_t *pi = reinterpret_cast<uint32_t *>(ps + (size_t)nqc * n_slices * k);
-        dim3 grid(n_slices, qg);
-        topk_tc_kernel<<<grid, TC_THREADS, sizeof(TcSmem), st>>>(db->tmap_n, db->n, tps, db->qn + q0 * 32, (int)nqc, k,
-                                                                 0.00390625f, ps, pi, g_tc_dbg);
+        ASR_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
+        const int grid = (int)std::min<int64_t>(db->sms, n_qt * n_slices);
+        topk_tc_kernel<<<grid, TC_THREADS, sizeof(TcSmem), st>>>(db->tmap_n, db->n, tps, n_slices, db->qn + q0 * 32, (int)nqc,
+                                                                 k, 0.00390625f, ps, pi, counter, g_tc_dbg);
         ASR_LAUNCH_CHECK();
         topk_merge_kernel<<<(unsigned)nqc, MG_WARPS * 32, 0, st>>>(ps, pi, nullptr, db->idx_base, n_slices, k,
                                                                   out_score_dev + q0 * k, out_idx_dev + q0 * k);
@@ -1037,7 +1068,8 @@ int asr_topk(asr_db_t *db, const float *q_dev, int64_t nq, int k, int normalise,
     ASR_CHECK_ARG(q_dev && out_score_dev && out_idx_dev, "NULL buffer");
     cudaStream_t st = (cudaStream_t)stream;
     const char *force = getenv("ASR_TOPK_PATH");       // "exact" | "tc" (tests exercise both)
-    const bool want_tc = force ? (strcmp(force, "tc") == 0) : (nq > 2);
+    // measured crossover (1e7 rows, k = 25): the exact QT=16 kernel wins up to ~24 queries
+    const bool want_tc = force ? (strcmp(force, "tc") == 0) : (nq > 24);
     if (want_tc && normalise && k <= TC_KMAX) return topk_tc(db, q_dev, nq, k, out_score_dev, out_idx_dev, st);
     const int qt = nq <= 2 ? 1 : (nq <= 8 ? 4 : 16);
     const int occ = qt == 1 ? 3 : (qt == 4 ? 2 : 1);
