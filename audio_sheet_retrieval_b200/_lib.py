@@ -52,6 +52,9 @@ def _load():
     lib.asr_encoder_embed_host.argtypes = [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int]
     lib.asr_encoder_debug_activation.argtypes = [c_void_p, c_int, c_int, c_int64, c_void_p,
                                                  POINTER(c_int), POINTER(c_int), POINTER(c_int)]
+    lib.asr_extract_windows.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                        c_void_p]
+    lib.asr_extract_windows.restype = c_int
     lib.asr_encoder_set_timing.argtypes = [c_void_p, c_int]
     lib.asr_encoder_get_timing.argtypes = [c_void_p, POINTER(c_double), POINTER(c_double), POINTER(c_double),
                                            POINTER(c_int64)]

@@ -9,13 +9,31 @@ out of scope; `set_sheet_db` / `set_audio_db` take codes computed with `embed_ne
 """
 from __future__ import print_function
 
+import json
+import os
 import pickle
 
 import numpy as np
 import torch
 
+from . import _lib
 from .retrieval import EmbeddingDB, _as_codes
 from .retrieval_wrapper import RetrievalWrapper
+
+
+def extract_windows_device(src, starts, r0, win_h, win_w):
+    """src: 2-D CUDA tensor (uint8 or float32) holding one unrolled sheet / spectrogram.
+    -> (n, 1, win_h, win_w) CUDA tensor of the same dtype (asr_extract_windows)."""
+    assert src.is_cuda and src.dim() == 2 and src.is_contiguous() and src.dtype in (torch.uint8, torch.float32)
+    starts = np.asarray(starts, dtype=np.int32)
+    if len(starts) and (starts.min() < 0 or starts.max() > src.shape[1] - win_w):
+        raise ValueError("window start out of range")
+    st = torch.as_tensor(starts).to(src.device)
+    out = torch.empty((len(starts), 1, win_h, win_w), dtype=src.dtype, device=src.device)
+    _lib.check(_lib.lib.asr_extract_windows(_lib.dptr(src), _lib.IN_U8 if src.dtype == torch.uint8 else _lib.IN_F32,
+                                            int(src.shape[0]), int(src.shape[1]), _lib.dptr(st), len(starts), int(r0),
+                                            int(win_h), int(win_w), _lib.dptr(out), _lib.stream_ptr()))
+    return out
 
 
 class AudioSheetServer(object):
@@ -50,6 +68,71 @@ class AudioSheetServer(object):
         self.id_to_perform = id_to_perform
         self.perform_excerpts = excerpts
         self._audio_db = EmbeddingDB(self.perform_excerpt_codes, ids=self.perform_excerpt_ids)
+
+    # -- DB construction from raw material (:403-494) -------------------------------------------
+    def _embed_windows(self, view, src_2d, starts, r0, win_h, win_w):
+        """One H2D copy of the whole piece, windows cut and embedded on the device."""
+        net = self.embed_network.net
+        mode = self.embed_network.prepare_view_1.asr_prepare_mode if view == 1 else _lib.PREP_NONE
+        enc = net.encoder(view, mode)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        src = torch.as_tensor(np.ascontiguousarray(src_2d))
+        src = src.to(dev) if src.dtype == torch.uint8 else src.to(dev, torch.float32)
+        wins = extract_windows_device(src.contiguous(), starts, r0, win_h, win_w)
+        codes = torch.empty((wins.shape[0], 32), dtype=torch.float32, device=dev)
+        for s0 in range(0, wins.shape[0], enc.max_batch):
+            enc.embed_device(wins[s0:s0 + enc.max_batch], codes=codes[s0:s0 + enc.max_batch])
+        return codes
+
+    def initialize_audio_db_from_specs(self, pieces, spectrograms, keep_snippets=False):
+        """ init audio data base: excerpts at hop spec_context // 4 of every spectrogram (:403-445) """
+        print("Initializing audio db ...")
+        id_to_perform, codes, ids = dict(), [], []
+        for piece_idx, piece in enumerate(pieces):
+            id_to_perform[piece_idx] = piece
+            spectrogram = spectrograms[piece_idx]
+            indices = np.arange(0, spectrogram.shape[1] - self.spec_shape[1], self.spec_shape[1] // 4)
+            codes.append(self._embed_windows(2, spectrogram, indices, 0, self.spec_shape[0], self.spec_shape[1]))
+            ids.append(np.ones(len(indices), dtype=np.int64) * piece_idx)
+        codes = torch.cat(codes).cpu().numpy() if codes else np.zeros((0, 32), np.float32)
+        self.set_audio_db(codes, np.concatenate(ids), id_to_perform)
+        print("%s audio excerpts of %d pieces collected" % (codes.shape[0], len(pieces)))
+
+    def initialize_sheet_db_from_imges(self, pieces, scores, keep_snippets=False):
+        """ init sheet music data base: snippets at hop sheet_context // 4 from the vertical centre of every
+        unrolled score (:447-494; the reference spells it `imges`) """
+        print("Initializing sheet music db ...")
+        id_to_piece, codes, ids = dict(), [], []
+        for piece_idx, piece in enumerate(pieces):
+            id_to_piece[piece_idx] = piece
+            piece_image = scores[piece_idx]
+            indices = np.arange(0, piece_image.shape[1] - self.sheet_shape[1], self.sheet_shape[1] // 4)
+            r0 = piece_image.shape[0] // 2 - self.sheet_shape[0] // 2
+            codes.append(self._embed_windows(1, piece_image, indices, r0, self.sheet_shape[0], self.sheet_shape[1]))
+            ids.append(np.ones(len(indices), dtype=np.int64) * piece_idx)
+        codes = torch.cat(codes).cpu().numpy() if codes else np.zeros((0, 32), np.float32)
+        self.set_sheet_db(codes, np.concatenate(ids), id_to_piece)
+        print("%s sheet snippet codes of %d pieces collected" % (codes.shape[0], len(pieces)))
+
+    # -- memory-mappable DB directories (sharded loading for multi-GPU serving) -------------------
+    @staticmethod
+    def save_db_dir(path, codes, ids, id_to_name):
+        """codes.npy (n,32) float32 | ids.npy (n,) int32 | meta.json; both arrays can be np.load(mmap_mode='r')-ed."""
+        os.makedirs(path, exist_ok=True)
+        np.save(os.path.join(path, "codes.npy"), np.ascontiguousarray(codes, np.float32))
+        np.save(os.path.join(path, "ids.npy"), np.ascontiguousarray(ids, np.int32))
+        with open(os.path.join(path, "meta.json"), "w") as fp:
+            json.dump({"n": int(len(ids)), "dim": int(codes.shape[1]),
+                       "id_to_name": {str(k): v for k, v in id_to_name.items()}}, fp)
+
+    @staticmethod
+    def load_db_dir(path, rank=0, world=1):
+        """-> (codes rows [lo,hi) of this rank, ALL ids, id_to_name, lo).  Only the shard's rows are read."""
+        meta = json.load(open(os.path.join(path, "meta.json")))
+        codes = np.load(os.path.join(path, "codes.npy"), mmap_mode="r")
+        ids = np.load(os.path.join(path, "ids.npy"))
+        lo, hi = meta["n"] * rank // world, meta["n"] * (rank + 1) // world
+        return np.ascontiguousarray(codes[lo:hi]), ids, {int(k): v for k, v in meta["id_to_name"].items()}, lo
 
     def load_sheet_db_file(self, sheet_db_path):
         """ load sheet codes (:496-501) """
@@ -128,6 +211,31 @@ class AudioSheetServer(object):
             sheet_snippets[i, 0] = sheet[r0:r1, idx:idx + self.sheet_shape[1]]
         sheet_codes = self.embed_network.compute_view_1(sheet_snippets)
         return self._vote(self._audio_db, sheet_codes, self.id_to_perform, top_k, n_candidates, verbose)
+
+    # -- streaming identification (the vote of `run`, :118-138, without the GUI) ----------------------
+    def reset_stream(self):
+        self._stream_ids = np.zeros(0, dtype=np.int64)
+
+    def process_frame(self, running_spec, top_k=5, n_candidates=25, running_frames=100):
+        """One step of the streaming loop: embed the current (92, 42) window, retrieve n_candidates sheet
+        snippets, vote over the ids of the last `running_frames` frames.  -> (names, probabilities)."""
+        if not hasattr(self, "_stream_ids"):
+            self.reset_stream()
+        spec_code = self.embed_network.compute_view_2(running_spec[np.newaxis, np.newaxis, :, :])
+        piece_ids, _ = self._retrieve_sheet_snippet_ids(spec_code, n_candidates=n_candidates)
+        self._stream_ids = np.concatenate((self._stream_ids, piece_ids))
+        first_idx = running_frames * n_candidates
+        if running_frames is not None and self._stream_ids.shape[0] > first_idx:
+            self._stream_ids = self._stream_ids[-first_idx:]
+        dev = self._sheet_db.device
+        ids_dev = torch.as_tensor(self._stream_ids.astype(np.int32)).to(dev)
+        rows = torch.arange(len(self._stream_ids), dtype=torch.int64, device=dev).view(1, -1)
+        from .retrieval import vote_device
+        out_ids, out_cnt = vote_device(rows, ids_dev, top_k)           # row -> id table = the window itself
+        out_ids, out_cnt = out_ids[0].cpu().numpy(), out_cnt[0].cpu().numpy()
+        keep = out_ids >= 0
+        probs = out_cnt[keep].astype(float) / len(self._stream_ids)
+        return [self.id_to_piece[i] for i in out_ids[keep]], probs
 
     # -- batched identification over many recordings (config "piece identification") -----------
     def identify_from_codes(self, query_codes, n_recordings, top_k=1, n_candidates=25, direction="A2S"):

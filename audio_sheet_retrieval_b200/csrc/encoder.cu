@@ -508,6 +508,22 @@ __global__ void ref_pool_kernel(const float *__restrict__ in, int nc, int H, int
     out[i] = fmaxf(fmaxf(ip[0], ip[1]), fmaxf(ip[W], ip[W + 1]));
 }
 
+// --------------------------------------------------------------------------------------
+// window extraction: out[i] = src[r0 : r0+win_h, starts[i] : starts[i]+win_w]
+// (audio_sheet_retrieval/audio_sheet_server.py:216-223, 260-271, 421-428, 465-477)
+// --------------------------------------------------------------------------------------
+template <typename T>
+__global__ void extract_windows_kernel(const T *__restrict__ src, int src_w, const int *__restrict__ starts, int r0,
+                                       int win_h, int win_w, T *__restrict__ out) {
+    const int i = blockIdx.y;
+    const int start = starts[i];
+    T *o = out + (size_t)i * win_h * win_w;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < win_h * win_w; e += gridDim.x * blockDim.x) {
+        const int y = e / win_w, x = e - y * win_w;
+        o[e] = src[(size_t)(r0 + y) * src_w + start + x];
+    }
+}
+
 }  // namespace asr
 
 using namespace asr;
@@ -943,6 +959,25 @@ int asr_encoder_debug_activation(asr_encoder_t *e, int layer, int path, int64_t 
                     memcpy(&f, &bits, 4);
                     out_host[(((size_t)s * g.cout + ch) * g.Ho + y) * g.Wo + x] = f;
                 }
+    return ASR_OK;
+}
+
+int asr_extract_windows(const void *src_dev, int dtype, int src_h, int src_w, const int32_t *starts_dev, int n, int r0,
+                        int win_h, int win_w, void *out_dev, void *stream) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    ASR_CHECK_ARG(src_dev && starts_dev && out_dev, "NULL buffer");
+    ASR_CHECK_ARG(dtype == ASR_IN_F32 || dtype == ASR_IN_U8, "bad dtype");
+    ASR_CHECK_ARG(r0 >= 0 && win_h >= 1 && win_w >= 1 && r0 + win_h <= src_h && win_w <= src_w, "window does not fit");
+    if (n == 0) return ASR_OK;
+    dim3 grid((win_h * win_w + 255) / 256, (unsigned)n);
+    if (dtype == ASR_IN_U8)
+        extract_windows_kernel<uint8_t><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const uint8_t *>(src_dev), src_w, starts_dev, r0, win_h, win_w, reinterpret_cast<uint8_t *>(out_dev));
+    else
+        extract_windows_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const float *>(src_dev), src_w, starts_dev, r0, win_h, win_w, reinterpret_cast<float *>(out_dev));
+    ASR_LAUNCH_CHECK();
     return ASR_OK;
 }
 

@@ -93,6 +93,13 @@ int asr_encoder_embed(asr_encoder_t *enc, const void *x_dev, int x_dtype, int64_
  * Blocks until the results are in codes_host / latents_host. */
 int asr_encoder_embed_host(asr_encoder_t *enc, const void *x_host, int x_dtype, int64_t n,
                            float *codes_host, float *latents_host, int path);
+/* Cut n windows out of one unrolled sheet image / spectrogram resident on the device:
+ * out[i] = src[r0 : r0+win_h, starts[i] : starts[i]+win_w]  (the slicing loops of
+ * asr/audio_sheet_server.py:216-223, 260-271, 421-428, 465-477).  src (src_h, src_w) and out
+ * (n, win_h, win_w) have element type `dtype` (ASR_IN_F32 / ASR_IN_U8); every start must satisfy
+ * 0 <= start <= src_w - win_w (not checked on the device). */
+int asr_extract_windows(const void *src_dev, int dtype, int src_h, int src_w, const int32_t *starts_dev, int n, int r0,
+                        int win_h, int win_w, void *out_dev, void *stream);
 /* debug: copy layer `layer`'s activation (after ELU/pool) of the last embed call to host as
  * NCHW float32 (n, c, h, w); returns c,h,w through the out params. */
 int asr_encoder_debug_activation(asr_encoder_t *enc, int layer, int path, int64_t n, float *out_host,

@@ -122,3 +122,67 @@ def test_detect_score_end_to_end():
     srv.set_sheet_db(np.concatenate(codes), np.array(ids), dict((i, "rec%d" % i) for i in range(4)))
     names, votes = srv.detect_score(specs[2], top_k=3, n_candidates=5)
     assert names[0] == "rec2" and votes[0] > 0.5 and abs(votes.sum() - 1.0) < 1e-12
+
+
+def test_db_from_raw_material_matches_reference_loop(tmp_path):
+    """initialize_*_db_from_* (audio_sheet_server.py:403-494): same window grid, same codes, same ids."""
+    from audio_sheet_retrieval_b200.audio_sheet_server import AudioSheetServer, extract_windows_device
+    from audio_sheet_retrieval_b200.models import mutopia_ccal_cont_rsz as model
+    import torch
+    rng = np.random.RandomState(3)
+    srv = AudioSheetServer()
+    srv.initialize_embedding_network(model, PKL)
+    specs = [np.abs(rng.normal(0, 0.3, (92, T))).astype(np.float32) for T in (300, 173, 95)]
+    scores = [rng.randint(0, 256, (H, Wd)).astype(np.uint8) for H, Wd in ((180, 900), (160, 451), (200, 260))]
+    # windows are cut bit-exactly
+    w = extract_windows_device(torch.as_tensor(scores[0]).cuda(), [0, 50, 700], 10, 160, 200).cpu().numpy()
+    assert (w[1, 0] == scores[0][10:170, 50:250]).all() and (w[2, 0] == scores[0][10:170, 700:900]).all()
+    srv.initialize_audio_db_from_specs(["a", "b", "c"], specs)
+    srv.initialize_sheet_db_from_imges(["a", "b", "c"], scores)
+    onet = OracleNet("mutopia_ccal_cont_rsz", load_param_list(PKL))
+    ref_codes, ref_ids = [], []
+    for pi, sp in enumerate(specs):
+        idx = np.arange(0, sp.shape[1] - 42, 42 // 4)
+        ref_codes.append(onet.compute_view_2(np.stack([sp[None, :, i:i + 42] for i in idx])))
+        ref_ids += [pi] * len(idx)
+    ref_codes = np.concatenate(ref_codes)
+    assert (srv.perform_excerpt_ids == np.array(ref_ids)).all()
+    assert _cos(srv.perform_excerpt_codes, ref_codes).min() >= 0.999
+    ref_codes, ref_ids = [], []
+    for pi, im in enumerate(scores):
+        idx = np.arange(0, im.shape[1] - 200, 200 // 4)
+        r0 = im.shape[0] // 2 - 80
+        ref_codes.append(onet.compute_view_1(np.stack([im[None, r0:r0 + 160, i:i + 200] for i in idx]).astype(np.float32)))
+        ref_ids += [pi] * len(idx)
+    assert (srv.sheet_snippet_ids == np.array(ref_ids)).all()
+    assert _cos(srv.sheet_snippet_codes, np.concatenate(ref_codes)).min() >= 0.999
+    # DB directory round trip, sharded
+    AudioSheetServer.save_db_dir(str(tmp_path / "db"), srv.sheet_snippet_codes, srv.sheet_snippet_ids, srv.id_to_piece)
+    parts = [AudioSheetServer.load_db_dir(str(tmp_path / "db"), r, 3) for r in range(3)]
+    assert (np.concatenate([p[0] for p in parts]) == srv.sheet_snippet_codes).all()
+    assert parts[1][3] == len(srv.sheet_snippet_ids) // 3 and parts[0][2] == {0: "a", 1: "b", 2: "c"}
+
+
+def test_streaming_vote_matches_reference_loop():
+    """The vote of AudioSheetServer.run (:118-138) restated with NumPy vs process_frame."""
+    from audio_sheet_retrieval_b200.audio_sheet_server import AudioSheetServer
+    from audio_sheet_retrieval_b200.models import mutopia_ccal_cont_rsz as model
+    from oracle import search
+    rng = np.random.RandomState(4)
+    srv = AudioSheetServer()
+    srv.initialize_embedding_network(model, PKL)
+    db = rng.normal(size=(600, 32)).astype(np.float32)
+    ids = np.repeat(np.arange(12), 50)
+    srv.set_sheet_db(db, ids, dict((i, "p%d" % i) for i in range(12)))
+    spec = np.abs(rng.normal(0, 0.3, (92, 42 + 12))).astype(np.float32)
+    all_ids = np.zeros(0, dtype=np.int64)
+    srv.reset_stream()
+    for f in range(12):
+        win = spec[:, f:f + 42]
+        names, probs = srv.process_frame(win, top_k=4, n_candidates=5, running_frames=6)
+        code = srv.embed_network.compute_view_2(win[None, None])
+        _, idx = search.pinned_topk(code, db, 5)
+        all_ids = np.concatenate((all_ids, ids[idx[0]]))[-30:]
+        ref_ids, ref_votes, _ = search.vote_ref(all_ids, 4)
+        assert names == ["p%d" % i for i in ref_ids]
+        np.testing.assert_allclose(probs, ref_votes / float(len(all_ids)), atol=1e-12)
