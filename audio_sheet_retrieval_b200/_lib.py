@@ -52,6 +52,10 @@ def _load():
     lib.asr_encoder_embed_host.argtypes = [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int]
     lib.asr_encoder_debug_activation.argtypes = [c_void_p, c_int, c_int, c_int64, c_void_p,
                                                  POINTER(c_int), POINTER(c_int), POINTER(c_int)]
+    lib.asr_cosine_distances.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]
+    lib.asr_cosine_distances.restype = c_int
+    lib.asr_dtw.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.asr_dtw.restype = c_int
     lib.asr_extract_windows.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                         c_void_p]
     lib.asr_extract_windows.restype = c_int

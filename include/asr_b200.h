@@ -167,6 +167,17 @@ int asr_cca_solve(const double *sums_dev, int64_t n_total, const float *shift1_d
                   double r1, double r2, double rT, int mode, double *m1_dev, double *m2_dev,
                   double *U_dev, double *V_dev, double *sigma_dev, void *stream);
 
+/* ------------------------------------------------------------------------- *
+ * Alignment (SURVEY 8f "next" row 3).  Replaces cdist(img_codes, spec_codes, 'cosine')
+ * (asr/utils/alignment.py:149) and dtw_by_dist (asr/utils/dtw_by_dist.py:6-34, 69-83).
+ * ------------------------------------------------------------------------- */
+/* out_dev (r,c) float64 cosine distances between a (r,32) and b (c,32) float32 */
+int asr_cosine_distances(const float *a_dev, int r, const float *b_dev, int c, double *out_dev, void *stream);
+/* dist_dev (r,c) float64 -> acc_dev (r,c) accumulated cost; warp path (i,j) from (0,0) to (r-1,c-1) in
+ * path_i_dev / path_j_dev (capacity r+c-1 each), its length in path_len_dev.  Ties: diag, then up, then left. */
+int asr_dtw(const double *dist_dev, int r, int c, double *acc_dev, int32_t *path_i_dev, int32_t *path_j_dev,
+            int32_t *path_len_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

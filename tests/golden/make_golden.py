@@ -184,6 +184,40 @@ def main():
     out["srv_p_names"] = np.array([int(n.split("_")[1]) for n in names])
     out["srv_p_votes"] = votes
 
+    # ---- DTW alignment (asr/utils/dtw_by_dist.py:6-34,69-83 ; asr/utils/alignment.py:113-174) ----
+    gd = {"__name__": "ref_dtw"}
+    exec(compile(_src("utils/dtw_by_dist.py"), "ref:utils/dtw_by_dist.py", "exec"), gd)
+    ref_dtw = gd["dtw_by_dist"]
+    for tag, shape in (("a", (60, 45)), ("b", (40, 70))):            # "b" exercises the transposition branch
+        d = np.abs(rng.normal(size=shape)) + 0.3 * np.abs(np.subtract.outer(np.arange(shape[0]) / shape[0],
+                                                                             np.arange(shape[1]) / shape[1]))
+        md, C, D1, path = ref_dtw(d.copy())
+        out["dtw_%s_dist" % tag] = d
+        out["dtw_%s_min" % tag] = np.array([md])
+        out["dtw_%s_acc" % tag] = D1
+        out["dtw_%s_p0" % tag], out["dtw_%s_p1" % tag] = np.asarray(path[0]), np.asarray(path[1])
+    from scipy.spatial.distance import cdist as _cdist
+    from scipy.interpolate import interp1d as _interp1d
+    sys.modules["dtw_by_dist"] = types.SimpleNamespace(dtw_by_dist=ref_dtw)     # `from dtw_by_dist import ...`
+    ga = {"np": NP, "xrange": range, "cdist": _cdist, "interp1d": _interp1d}
+    asrc = _src("utils/alignment.py")
+    for name in ("align_baseline", "align_pydtw", "compute_alignment", "estimate_alignment_error"):
+        exec(compile(_slice_def(asrc, name), "ref:" + name, "exec"), ga)
+    from oracle.align import synth_alignment_problem
+    img, spec, true_idx = synth_alignment_problem(120, 90, seed=3)
+    sheet_idxs = np.arange(120) * 5 + 100
+    spec_idxs = np.arange(90) * 2 + 10
+    mapping, res = ga["compute_alignment"](img, spec, sheet_idxs, spec_idxs, "pydtw")
+    out["al_img"], out["al_spec"], out["al_true"] = img, spec, true_idx
+    out["al_dists"] = res["dists"]
+    out["al_aligned"] = res["aligned_sheet_idxs"]
+    out["al_map_k"] = np.array(sorted(mapping.keys()))
+    out["al_map_v"] = np.array([mapping[k] for k in sorted(mapping.keys())])
+    err = ga["estimate_alignment_error"](sheet_idxs[true_idx].astype(float), spec_idxs, mapping)
+    out["al_err"] = err
+    mapping_b, res_b = ga["compute_alignment"](img, spec, sheet_idxs, spec_idxs, "baseline")
+    out["al_b_aligned"] = res_b["aligned_sheet_idxs"]
+
     np.savez_compressed(os.path.join(OUT, "reference_numpy_paths.npz"), **out)
     print("wrote", os.path.join(OUT, "reference_numpy_paths.npz"), sorted(out))
 

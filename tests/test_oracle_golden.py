@@ -138,3 +138,16 @@ def test_prepare_rsz_is_box_mean():
     a = prepare_rsz(x)
     b = (x / np.float32(255)).reshape(3, 1, 80, 2, 100, 2).mean(axis=(3, 5))
     assert np.abs(a - b).max() < 2e-7
+
+
+def test_dtw_matches_reference(golden):
+    from oracle import align
+    for t in "ab":
+        md, C, D1, path = align.dtw_by_dist(golden["dtw_%s_dist" % t].copy())
+        assert md == golden["dtw_%s_min" % t][0]
+        assert (D1 == golden["dtw_%s_acc" % t]).all()
+        assert (path[0] == golden["dtw_%s_p0" % t]).all() and (path[1] == golden["dtw_%s_p1" % t]).all()
+    m, r = align.compute_alignment(golden["al_img"], golden["al_spec"], np.arange(120) * 5 + 100,
+                                   np.arange(90) * 2 + 10, "pydtw")
+    assert (r["aligned_sheet_idxs"] == golden["al_aligned"]).all()
+    np.testing.assert_allclose([m[k] for k in sorted(m)], golden["al_map_v"], atol=1e-12)
