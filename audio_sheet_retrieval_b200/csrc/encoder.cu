@@ -51,6 +51,7 @@ struct ConvPlan {
     int stage_bytes;    // 16 (front guard) + KC*sps + tail slack
     int wbytes, staging_bytes, smem_bytes;
     int off_bias, off_stage, off_staging, off_bar;
+    unsigned wp_magic;
 };
 
 struct ConvParams {
@@ -320,7 +321,8 @@ __device__ __forceinline__ float l0_fetch(const L0Params &p, const uint8_t *xu, 
 }
 
 constexpr int L0_MAXC = 32;
-constexpr int L0_TW = 32, L0_TH = 8;    // pixels per block
+constexpr int L0_TW = 32, L0_TROWS = 8, L0_PIX = 4;   // 32 x 8 threads, each computes 4 vertically adjacent pixels
+constexpr int L0_TH = L0_TROWS * L0_PIX;                // 32 x 32 pixels per block
 
 // Folded weights travel in the kernel parameter block (constant bank): with the channel loops fully
 // unrolled every FFMA takes its weight straight from c[0][..], no load instruction.
@@ -330,7 +332,7 @@ struct L0Weights {
 };
 
 template <int C>   // C > 0: compile-time channel count; C == 0: run-time p.C
-__global__ void __launch_bounds__(L0_TW * L0_TH) l0_conv_kernel(const L0Params p, const L0Weights wt) {
+__global__ void __launch_bounds__(L0_TW * L0_TROWS) l0_conv_kernel(const L0Params p, const L0Weights wt) {
     __shared__ float tile[L0_TH + 2][L0_TW + 2];
     const int tid = threadIdx.x;
     const int n = blockIdx.z;
@@ -338,45 +340,56 @@ __global__ void __launch_bounds__(L0_TW * L0_TH) l0_conv_kernel(const L0Params p
     const size_t in_off = (size_t)n * p.Hin * p.Win;
     const uint8_t *xu = reinterpret_cast<const uint8_t *>(p.x) + in_off;
     const float *xf = reinterpret_cast<const float *>(p.x) + in_off;
-    for (int i = tid; i < (L0_TH + 2) * (L0_TW + 2); i += L0_TW * L0_TH) {
+    for (int i = tid; i < (L0_TH + 2) * (L0_TW + 2); i += L0_TW * L0_TROWS) {
         const int ty = i / (L0_TW + 2), tx = i - ty * (L0_TW + 2);
         tile[ty][tx] = l0_fetch(p, xu, xf, y0 + ty - 1, x0 + tx - 1);
     }
     __syncthreads();
-    const int ty = tid / L0_TW, tx = tid - ty * L0_TW;
-    const int y = y0 + ty, x = x0 + tx;
-    if (y >= p.H || x >= p.W) return;
-    float v[9];
-#pragma unroll
-    for (int t = 0; t < 9; ++t) v[t] = tile[ty + t / 3][tx + t % 3];
-    uint8_t *out_px = reinterpret_cast<uint8_t *>(p.out) + (long long)n * p.out_sample +
-                      ((long long)(y + 1) * p.Wp + x + 1) * 16;
+    const int tr = tid / L0_TW, tx = tid - tr * L0_TW;
+    const int x = x0 + tx;
+    if (x >= p.W) return;
     constexpr int NCH_T = C > 0 ? (C + 15) / 16 * 2 : 0;
     const int nch = C > 0 ? NCH_T : p.NCH;
     const int cc = C > 0 ? C : p.C;
+    // sliding 3-row window over the thread's 4 pixels
+    float v[9];
 #pragma unroll
-    for (int ch = 0; ch < (C > 0 ? NCH_T : 4); ++ch) {
-        if (ch < nch) {
-            uint32_t pk[4];
+    for (int t = 0; t < 6; ++t) v[3 + t] = tile[tr * L0_PIX + t / 3][tx + t % 3];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float r[2];
+    for (int py = 0; py < L0_PIX; ++py) {
+        const int ty = tr * L0_PIX + py, y = y0 + ty;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int c = ch * 8 + 2 * j + h;
-                    float acc = 0.f;
-                    if (c < cc) {
-                        acc = wt.b[c];
+        for (int t = 0; t < 6; ++t) v[t] = v[t + 3];
 #pragma unroll
-                        for (int t = 0; t < 9; ++t) acc = fmaf(v[t], wt.w[c * 9 + t], acc);
-                        acc = elu_f(acc);
+        for (int t = 0; t < 3; ++t) v[6 + t] = tile[ty + 2][tx + t];
+        if (y < p.H) {
+            uint8_t *out_px = reinterpret_cast<uint8_t *>(p.out) + (long long)n * p.out_sample +
+                              ((long long)(y + 1) * p.Wp + x + 1) * 16;
+#pragma unroll
+            for (int ch = 0; ch < (C > 0 ? NCH_T : 4); ++ch) {
+                if (ch < nch) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float r[2];
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int c = ch * 8 + 2 * j + h;
+                            float acc = 0.f;
+                            if (c < cc) {
+                                acc = wt.b[c];
+#pragma unroll
+                                for (int t = 0; t < 9; ++t) acc = fmaf(v[t], wt.w[c * 9 + t], acc);
+                                acc = elu_f(acc);
+                            }
+                            r[h] = acc;
+                        }
+                        __nv_bfloat162 hh = __floats2bfloat162_rn(r[0], r[1]);
+                        pk[j] = *reinterpret_cast<uint32_t *>(&hh);
                     }
-                    r[h] = acc;
+                    *reinterpret_cast<uint4 *>(out_px + (long long)ch * p.out_plane) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
-                __nv_bfloat162 hh = __floats2bfloat162_rn(r[0], r[1]);
-                pk[j] = *reinterpret_cast<uint32_t *>(&hh);
             }
-            *reinterpret_cast<uint4 *>(out_px + (long long)ch * p.out_plane) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
     }
 }
@@ -552,9 +565,11 @@ struct asr_encoder {
     float *ref_w[8] = {nullptr}, *ref_bn[8] = {nullptr};
     float *ref_in = nullptr, *ref_act[8] = {nullptr}, *ref_tmp = nullptr;
     int last_path = -1;
+    int64_t l01_chunk = 0;          // samples per layer-0/layer-1 sub-chunk (0 = whole batch)
     // optional per-group device timing (bench.py roofline): events around [layer 0], [layers 1..7], [head]
     bool timing = false;
-    std::vector<cudaEvent_t> ev_pool;
+    std::vector<cudaEvent_t> ev_pool;     // pairs (start, stop)
+    std::vector<int> ev_cat;              // category of pair i: 0 layer 0, 1 tcgen05 conv, 2 head
     size_t ev_used = 0;
     // host-buffer entry
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
@@ -602,18 +617,24 @@ static bool plan_conv(const LayerGeom &g, ConvPlan &pl) {
     pl.off_staging = off; off += pl.staging_bytes; off = (off + 127) / 128 * 128;
     pl.off_bar = off; off += 256;
     pl.smem_bytes = off;
+    pl.wp_magic = (unsigned)((0x100000000ull + (unsigned)Wp - 1) / (unsigned)Wp);
+    for (unsigned o = 0; o < (unsigned)pl.MT * 128u; ++o)       // fast division must be exact for every o the kernel sees
+        if ((unsigned)(((unsigned long long)o * pl.wp_magic) >> 32) != o / (unsigned)Wp) return false;
     return off <= SMEM_LIMIT;
 }
 
 static int pad16(int c) { return (c + 15) / 16 * 16; }
 
-static void mark(asr_encoder *e, cudaStream_t st) {
+static void mark(asr_encoder *e, cudaStream_t st, int cat, bool start) {
     if (!e->timing) return;
     if (e->ev_used == e->ev_pool.size()) {
         cudaEvent_t ev;
         cudaEventCreate(&ev);
         e->ev_pool.push_back(ev);
+        e->ev_cat.push_back(0);
     }
+    if (start) e->ev_cat[e->ev_used / 2] = cat;
+    e->ev_cat.resize(std::max(e->ev_cat.size(), e->ev_pool.size()));
     cudaEventRecord(e->ev_pool[e->ev_used++], st);
 }
 
@@ -757,6 +778,13 @@ int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *d, int max_b
             E_CUDA(cudaMemcpy(e->wblob[l], blob.data(), blob.size(), cudaMemcpyHostToDevice));
         }
         // activations of both paths
+        if (l == 0) {
+            // Optional experiment (off by default): run layers 0 and 1 over sub-chunks that reuse one L2-sized
+            // region of the layer-0 buffer.  Measured on B200 it LOSES (479k -> 409k pairs/s at 128 samples,
+            // worse below): the small launches cost more than the HBM round trip they save.
+            long long c = getenv("ASR_L01_CHUNK") ? atoll(getenv("ASR_L01_CHUNK")) : 0;
+            e->l01_chunk = (c <= 0 || c >= max_batch) ? 0 : std::max<long long>(16, c / 16 * 16);
+        }
         e->act_plane[l] = (long long)(g.Ho + 2) * (g.Wo + 2) * 16;
         e->act_sample[l] = e->act_plane[l] * (g.coutp / 8);
         E_CUDA(cudaMalloc(&e->act[l], (size_t)e->act_sample[l] * B));
@@ -825,26 +853,27 @@ int asr_encoder_embed(asr_encoder_t *e, const void *x_dev, int x_dtype, int64_t 
     hp.codes = codes_dev; hp.latents = latents_dev;
     e->last_path = path;
     if (path == ASR_PATH_TCGEN05) {
-        mark(e, st);
-        {
+        auto launch_l0 = [&](int64_t n0, int64_t nn, bf16 *out) -> int {
             const LayerGeom &g = e->g[0];
             L0Params p;
-            p.x = x_dev; p.x_u8 = x_dtype == ASR_IN_U8; p.prepare = d.prepare;
+            const size_t esz = x_dtype == ASR_IN_U8 ? 1 : 4;
+            p.x = reinterpret_cast<const uint8_t *>(x_dev) + (size_t)n0 * d.in_h * d.in_w * esz;
+            p.x_u8 = x_dtype == ASR_IN_U8; p.prepare = d.prepare;
             p.Hin = d.in_h; p.Win = d.in_w; p.H = g.H; p.W = g.W; p.Wp = g.W + 2; p.Hp = g.H + 2;
-            p.C = g.cout; p.NCH = g.coutp / 8; p.w = e->l0_w; p.out = e->act[0];
-            p.out_plane = e->act_plane[0]; p.out_sample = e->act_sample[0]; p.n = (int)n;
-            dim3 grid((g.W + L0_TW - 1) / L0_TW, (g.H + L0_TH - 1) / L0_TH, (unsigned)n);
-            if (g.cout == 12) l0_conv_kernel<12><<<grid, L0_TW * L0_TH, 0, st>>>(p, e->l0_host);
-            else if (g.cout == 24) l0_conv_kernel<24><<<grid, L0_TW * L0_TH, 0, st>>>(p, e->l0_host);
-            else l0_conv_kernel<0><<<grid, L0_TW * L0_TH, 0, st>>>(p, e->l0_host);
+            p.C = g.cout; p.NCH = g.coutp / 8; p.w = e->l0_w; p.out = out;
+            p.out_plane = e->act_plane[0]; p.out_sample = e->act_sample[0]; p.n = (int)nn;
+            dim3 grid((g.W + L0_TW - 1) / L0_TW, (g.H + L0_TH - 1) / L0_TH, (unsigned)nn);
+            if (g.cout == 12) l0_conv_kernel<12><<<grid, L0_TW * L0_TROWS, 0, st>>>(p, e->l0_host);
+            else if (g.cout == 24) l0_conv_kernel<24><<<grid, L0_TW * L0_TROWS, 0, st>>>(p, e->l0_host);
+            else l0_conv_kernel<0><<<grid, L0_TW * L0_TROWS, 0, st>>>(p, e->l0_host);
             ASR_LAUNCH_CHECK();
-        }
-        mark(e, st);
-        for (int l = 1; l < 8; ++l) {
+            return ASR_OK;
+        };
+        auto launch_conv = [&](int l, const bf16 *in, bf16 *out, int64_t nn) -> int {
             const LayerGeom &g = e->g[l];
             const ConvPlan &pl = e->plan[l];
             ConvParams p;
-            p.in = e->act[l - 1]; p.out = e->act[l]; p.wblob = e->wblob[l]; p.n_samples = (int)n;
+            p.in = in; p.out = out; p.wblob = e->wblob[l]; p.n_samples = (int)nn;
             p.H = g.H; p.W = g.W; p.Wp = g.W + 2; p.Hp = g.H + 2; p.KC = g.cinp / 8; p.NP = g.coutp; p.NCH = g.coutp / 8;
             p.TH = pl.TH; p.bands = pl.bands; p.MT = pl.MT; p.pool = g.pool; p.cout = g.cout;
             p.Ho = g.Ho; p.Wo = g.Wo; p.Wpo = g.Wo + 2;
@@ -853,13 +882,8 @@ int asr_encoder_embed(asr_encoder_t *e, const void *x_dev, int x_dtype, int64_t 
             p.sps = pl.sps; p.stage_bytes = pl.stage_bytes; p.n_stages = pl.n_stages; p.slot_cols = pl.slot_cols;
             p.n_slots = pl.n_slots; p.tmem_cols = pl.tmem_cols; p.wbytes = pl.wbytes;
             p.off_bias = pl.off_bias; p.off_stage = pl.off_stage; p.off_staging = pl.off_staging; p.off_bar = pl.off_bar;
-            p.wp_magic = (unsigned)((0x100000000ull + (unsigned)p.Wp - 1) / (unsigned)p.Wp);
-            for (unsigned o = 0; o < (unsigned)pl.MT * 128u; ++o)
-                if ((unsigned)(((unsigned long long)o * p.wp_magic) >> 32) != o / (unsigned)p.Wp) {
-                    set_error("asr_encoder_embed: internal error (fast division)");
-                    return ASR_ERR_UNSUPPORTED;
-                }
-            const int items = (int)n * pl.bands;
+            p.wp_magic = pl.wp_magic;
+            const int items = (int)nn * pl.bands;
             const int grid = std::min(items, sm_count());
             switch (p.KC / 2) {
                 case 1: conv3x3_tc_kernel<1><<<grid, CONV_THREADS, pl.smem_bytes, st>>>(p); break;
@@ -871,8 +895,26 @@ int asr_encoder_embed(asr_encoder_t *e, const void *x_dev, int x_dtype, int64_t 
                 default: set_error("asr_encoder_embed: unsupported input channel count"); return ASR_ERR_UNSUPPORTED;
             }
             ASR_LAUNCH_CHECK();
+            return ASR_OK;
+        };
+        // Layers 0 and 1 can run over sub-chunks that reuse one region of the layer-0 buffer (see create).
+        const int64_t sub = e->l01_chunk > 0 ? e->l01_chunk : n;
+        for (int64_t n0 = 0; n0 < n; n0 += sub) {
+            const int64_t nn = std::min<int64_t>(sub, n - n0);
+            mark(e, st, 0, true);
+            if ((rc = launch_l0(n0, nn, e->act[0]))) return rc;
+            mark(e, st, 0, false);
+            mark(e, st, 1, true);
+            if ((rc = launch_conv(1, e->act[0], reinterpret_cast<bf16 *>(reinterpret_cast<uint8_t *>(e->act[1]) +
+                                                                           (size_t)n0 * e->act_sample[1]), nn)))
+                return rc;
+            mark(e, st, 1, false);
         }
-        mark(e, st);
+        mark(e, st, 1, true);
+        for (int l = 2; l < 8; ++l)
+            if ((rc = launch_conv(l, e->act[l - 1], e->act[l], n))) return rc;
+        mark(e, st, 1, false);
+        mark(e, st, 2, true);
         hp.in = e->act[7]; hp.is_p8 = 1; hp.plane = e->act_plane[7]; hp.sample = e->act_sample[7];
     } else {
         rc = ensure_ref_buffers(e);
@@ -901,7 +943,7 @@ int asr_encoder_embed(asr_encoder_t *e, const void *x_dev, int x_dtype, int64_t 
     }
     head_kernel<<<(unsigned)n, 128, 0, st>>>(hp);
     ASR_LAUNCH_CHECK();
-    if (path == ASR_PATH_TCGEN05) mark(e, st);
+    if (path == ASR_PATH_TCGEN05) mark(e, st, 2, false);
     return ASR_OK;
 }
 
@@ -915,14 +957,13 @@ int asr_encoder_set_timing(asr_encoder_t *e, int enable) {
 int asr_encoder_get_timing(asr_encoder_t *e, double *ms_layer0, double *ms_conv_tc, double *ms_head, int64_t *n_calls) {
     ASR_CHECK_ARG(e != nullptr, "NULL handle");
     double a = 0, b = 0, c = 0;
-    const size_t calls = e->ev_used / 4;
-    if (calls) ASR_CUDA(cudaEventSynchronize(e->ev_pool[e->ev_used - 1]));
-    for (size_t i = 0; i < calls; ++i) {
-        float t0 = 0, t1 = 0, t2 = 0;
-        ASR_CUDA(cudaEventElapsedTime(&t0, e->ev_pool[4 * i], e->ev_pool[4 * i + 1]));
-        ASR_CUDA(cudaEventElapsedTime(&t1, e->ev_pool[4 * i + 1], e->ev_pool[4 * i + 2]));
-        ASR_CUDA(cudaEventElapsedTime(&t2, e->ev_pool[4 * i + 2], e->ev_pool[4 * i + 3]));
-        a += t0; b += t1; c += t2;
+    const size_t pairs = e->ev_used / 2;
+    size_t calls = 0;
+    if (pairs) ASR_CUDA(cudaEventSynchronize(e->ev_pool[e->ev_used - 1]));
+    for (size_t i = 0; i < pairs; ++i) {
+        float t = 0;
+        ASR_CUDA(cudaEventElapsedTime(&t, e->ev_pool[2 * i], e->ev_pool[2 * i + 1]));
+        if (e->ev_cat[i] == 0) a += t; else if (e->ev_cat[i] == 1) b += t; else { c += t; ++calls; }
     }
     if (ms_layer0) *ms_layer0 = a;
     if (ms_conv_tc) *ms_conv_tc = b;
@@ -934,6 +975,8 @@ int asr_encoder_get_timing(asr_encoder_t *e, double *ms_layer0, double *ms_conv_
 
 int asr_encoder_debug_activation(asr_encoder_t *e, int layer, int path, int64_t n, float *out_host, int *c, int *h, int *w) {
     ASR_CHECK_ARG(e && layer >= 0 && layer < 8 && n >= 1 && n <= e->max_batch, "bad argument");
+    ASR_CHECK_ARG(!(layer == 0 && path == ASR_PATH_TCGEN05 && e->l01_chunk > 0 && n > e->l01_chunk),
+                  "layer-0 activations are only kept for the last sub-chunk");
     const LayerGeom &g = e->g[layer];
     if (c) *c = g.cout;
     if (h) *h = g.Ho;
