@@ -186,3 +186,28 @@ def test_streaming_vote_matches_reference_loop():
         ref_ids, ref_votes, _ = search.vote_ref(all_ids, 4)
         assert names == ["p%d" % i for i in ref_ids]
         np.testing.assert_allclose(probs, ref_votes / float(len(all_ids)), atol=1e-12)
+
+
+def test_config1_full_size_metrics_vs_oracle():
+    """BASELINE config 1 at its full size: 2 000 synthetic pairs, tutorial weights, both directions.
+    R@1/R@5/R@10/R@25 within 0.5 % absolute, MRR within 0.005, median rank within 0.5 % of N vs the
+    oracle's eval_retrieval on oracle embeddings (north_star tolerance)."""
+    from audio_sheet_retrieval_b200.models import mutopia_ccal_cont_rsz as model
+    from audio_sheet_retrieval_b200.retrieval_wrapper import RetrievalWrapper
+    from audio_sheet_retrieval_b200.utils.train_dcca_pool import eval_retrieval
+    from audio_sheet_retrieval_b200.utils.mutopia_data import SyntheticPairPool
+    n = 2000
+    X1, X2 = SyntheticPairPool(n, seed=23)[0:n]
+    w = RetrievalWrapper(model, PKL, prepare_view_1=model.prepare, prepare_view_2=None)
+    c1, c2 = w.compute_view_1(X1), w.compute_view_2(X2)
+    onet = OracleNet("mutopia_ccal_cont_rsz", load_param_list(PKL))
+    r1, r2 = onet.compute_view_1(X1), onet.compute_view_2(X2)
+    assert _cos(c1, r1).min() >= 0.999 and _cos(c2, r2).min() >= 0.999
+    for a, b, ra, rb in ((c1, c2, r1, r2), (c2, c1, r2, r1)):            # S2A and A2S
+        mr, med, md, hr, mrr = eval_retrieval(a, b)
+        mr_o, med_o, md_o, hr_o, mrr_o = metrics.eval_retrieval_ref(ra, rb)
+        for k in (1, 5, 10, 25):
+            assert abs(100.0 * hr[k] / n - 100.0 * hr_o[k] / n) <= 0.5
+        assert abs(mrr - mrr_o) <= 0.005
+        assert abs(med - med_o) <= 0.005 * n
+        assert abs(md - md_o) <= 5e-3          # mean diagonal cosine distance: bounded by the per-row embedding tolerance
