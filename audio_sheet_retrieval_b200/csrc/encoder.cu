@@ -31,6 +31,8 @@
 #include <cstring>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace asr {
@@ -51,7 +53,8 @@ struct ConvPlan {
     int stage_bytes;    // 16 (front guard) + KC*sps + tail slack
     int wbytes, staging_bytes, smem_bytes;
     int off_bias, off_stage, off_staging, off_bar;
-    unsigned wp_magic;
+    unsigned wp_magic, wo_magic;
+    int Hc;
 };
 
 struct ConvParams {
@@ -65,6 +68,9 @@ struct ConvParams {
     int sps, stage_bytes, n_stages, slot_cols, n_slots, tmem_cols, wbytes;
     int off_bias, off_stage, off_staging, off_bar;
     unsigned wp_magic;   // ceil(2^32 / Wp): o / Wp == __umulhi(o, wp_magic) for every o the kernel sees
+    unsigned wo_magic;   // same for the pooled width Wo (0 when Wo == 1)
+    int Hc;              // conv rows that are needed (H, or 2*Ho for a pooled layer)
+    int dbg;             // diagnostics only (env ASR_CONV_DEBUG): 1 = epilogue releases slots without draining, 2 = no MMAs
 };
 
 constexpr int N_MMA_WARPS = 4;           // tile tc is issued by MMA warp (tc & 3) and drained by epilogue group (tc & 3)
@@ -79,6 +85,11 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 // --------------------------------------------------------------------------------------
 // tcgen05 implicit-GEMM convolution (layers 1..7)
 // --------------------------------------------------------------------------------------
+// 128-position tiles of the band that starts at conv row y0 (the last band of a sample may be short)
+__device__ __forceinline__ int band_tiles(const ConvParams &p, int y0) {
+    return (min(p.TH, p.Hc - y0) * p.Wp + 127) >> 7;
+}
+
 template <int KPAIRS>
 __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(const ConvParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -151,16 +162,17 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(const ConvP
         const uint32_t wp = (uint32_t)p.Wp;
         mbar_wait(w_full, 0);
         int it = 0;
+        uint32_t tc0 = 0;      // running tile counter (same sequence in the MMA and the epilogue warps)
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const int s = it % p.n_stages;
             const uint32_t ph = (uint32_t)((it / p.n_stages) & 1);
+            const int mtb = band_tiles(p, (item % p.bands) * p.TH);
             mbar_wait(&in_full[s], ph);
             tc_fence_after();
             // descriptor of padded position -1 of the band (tap dy=-1, dx=-1 of output position 0)
             const uint32_t band_lo = (((smem_u32(stage_sm + (size_t)s * p.stage_bytes + 16) & 0x3FFFFu) >> 4) | a_lbo) - 1u;
             // my tiles of this band: tc0 + mt with (tc0 + mt) & 3 == my
-            const uint32_t tc0 = (uint32_t)it * (uint32_t)p.MT;
-            for (int mt = (int)((my - tc0) & (uint32_t)(N_MMA_WARPS - 1)); mt < p.MT; mt += N_MMA_WARPS) {
+            for (int mt = (int)((my - tc0) & (uint32_t)(N_MMA_WARPS - 1)); mt < mtb; mt += N_MMA_WARPS) {
                 const uint32_t tc = tc0 + (uint32_t)mt;
                 const uint32_t tile_lo = band_lo + (uint32_t)mt * 128u;
                 const uint32_t slot = tc & slot_mask;
@@ -174,7 +186,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(const ConvP
                     uint32_t a_lo = tile_lo + (uint32_t)(t / 3) * wp + (uint32_t)(t % 3);
 #pragma unroll
                     for (int kp = 0; kp < KPAIRS; ++kp) {
-                        tc_mma_bf16_pred(d_tmem, a_lo, b_lo, UMMA_DESC_HI, idesc, (t | kp) != 0 ? 1u : 0u, leader);
+                        tc_mma_bf16_pred(d_tmem, a_lo, b_lo, UMMA_DESC_HI, idesc, (t | kp) != 0 ? 1u : 0u,
+                                         (p.dbg & 2) ? 0u : leader);
                         a_lo += kstep_a;
                         b_lo += kstep_b;
                     }
@@ -182,6 +195,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(const ConvP
                 tc_commit_pred(&acc_full[slot], leader);
             }
             tc_commit_pred(&in_empty[s], leader);
+            tc0 += (uint32_t)mtb;
         }
     } else {
         // ================= epilogue: TMEM -> bias + ELU -> bf16 -> (pool) -> global =================
@@ -191,88 +205,117 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(const ConvP
         const int etid = tid - 32 * EPI_WARP0;   // 0..511
         mbar_wait(w_full, 0);                    // bias visible
         int it = 0;
+        uint32_t tc0 = 0;
         const int n_groups16 = (p.cout + 3) >> 2;     // 4-channel groups that hold real channels
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const int n = item / p.bands, y0 = (item % p.bands) * p.TH;
+            const int mtb = band_tiles(p, y0);
             uint8_t *out_n = reinterpret_cast<uint8_t *>(p.out) + (long long)n * p.out_sample;
-            const uint32_t tc0 = (uint32_t)it * (uint32_t)p.MT;
-            for (int mt = (int)((grp - tc0) & (uint32_t)(N_EPI_GROUPS - 1)); mt < p.MT; mt += N_EPI_GROUPS) {
+            for (int mt = (int)((grp - tc0) & (uint32_t)(N_EPI_GROUPS - 1)); mt < mtb; mt += N_EPI_GROUPS) {
                 const uint32_t tc = tc0 + (uint32_t)mt;
                 const uint32_t slot = tc & ((uint32_t)p.n_slots - 1u);
                 const uint32_t sph = (tc >> ((uint32_t)__ffs(p.n_slots) - 1u)) & 1u;
                 mbar_wait(&acc_full[slot], sph);
                 tc_fence_after();
                 const int o = mt * 128 + quarter * 32 + lane;       // padded raster position in the band
-                const int r = (int)__umulhi((unsigned)o, p.wp_magic), c = o - r * p.Wp;
-                const int y = y0 + r;
-                const bool in_band = r < p.TH;
-                const bool valid = in_band && c >= 1 && c <= p.W && y < p.H;
                 const uint32_t taddr = tmem_base + slot * (uint32_t)p.slot_cols + ((uint32_t)(quarter * 32) << 16);
-                for (int ng = 0; ng < p.NP / 16; ++ng) {
-                    float v[16];
-                    tmem_ld16(taddr + (uint32_t)(ng * 16), v);
-                    uint32_t pk[8];
+                if (p.pool) {
+                    // ELU and the bf16 rounding are monotone, so max-pool commutes with them: stage the raw
+                    // accumulators (fp16: 2^-12 relative, far below the bf16 output rounding) and apply
+                    // bias + ELU after the 2x2 max, on a quarter of the values.
+                    const bool in_band = o < p.TH * p.Wp;
+                    for (int ng = 0; ng < ((p.dbg & 1) ? 0 : p.NP / 16); ++ng) {
+                        float v[16];
+                        tmem_ld16(taddr + (uint32_t)(ng * 16), v);
+                        uint32_t pk[8];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (ng * 4 + j < n_groups16) {     // warp-uniform: padded channels stay exactly zero
-                            const float4 b4 = *reinterpret_cast<const float4 *>(&bias_sm[ng * 16 + 4 * j]);
-                            __nv_bfloat162 h0 = __floats2bfloat162_rn(elu_f(v[4 * j] + b4.x), elu_f(v[4 * j + 1] + b4.y));
-                            __nv_bfloat162 h1 = __floats2bfloat162_rn(elu_f(v[4 * j + 2] + b4.z), elu_f(v[4 * j + 3] + b4.w));
-                            pk[2 * j] = *reinterpret_cast<uint32_t *>(&h0);
-                            pk[2 * j + 1] = *reinterpret_cast<uint32_t *>(&h1);
-                        } else {
-                            pk[2 * j] = 0u;
-                            pk[2 * j + 1] = 0u;
+                        for (int j = 0; j < 8; ++j) {
+                            __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+                            pk[j] = *reinterpret_cast<uint32_t *>(&h);
                         }
-                    }
-                    if (p.pool) {
                         if (in_band) {
                             uint4 *d0 = reinterpret_cast<uint4 *>(staging_sm + ((size_t)(2 * ng) * p.TH * p.Wp + o) * 16);
                             uint4 *d1 = reinterpret_cast<uint4 *>(staging_sm + ((size_t)(2 * ng + 1) * p.TH * p.Wp + o) * 16);
                             *d0 = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                             *d1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                         }
-                    } else if (valid) {
-                        const long long pos = ((long long)(y + 1) * p.Wp + c) * 16;
-                        *reinterpret_cast<uint4 *>(out_n + (long long)(2 * ng) * p.out_plane + pos) =
-                            make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        *reinterpret_cast<uint4 *>(out_n + (long long)(2 * ng + 1) * p.out_plane + pos) =
-                            make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    }
+                } else {
+                    const int r = (int)__umulhi((unsigned)o, p.wp_magic), c = o - r * p.Wp;
+                    const int y = y0 + r;
+                    const bool valid = r < p.TH && c >= 1 && c <= p.W && y < p.H;
+                    for (int ng = 0; ng < ((p.dbg & 1) ? 0 : p.NP / 16); ++ng) {
+                        float v[16];
+                        tmem_ld16(taddr + (uint32_t)(ng * 16), v);
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (ng * 4 + j < n_groups16) {     // warp-uniform: padded channels stay exactly zero
+                                const float4 b4 = *reinterpret_cast<const float4 *>(&bias_sm[ng * 16 + 4 * j]);
+                                __nv_bfloat162 h0 = __floats2bfloat162_rn(elu_f(v[4 * j] + b4.x), elu_f(v[4 * j + 1] + b4.y));
+                                __nv_bfloat162 h1 = __floats2bfloat162_rn(elu_f(v[4 * j + 2] + b4.z), elu_f(v[4 * j + 3] + b4.w));
+                                pk[2 * j] = *reinterpret_cast<uint32_t *>(&h0);
+                                pk[2 * j + 1] = *reinterpret_cast<uint32_t *>(&h1);
+                            } else {
+                                pk[2 * j] = 0u;
+                                pk[2 * j + 1] = 0u;
+                            }
+                        }
+                        if (valid) {
+                            const long long pos = ((long long)(y + 1) * p.Wp + c) * 16;
+                            *reinterpret_cast<uint4 *>(out_n + (long long)(2 * ng) * p.out_plane + pos) =
+                                make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            *reinterpret_cast<uint4 *>(out_n + (long long)(2 * ng + 1) * p.out_plane + pos) =
+                                make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                        }
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[slot]);
             }
-            if (p.pool) {
+            tc0 += (uint32_t)mtb;
+            if (p.pool && !(p.dbg & 1)) {
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");   // band staged
-                const int prow = p.TH / 2;
-                const int total = p.NCH * prow * p.Wo;
-                for (int e = etid; e < total; e += EPI_THREADS) {
-                    const int ch = e / (prow * p.Wo);
-                    const int rem = e - ch * prow * p.Wo;
-                    const int pr = rem / p.Wo, pc = rem - pr * p.Wo;
-                    const int yo = y0 / 2 + pr;
-                    if (yo < p.Ho) {
-                        const uint8_t *b = staging_sm + ((size_t)ch * p.TH * p.Wp + (size_t)(2 * pr) * p.Wp + 1 + 2 * pc) * 16;
-                        uint4 q00 = *reinterpret_cast<const uint4 *>(b);
-                        uint4 q01 = *reinterpret_cast<const uint4 *>(b + 16);
-                        uint4 q10 = *reinterpret_cast<const uint4 *>(b + (size_t)p.Wp * 16);
-                        uint4 q11 = *reinterpret_cast<const uint4 *>(b + (size_t)p.Wp * 16 + 16);
-                        uint4 o4;
-                        const uint32_t *a0 = &q00.x, *a1 = &q01.x, *a2 = &q10.x, *a3 = &q11.x;
-                        uint32_t *oo = &o4.x;
+                const int per_ch = (p.TH / 2) * p.Wo;
+                const int yo0 = y0 / 2;
+                for (int ch = 0; ch < p.NCH; ++ch) {
+                    const int nreal = min(8, p.cout - 8 * ch);       // real channels of this chunk (<= 0: padding only)
+                    float bch[8];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            __nv_bfloat162 m0 = __hmax2(*reinterpret_cast<const __nv_bfloat162 *>(&a0[j]),
-                                                        *reinterpret_cast<const __nv_bfloat162 *>(&a1[j]));
-                            __nv_bfloat162 m1 = __hmax2(*reinterpret_cast<const __nv_bfloat162 *>(&a2[j]),
-                                                        *reinterpret_cast<const __nv_bfloat162 *>(&a3[j]));
-                            __nv_bfloat162 m = __hmax2(m0, m1);
-                            oo[j] = *reinterpret_cast<uint32_t *>(&m);
+                    for (int j = 0; j < 8; ++j) bch[j] = bias_sm[ch * 8 + j];
+                    const uint8_t *sch = staging_sm + (size_t)ch * p.TH * p.Wp * 16 + 16;
+                    uint8_t *och = out_n + (long long)ch * p.out_plane + 16;
+                    for (int e = etid; e < per_ch; e += EPI_THREADS) {
+                        const int pr = p.wo_magic ? (int)__umulhi((unsigned)e, p.wo_magic) : e;
+                        const int pc = e - pr * p.Wo;
+                        if (yo0 + pr < p.Ho) {
+                            uint4 o4 = make_uint4(0u, 0u, 0u, 0u);
+                            if (nreal > 0) {
+                                const uint8_t *b = sch + ((size_t)(2 * pr) * p.Wp + 2 * pc) * 16;
+                                const uint4 q00 = *reinterpret_cast<const uint4 *>(b);
+                                const uint4 q01 = *reinterpret_cast<const uint4 *>(b + 16);
+                                const uint4 q10 = *reinterpret_cast<const uint4 *>(b + (size_t)p.Wp * 16);
+                                const uint4 q11 = *reinterpret_cast<const uint4 *>(b + (size_t)p.Wp * 16 + 16);
+                                const uint32_t *a0 = &q00.x, *a1 = &q01.x, *a2 = &q10.x, *a3 = &q11.x;
+                                uint32_t *oo = &o4.x;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    if (2 * j < nreal) {          // warp-uniform; channel counts are multiples of 4... or 2
+                                        const __half2 m0 = __hmax2(*reinterpret_cast<const __half2 *>(&a0[j]),
+                                                                   *reinterpret_cast<const __half2 *>(&a1[j]));
+                                        const __half2 m1 = __hmax2(*reinterpret_cast<const __half2 *>(&a2[j]),
+                                                                   *reinterpret_cast<const __half2 *>(&a3[j]));
+                                        const float2 f = __half22float2(__hmax2(m0, m1));
+                                        const float r0 = elu_f(f.x + bch[2 * j]);
+                                        const float r1 = (2 * j + 1 < nreal) ? elu_f(f.y + bch[2 * j + 1]) : 0.f;
+                                        __nv_bfloat162 h = __floats2bfloat162_rn(r0, r1);
+                                        oo[j] = *reinterpret_cast<uint32_t *>(&h);
+                                    }
+                                }
+                            }
+                            *reinterpret_cast<uint4 *>(och + ((long long)(yo0 + pr + 1) * p.Wpo + pc) * 16) = o4;
                         }
-                        *reinterpret_cast<uint4 *>(out_n + (long long)ch * p.out_plane +
-                                                   ((long long)(yo + 1) * p.Wpo + pc + 1) * 16) = o4;
                     }
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");   // staging free again
@@ -587,17 +630,29 @@ static bool plan_conv(const LayerGeom &g, ConvPlan &pl) {
     pl.n_slots = std::min(MAX_SLOTS, 512 / pl.slot_cols);
     int cols = pl.n_slots * pl.slot_cols;
     pl.tmem_cols = cols <= 32 ? 32 : (cols <= 64 ? 64 : (cols <= 128 ? 128 : (cols <= 256 ? 256 : 512)));
-    const int th_max = g.pool ? (g.H & ~1) : g.H;
+    // rows of conv output that are needed: all of them, or the 2*Ho rows the pool reads
+    const int Hc = g.pool ? 2 * g.Ho : g.H;
     const int step = g.pool ? 2 : 1;
+    // Pick the band height: fewest 128-position tiles per sample (the MMA work), then fewest halo
+    // re-reads; two input stages whenever some band height fits with two.
     for (int ns = 2; ns >= 1; --ns) {
         int best = 0;
-        for (int th = step; th <= std::min(th_max, 16); th += step) {
+        long long best_cost = 0;
+        for (int th = step; th <= std::min(Hc, 64); th += step) {
             long long sps = (long long)(th + 2) * Wp * 16;
             long long stage = 16 + KC * sps + TAIL_SLACK;
             long long staging = g.pool ? (long long)NCH * th * Wp * 16 : 0;
             long long tot = pl.wbytes + NP * 4 + 128 + ns * stage + 128 + staging + 256 + 256;
-            if (sps / 16 >= 16384) continue;
-            if (tot <= SMEM_LIMIT) best = th;
+            if (sps / 16 >= 16384 || tot > SMEM_LIMIT) continue;
+            long long tiles = 0, rows_in = 0;
+            for (int y0 = 0; y0 < Hc; y0 += th) {
+                tiles += (std::min(th, Hc - y0) * Wp + 127) / 128;
+                rows_in += std::min(th, Hc - y0) + 2;
+            }
+            // Tiles first, halo as tie-break.  Pooled layers synchronise their epilogue warps per band, so
+            // for them fewer, taller bands win over a slightly lower tile count (measured on layer 3).
+            const long long cost = g.pool ? -th : tiles * 1000 + rows_in * 1000 / (Hc + 2);
+            if (!best || cost <= best_cost) { best = th; best_cost = cost; }
         }
         if (best) {
             pl.TH = best;
@@ -606,7 +661,7 @@ static bool plan_conv(const LayerGeom &g, ConvPlan &pl) {
         }
         if (ns == 1) return false;
     }
-    pl.bands = (g.H + pl.TH - 1) / pl.TH;
+    pl.bands = (Hc + pl.TH - 1) / pl.TH;
     pl.MT = (pl.TH * Wp + 127) / 128;
     pl.sps = (pl.TH + 2) * Wp * 16;
     pl.stage_bytes = ((16 + KC * pl.sps + TAIL_SLACK) + 127) / 128 * 128;
@@ -620,6 +675,13 @@ static bool plan_conv(const LayerGeom &g, ConvPlan &pl) {
     pl.wp_magic = (unsigned)((0x100000000ull + (unsigned)Wp - 1) / (unsigned)Wp);
     for (unsigned o = 0; o < (unsigned)pl.MT * 128u; ++o)       // fast division must be exact for every o the kernel sees
         if ((unsigned)(((unsigned long long)o * pl.wp_magic) >> 32) != o / (unsigned)Wp) return false;
+    pl.Hc = Hc;
+    pl.wo_magic = 0;
+    if (g.pool && g.Wo > 1) {
+        pl.wo_magic = (unsigned)((0x100000000ull + (unsigned)g.Wo - 1) / (unsigned)g.Wo);
+        for (unsigned e = 0; e < (unsigned)(pl.TH / 2 * g.Wo) + EPI_THREADS; ++e)
+            if ((unsigned)(((unsigned long long)e * pl.wo_magic) >> 32) != e / (unsigned)g.Wo) return false;
+    }
     return off <= SMEM_LIMIT;
 }
 
@@ -882,7 +944,9 @@ int asr_encoder_embed(asr_encoder_t *e, const void *x_dev, int x_dtype, int64_t 
             p.sps = pl.sps; p.stage_bytes = pl.stage_bytes; p.n_stages = pl.n_stages; p.slot_cols = pl.slot_cols;
             p.n_slots = pl.n_slots; p.tmem_cols = pl.tmem_cols; p.wbytes = pl.wbytes;
             p.off_bias = pl.off_bias; p.off_stage = pl.off_stage; p.off_staging = pl.off_staging; p.off_bar = pl.off_bar;
-            p.wp_magic = pl.wp_magic;
+            p.wp_magic = pl.wp_magic; p.wo_magic = pl.wo_magic; p.Hc = pl.Hc;
+            static const int conv_dbg = getenv("ASR_CONV_DEBUG") ? atoi(getenv("ASR_CONV_DEBUG")) : 0;
+            p.dbg = conv_dbg;
             const int items = (int)nn * pl.bands;
             const int grid = std::min(items, sm_count());
             switch (p.KC / 2) {
