@@ -193,6 +193,35 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// two 8-column groups at taddr and taddr + stride in one round trip (thread = lane = row)
+__device__ __forceinline__ void tmem_ld8x2(uint32_t taddr, uint32_t stride, float *v) {
+    uint32_t r[16];
+#pragma unroll
+    for (int g = 0; g < 2; ++g)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[8 * g]), "=r"(r[8 * g + 1]), "=r"(r[8 * g + 2]), "=r"(r[8 * g + 3]), "=r"(r[8 * g + 4]),
+                       "=r"(r[8 * g + 5]), "=r"(r[8 * g + 6]), "=r"(r[8 * g + 7])
+                     : "r"(taddr + (uint32_t)g * stride)
+                     : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// four 8-column groups at taddr + {0, 1, 2, 3} * stride in one round trip (thread = lane = row)
+__device__ __forceinline__ void tmem_ld8x4(uint32_t taddr, uint32_t stride, float *v) {
+    uint32_t r[32];
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[8 * g]), "=r"(r[8 * g + 1]), "=r"(r[8 * g + 2]), "=r"(r[8 * g + 3]), "=r"(r[8 * g + 4]),
+                       "=r"(r[8 * g + 5]), "=r"(r[8 * g + 6]), "=r"(r[8 * g + 7])
+                     : "r"(taddr + (uint32_t)g * stride)
+                     : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // 32 lanes x 64 consecutive fp32 columns -> 64 registers per thread (one round trip instead of four)
 __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float *v) {
     uint32_t r[64];
