@@ -707,6 +707,274 @@ __global__ void __launch_bounds__(L0_TW * L0_TROWS) l0_conv_kernel(const L0Param
 }
 
 // --------------------------------------------------------------------------------------
+// layer 0 on the tensor cores.  With Cin = 1 the 3x3 convolution is a banded (Toeplitz) product:
+//   D[g, (r, co)] = sum_dx sum_k A[g + dx, k] * B_dx[k, (r, co)],   B_dx[k, (r, co)] = w[co][dy = k - r][dx]
+// g runs over the padded columns of a batch of samples (raster over (sample, column): A row = one
+// pixel column, garbage at the two pad columns as in the raster conv kernel), k over 16 input rows,
+// r over the R0 output rows they support.  A holds, per pixel column, 8 vertically adjacent pixels
+// in 16 bytes -- the canonical K-major core-matrix row -- so the dx shift is again a descriptor
+// shift and no im2col is materialised.  Pixels and weights are split into bf16 hi + lo parts and
+// three products (hi*hi, lo*hi, hi*lo) are accumulated: ~2^-16 relative, i.e. fp32-grade for the
+// bf16 activations that follow, at an MMA cost that stays negligible next to the ELU epilogue.
+// One persistent CTA per SM: 8 converter warps (global -> hi/lo A tiles, one tile each in flight), one MMA
+// warp (9 MMAs per tile into one of two TMEM slots), 16 drain warps (warp = TMEM lane quarter x
+// row subset: bias + ELU + bf16 + P8 store).
+// --------------------------------------------------------------------------------------
+constexpr int L0T_PROD_WARPS = 8;                                   // converter warps; warp w converts every 8th tile
+constexpr int L0T_EPI_WARP0 = L0T_PROD_WARPS + 1;                    // warp 8 issues the MMAs
+constexpr int L0T_EPI_WARPS = 16;
+constexpr int L0T_THREADS = 32 * (L0T_EPI_WARP0 + L0T_EPI_WARPS);    // 800
+constexpr int L0T_AROWS = 136;      // 130 pixel columns of a tile + slack
+constexpr int L0T_NBUF = L0T_PROD_WARPS;   // one A tile (8.5 KB) per converter warp
+constexpr int L0T_SLOT_COLS = 256;
+
+struct L0TcParams {
+    L0Params b;                 // input description (x, dtype, prepare, sizes), output pointers
+    const uint8_t *blob;        // [dx][part: hi, lo][K chunk][NPAD][8] bf16, then C fp32 biases
+    int R0, NPAD;               // output rows per tile, padded N = R0 * C rounded up to 16
+    int TY;                     // row tiles per sample
+    int GT;                     // 128-column tiles over n * Wp raster columns
+    unsigned wp_magic;
+    int dbg;                    // diagnostics (env ASR_L0_DEBUG): 1 = no drain work, 2 = no input loads, 4 = no MMAs
+};
+
+// Converter, phase 1: issue the loads of 8 vertically adjacent pixels (image rows yb .. yb+7) of raster
+// column g.  Addresses are clamped so that every load is legal and none depends on a branch; `active`
+// predicates the loads of a thread that has no item.  raw[k][e]: e = 0 for a plain pixel, 0..3 for
+// the 2x2 box of ASR_PREP_SCALE_HALF.  Returns the validity mask of the column.
+template <int NE>
+__device__ __forceinline__ bool l0t_load8(const L0TcParams &q, long long g, int yb, bool active, float (*raw)[NE]) {
+    const L0Params &p = q.b;
+    const long long gc = g < 0 ? 0 : g;
+    const unsigned s = __umulhi((unsigned)gc, q.wp_magic);
+    const int xp = (int)((unsigned)gc - s * (unsigned)p.Wp);
+    const int x = xp - 1;
+    const bool col_ok = active && g >= 0 && (int)s < p.n && x >= 0 && x < p.W;
+    const size_t in_off = (size_t)min((int)s, p.n - 1) * p.Hin * p.Win;
+    const uint8_t *xu = reinterpret_cast<const uint8_t *>(p.x) + in_off;
+    const float *xf = reinterpret_cast<const float *>(p.x) + in_off;
+    const int xc = min(max(x, 0), p.W - 1);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int yc = min(max(yb + k, 0), p.H - 1);
+#pragma unroll
+        for (int e = 0; e < NE; ++e) raw[k][e] = 0.f;
+        if (active) {
+            if (NE == 4) {
+                const int o00 = 2 * yc * p.Win + 2 * xc;
+                if (p.x_u8) {
+                    raw[k][0] = xu[o00]; raw[k][1] = xu[o00 + 1];
+                    raw[k][NE - 2] = xu[o00 + p.Win]; raw[k][NE - 1] = xu[o00 + p.Win + 1];
+                } else {
+                    raw[k][0] = xf[o00]; raw[k][1] = xf[o00 + 1];
+                    raw[k][NE - 2] = xf[o00 + p.Win]; raw[k][NE - 1] = xf[o00 + p.Win + 1];
+                }
+            } else {
+                raw[k][0] = p.x_u8 ? (float)xu[yc * p.Win + xc] : xf[yc * p.Win + xc];
+            }
+        }
+    }
+    return col_ok;
+}
+// Converter, phase 2: `prepare` with the operation order of l0_fetch, then the border mask.  u8 / 255
+// comes from a 256-entry table of the correctly rounded quotients (same bits, no division sequence).
+template <int NE>
+__device__ __forceinline__ void l0t_finish8(const L0Params &p, const float *lut, bool col_ok, int yb, const float (*raw)[NE],
+                                            float *v) {
+    if (NE == 4) {
+        const float sc = 1.0f / 255.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            v[k] = ((raw[k][0] * sc + raw[k][1] * sc) + (raw[k][NE - 2] * sc + raw[k][NE - 1] * sc)) * 0.25f;
+    } else if (p.prepare == ASR_PREP_SCALE) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = p.x_u8 ? lut[(int)raw[k][0]] : raw[k][0] / 255.0f;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = raw[k][0];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (col_ok && yb + k >= 0 && yb + k < p.H) ? v[k] : 0.f;
+}
+
+// bf16 hi + lo split of 8 values -> the 16-byte K-major rows of the two A parts
+__device__ __forceinline__ void l0t_store8(uint8_t *a_buf, int c, int i, const float *v) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+        const float2 hf = __bfloat1622float2(h);
+        const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * k] - hf.x, v[2 * k + 1] - hf.y);
+        hi[k] = *reinterpret_cast<const uint32_t *>(&h);
+        lo[k] = *reinterpret_cast<const uint32_t *>(&l);
+    }
+    *reinterpret_cast<uint4 *>(a_buf + ((0 * 2 + c) * L0T_AROWS + i) * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4 *>(a_buf + ((1 * 2 + c) * L0T_AROWS + i) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// One converter warp builds whole A tiles (every L0T_PROD_WARPS-th tile of the CTA) in its own buffer:
+// 260 items (K chunk c, tile column i) = 9 per lane, in batches of three whose 24 loads are in flight
+// together (one item at a time for the 4-loads-per-pixel box filter); lanes walk along an image row.  Eight warps keep eight tiles in flight.
+template <int NE>
+__device__ __forceinline__ void l0t_convert(const L0TcParams &q, uint8_t *a_buf, const float *lut, uint64_t *a_ready,
+                                            uint64_t *a_free, int n_tiles, int cw) {
+    const L0Params &p = q.b;
+    const int lane = threadIdx.x & 31;
+    const bool off = (q.dbg & 2) != 0;
+    int k = cw;
+    for (int t = blockIdx.x + cw * (int)gridDim.x; t < n_tiles; t += L0T_PROD_WARPS * (int)gridDim.x, k += L0T_PROD_WARPS) {
+        const int gt = t / q.TY, ty = t - gt * q.TY;
+        const long long g0 = (long long)gt * 128 - 1;
+        const int y0 = ty * q.R0 - 1;
+        mbar_wait(a_free, (uint32_t)(((k / L0T_PROD_WARPS) & 1) ^ 1));
+        constexpr int U = NE == 1 ? 3 : 1;          // items whose loads are in flight together
+#pragma unroll 1
+        for (int batch = 0; batch < 9 / U; ++batch) {
+            float raw[U][8][NE];
+            bool ok[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int item = lane + 32 * (U * batch + u);
+                const int c = item >= 130 ? 1 : 0, i = item - 130 * c;
+                ok[u] = l0t_load8<NE>(q, g0 + i, y0 + 8 * c, item < 260 && !off, raw[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int item = lane + 32 * (U * batch + u);
+                const int c = item >= 130 ? 1 : 0, i = item - 130 * c;
+                float v[8];
+                l0t_finish8<NE>(p, lut, ok[u], y0 + 8 * c, raw[u], v);
+                if (item < 260) l0t_store8(a_buf, c, i, v);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready);
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(L0T_THREADS, 1) l0_tc_kernel(const L0TcParams q) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const L0Params &p = q.b;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int bbytes = 3 * 2 * 2 * q.NPAD * 16;
+    constexpr int ABUF = 2 * 2 * L0T_AROWS * 16;                    // [part][K chunk][L0T_AROWS][8] bf16
+    uint8_t *b_sm = smem;
+    uint8_t *a_sm = smem + bbytes;
+    float *bias_sm = reinterpret_cast<float *>(a_sm + L0T_NBUF * ABUF);
+    float *lut_sm = bias_sm + 32;                   // v / 255.0f for v = 0..255
+    uint64_t *bars = reinterpret_cast<uint64_t *>(lut_sm + 256);
+    uint64_t *a_ready = bars;                       // [NBUF] converters -> MMA warp
+    uint64_t *a_free = bars + L0T_NBUF;             // [NBUF] MMAs done reading the buffer
+    uint64_t *acc_full = bars + 2 * L0T_NBUF;       // [2]
+    uint64_t *acc_empty = bars + 2 * L0T_NBUF + 2;  // [2]
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 2 * L0T_NBUF + 4);
+
+    for (int i = tid; i < bbytes / 16; i += L0T_THREADS)
+        reinterpret_cast<uint4 *>(b_sm)[i] = reinterpret_cast<const uint4 *>(q.blob)[i];
+    if (tid < 32) bias_sm[tid] = tid < C ? reinterpret_cast<const float *>(q.blob + bbytes)[tid] : 0.f;
+    if (tid >= 64 && tid < 64 + 256) lut_sm[tid - 64] = (float)(tid - 64) / 255.0f;
+    if (tid == 0) {
+        for (int s = 0; s < L0T_NBUF; ++s) { mbar_init(&a_ready[s], 1); mbar_init(&a_free[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], L0T_EPI_WARPS); }
+        mbar_fence_init();
+    }
+    if (warp == L0T_PROD_WARPS) { tmem_alloc(tmem_ptr, 2 * L0T_SLOT_COLS); tmem_relinquish(); }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // weight matrices visible to the MMA
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const int n_tiles = q.GT * q.TY;
+
+    if (warp < L0T_PROD_WARPS) {
+        // ================= converters: A row i <-> raster column g0 - 1 + i; K element k <-> image row y0 - 1 + k
+        if (p.prepare == ASR_PREP_SCALE_HALF)
+            l0t_convert<4>(q, a_sm + warp * ABUF, lut_sm, &a_ready[warp], &a_free[warp], n_tiles, warp);
+        else
+            l0t_convert<1>(q, a_sm + warp * ABUF, lut_sm, &a_ready[warp], &a_free[warp], n_tiles, warp);
+    } else if (warp == L0T_PROD_WARPS) {
+        // ================= MMA issuer: per dx (A_hi, B_hi), (A_lo, B_hi), (A_hi, B_lo)
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(q.NPAD);
+            const uint32_t b0 = smem_u32(b_sm), b_part = 2 * q.NPAD * 16;
+            int k = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++k) {
+                const int buf = k % L0T_NBUF, slot = k & 1;
+                mbar_wait(&a_ready[buf], (uint32_t)((k / L0T_NBUF) & 1));
+                mbar_wait(&acc_empty[slot], (uint32_t)(((k >> 1) & 1) ^ 1));
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(a_sm + buf * ABUF);
+                const uint32_t d = tmem_base + (uint32_t)slot * L0T_SLOT_COLS;
+#pragma unroll
+                for (int dx = 0; dx < ((q.dbg & 4) ? 0 : 3); ++dx) {
+                    const uint64_t ah = umma_desc(a0 + dx * 16, L0T_AROWS * 16, 128);
+                    const uint64_t al = umma_desc(a0 + ABUF / 2 + dx * 16, L0T_AROWS * 16, 128);
+                    const uint64_t bh = umma_desc(b0 + (dx * 2) * b_part, q.NPAD * 16, 128);
+                    const uint64_t bl = umma_desc(b0 + (dx * 2 + 1) * b_part, q.NPAD * 16, 128);
+                    tc_mma_bf16(d, ah, bh, idesc, dx > 0 ? 1u : 0u);
+                    tc_mma_bf16(d, al, bh, idesc, 1u);
+                    tc_mma_bf16(d, ah, bl, idesc, 1u);
+                }
+                tc_commit(&acc_full[slot]);
+                tc_commit(&a_free[buf]);
+            }
+        }
+    } else {
+        // ================= drain: lane = raster column; group g takes rows g, g + 4, ...
+        const int ew = warp - L0T_EPI_WARP0;
+        const int quarter = warp & 3, grp = ew >> 2;
+        float bias_r[C];
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) bias_r[ch] = bias_sm[ch];
+        int k = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++k) {
+            const int slot = k & 1;
+            const int gt = t / q.TY, ty = t - gt * q.TY;
+            const int y0 = ty * q.R0;
+            const unsigned g = (unsigned)gt * 128u + (unsigned)(quarter * 32 + lane);
+            const unsigned s = __umulhi(g, q.wp_magic);
+            const int xp = (int)(g - s * (unsigned)p.Wp);
+            const bool valid = (int)s < p.n && xp >= 1 && xp <= p.W;
+            uint8_t *out_px = reinterpret_cast<uint8_t *>(p.out) + (long long)s * p.out_sample + ((long long)(y0 + 1) * p.Wp + xp) * 16;
+            const uint32_t taddr = tmem_base + (uint32_t)slot * L0T_SLOT_COLS + ((uint32_t)(quarter * 32) << 16);
+            const int nrows = (q.dbg & 1) ? 0 : min(q.R0, p.H - y0);
+            mbar_wait(&acc_full[slot], (uint32_t)((k >> 1) & 1));
+            tc_fence_after();
+            for (int r = grp; r < nrows; r += 4) {
+                uint8_t *o = out_px + (long long)r * p.Wp * 16;
+#pragma unroll
+                for (int c0 = 0; c0 < C; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(taddr + (uint32_t)(r * C + c0), v);
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int ch = c0 + 2 * j;
+                        const float r0 = ch < C ? elu_f(v[2 * j] + bias_r[ch < C ? ch : 0]) : 0.f;
+                        const float r1 = ch + 1 < C ? elu_f(v[2 * j + 1] + bias_r[ch + 1 < C ? ch + 1 : 0]) : 0.f;
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(r0, r1);
+                        pk[j] = *reinterpret_cast<const uint32_t *>(&h);
+                    }
+                    if (valid) {
+                        *reinterpret_cast<uint4 *>(o + (long long)(c0 / 8) * p.out_plane) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        if (c0 + 8 < C)
+                            *reinterpret_cast<uint4 *>(o + (long long)(c0 / 8 + 1) * p.out_plane) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[slot]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == L0T_PROD_WARPS) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * L0T_SLOT_COLS); }
+}
+
+// --------------------------------------------------------------------------------------
 // head: spatial mean -> 1x1 conv + BN (folded) -> latent -> (latent - mean) . P -> unit norm
 // --------------------------------------------------------------------------------------
 struct HeadParams {
@@ -866,6 +1134,9 @@ struct asr_encoder {
     // tcgen05 path
     float *l0_w = nullptr;          // [C0*9 + C0] (device copy, unused by the product path)
     L0Weights l0_host;              // folded layer-0 weights, passed by value at launch
+    uint8_t *l0_blob = nullptr;     // tensor-core layer 0: banded hi/lo weight matrices + biases
+    int l0_R0 = 0, l0_NPAD = 0;
+    unsigned l0_wp_magic = 0;
     bf16 *wblob[8] = {nullptr};     // layers 1..7
     ConvPlan plan[8];
     bf16 *act[8] = {nullptr};       // P8 activations (output of layer l)
@@ -1018,7 +1289,7 @@ extern "C" {
 
 int asr_encoder_destroy(asr_encoder_t *e) {
     if (!e) return ASR_OK;
-    cudaFree(e->l0_w);
+    cudaFree(e->l0_w); cudaFree(e->l0_blob);
     for (int l = 0; l < 8; ++l) {
         cudaFree(e->wblob[l]); cudaFree(e->act[l]); cudaFree(e->ref_w[l]); cudaFree(e->ref_bn[l]); cudaFree(e->ref_act[l]);
     }
@@ -1126,6 +1397,37 @@ int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *d, int max_b
             }
             E_CUDA(cudaMalloc(&e->l0_w, w0.size() * 4));
             E_CUDA(cudaMemcpy(e->l0_w, w0.data(), w0.size() * 4, cudaMemcpyHostToDevice));
+            static const int l0_tc = getenv("ASR_L0_TC") ? atoi(getenv("ASR_L0_TC")) : 1;
+            if (l0_tc && (g.cout == 12 || g.cout == 24)) {
+                // banded weight matrices of l0_tc_kernel: B_dx[k][(r, co)] = w[co][dy = k - r][dx], split hi + lo
+                const int C = g.cout, R0 = C == 12 ? 12 : 8, NPAD = R0 * C;
+                const size_t bbytes = (size_t)3 * 2 * 2 * NPAD * 16;
+                std::vector<uint8_t> blob(bbytes + C * 4, 0);
+                bf16 *wb = reinterpret_cast<bf16 *>(blob.data());
+                for (int dx = 0; dx < 3; ++dx)
+                    for (int r = 0; r < R0; ++r)
+                        for (int dy = 0; dy < 3; ++dy)
+                            for (int co = 0; co < C; ++co) {
+                                const int k = r + dy, nn = r * C + co;
+                                const float w = w0[(size_t)co * 9 + dy * 3 + dx];
+                                const bf16 hi = __float2bfloat16_rn(w);
+                                const bf16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+                                wb[((((size_t)dx * 2 + 0) * 2 + k / 8) * NPAD + nn) * 8 + (k & 7)] = hi;
+                                wb[((((size_t)dx * 2 + 1) * 2 + k / 8) * NPAD + nn) * 8 + (k & 7)] = lo;
+                            }
+                float *bb = reinterpret_cast<float *>(blob.data() + bbytes);
+                for (int co = 0; co < C; ++co) bb[co] = w0[(size_t)C * 9 + co];
+                const unsigned Wp = (unsigned)g.W + 2;
+                const unsigned magic = (unsigned)((0x100000000ull + Wp - 1) / Wp);
+                bool exact = true;
+                for (unsigned gg = 0; gg < (unsigned)max_batch * Wp + 512u && exact; ++gg)
+                    exact = (unsigned)(((unsigned long long)gg * magic) >> 32) == gg / Wp;
+                if (exact) {
+                    E_CUDA(cudaMalloc(&e->l0_blob, blob.size()));
+                    E_CUDA(cudaMemcpy(e->l0_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+                    e->l0_R0 = R0; e->l0_NPAD = NPAD; e->l0_wp_magic = magic;
+                }
+            }
         } else {
             if (!plan_rows(g, e->plan[l]) && !plan_conv(g, e->plan[l])) {
                 set_error("asr_encoder_create: layer " + std::to_string(l) + " does not fit in shared memory");
@@ -1192,6 +1494,8 @@ int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *d, int max_b
     }
     static bool attr_done = false;
     if (!attr_done) {
+        E_CUDA(cudaFuncSetAttribute(l0_tc_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        E_CUDA(cudaFuncSetAttribute(l0_tc_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         E_CUDA(cudaFuncSetAttribute(conv3x3_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         E_CUDA(cudaFuncSetAttribute(conv3x3_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         E_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
@@ -1249,6 +1553,22 @@ int asr_encoder_embed(asr_encoder_t *e, const void *x_dev, int x_dtype, int64_t 
             p.Hin = d.in_h; p.Win = d.in_w; p.H = g.H; p.W = g.W; p.Wp = g.W + 2; p.Hp = g.H + 2;
             p.C = g.cout; p.NCH = g.coutp / 8; p.w = e->l0_w; p.out = out;
             p.out_plane = e->act_plane[0]; p.out_sample = e->act_sample[0]; p.n = (int)nn;
+            if (e->l0_blob) {
+                L0TcParams q;
+                q.b = p; q.blob = e->l0_blob; q.R0 = e->l0_R0; q.NPAD = e->l0_NPAD;
+                q.TY = (g.H + q.R0 - 1) / q.R0;
+                q.GT = (int)(((long long)nn * p.Wp + 127) / 128);
+                q.wp_magic = e->l0_wp_magic;
+                static const int l0_dbg = getenv("ASR_L0_DEBUG") ? atoi(getenv("ASR_L0_DEBUG")) : 0;
+                q.dbg = l0_dbg;
+                const long long tiles = (long long)q.GT * q.TY;
+                const int grid_tc = (int)std::min<long long>(tiles, sm_count());
+                const int smem_tc = 3 * 2 * 2 * q.NPAD * 16 + L0T_NBUF * 2 * 2 * L0T_AROWS * 16 + 32 * 4 + 256 * 4 + 256;
+                if (g.cout == 12) l0_tc_kernel<12><<<grid_tc, L0T_THREADS, smem_tc, st>>>(q);
+                else l0_tc_kernel<24><<<grid_tc, L0T_THREADS, smem_tc, st>>>(q);
+                ASR_LAUNCH_CHECK();
+                return ASR_OK;
+            }
             dim3 grid((g.W + L0_TW - 1) / L0_TW, (g.H + L0_TH - 1) / L0_TH, (unsigned)nn);
             if (g.cout == 12) l0_conv_kernel<12><<<grid, L0_TW * L0_TROWS, 0, st>>>(p, e->l0_host);
             else if (g.cout == 24) l0_conv_kernel<24><<<grid, L0_TW * L0_TROWS, 0, st>>>(p, e->l0_host);
