@@ -73,6 +73,8 @@ struct ConvParams {
     int Hc;              // conv rows that are needed (H, or 2*Ho for a pooled layer)
     int JT;              // row-stacked kernel: 128-pixel tiles across one image row
     int coop;            // row-stacked kernel: all epilogue groups drain every tile together
+    int KCL;             // input chunks that hold real channels: the others are never loaded (zeroed in smem once)
+    int NCHR;            // output chunks that hold real channels: the others are never stored (buffers are pre-zeroed)
     int dbg;             // diagnostics only (env ASR_CONV_DEBUG): 1 = epilogue releases slots without draining, 2 = no MMAs
 };
 
@@ -119,6 +121,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(const ConvP
         tmem_alloc(tmem_ptr, (uint32_t)p.tmem_cols);
         tmem_relinquish();
     }
+    if (p.KCL < p.KC) {     // planes of all-padding input chunks: zero once, never loaded
+        for (int st = 0; st < p.n_stages; ++st) {
+            uint4 *z = reinterpret_cast<uint4 *>(smem + p.off_stage + (size_t)st * p.stage_bytes + 16 + (size_t)p.KCL * p.sps);
+            const int n16 = (p.stage_bytes - 16 - p.KCL * p.sps) / 16;
+            for (int i = tid; i < n16; i += CONV_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -140,11 +150,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(const ConvP
                 mbar_wait(&in_empty[s], ph ^ 1u);
                 const int rows_in = min(p.TH + 2, p.Hp - y0);
                 const uint32_t bytes = (uint32_t)(rows_in * p.Wp * 16);
-                mbar_expect_tx(&in_full[s], bytes * (uint32_t)p.KC);
+                mbar_expect_tx(&in_full[s], bytes * (uint32_t)p.KCL);
                 const uint8_t *src = reinterpret_cast<const uint8_t *>(p.in) + (long long)n * p.in_sample +
                                      (long long)y0 * p.Wp * 16;
                 uint8_t *dst = stage_sm + (size_t)s * p.stage_bytes + 16;
-                for (int kc = 0; kc < p.KC; ++kc)
+                for (int kc = 0; kc < p.KCL; ++kc)
                     tma_bulk_g2s(dst + (size_t)kc * p.sps, src + (long long)kc * p.in_plane, bytes, &in_full[s]);
             }
         }
@@ -266,10 +276,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(const ConvP
                         }
                         if (valid) {
                             const long long pos = ((long long)(y + 1) * p.Wp + c) * 16;
-                            *reinterpret_cast<uint4 *>(out_n + (long long)(2 * ng) * p.out_plane + pos) =
-                                make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                            *reinterpret_cast<uint4 *>(out_n + (long long)(2 * ng + 1) * p.out_plane + pos) =
-                                make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                            if (2 * ng < p.NCHR)
+                                *reinterpret_cast<uint4 *>(out_n + (long long)(2 * ng) * p.out_plane + pos) =
+                                    make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            if (2 * ng + 1 < p.NCHR)
+                                *reinterpret_cast<uint4 *>(out_n + (long long)(2 * ng + 1) * p.out_plane + pos) =
+                                    make_uint4(pk[4], pk[5], pk[6], pk[7]);
                         }
                     }
                 }
@@ -282,7 +294,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(const ConvP
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");   // band staged
                 const int per_ch = (p.TH / 2) * p.Wo;
                 const int yo0 = y0 / 2;
-                for (int ch = 0; ch < p.NCH; ++ch) {
+                for (int ch = 0; ch < p.NCHR; ++ch) {
                     const int nreal = min(8, p.cout - 8 * ch);       // real channels of this chunk (<= 0: padding only)
                     float bch[8];
 #pragma unroll
@@ -374,6 +386,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_rows_kernel(const Con
         tmem_alloc(tmem_ptr, (uint32_t)p.tmem_cols);
         tmem_relinquish();
     }
+    if (p.KCL < p.KC) {     // planes of all-padding input chunks: zero once, never loaded
+        for (int st = 0; st < p.n_stages; ++st) {
+            uint4 *z = reinterpret_cast<uint4 *>(smem + p.off_stage + (size_t)st * p.stage_bytes + 16 + (size_t)p.KCL * p.sps);
+            const int n16 = (p.stage_bytes - 16 - p.KCL * p.sps) / 16;
+            for (int i = tid; i < n16; i += CONV_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -394,11 +414,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_rows_kernel(const Con
                 mbar_wait(&in_empty[s], ph ^ 1u);
                 const int rows_in = min(p.TH + 2, p.Hp - y0);
                 const uint32_t bytes = (uint32_t)(rows_in * p.Wp * 16);
-                mbar_expect_tx(&in_full[s], bytes * (uint32_t)p.KC);
+                mbar_expect_tx(&in_full[s], bytes * (uint32_t)p.KCL);
                 const uint8_t *src = reinterpret_cast<const uint8_t *>(p.in) + (long long)n * p.in_sample +
                                      (long long)y0 * p.Wp * 16;
                 uint8_t *dst = stage_sm + (size_t)s * p.stage_bytes + 16;
-                for (int kc = 0; kc < p.KC; ++kc)
+                for (int kc = 0; kc < p.KCL; ++kc)
                     tma_bulk_g2s(dst + (size_t)kc * p.sps, src + (long long)kc * p.in_plane, bytes, &in_full[s]);
             }
         }
@@ -504,7 +524,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_rows_kernel(const Con
                     const int pr = grp >> 1;
                     const int yo = (y >> 1) + pr;
                     const long long opos = ((long long)(yo + 1) * p.Wpo + ((c - 1) >> 1) + 1) * 16 + 8 * odd;
-                    for (int h = grp & 1; h < p.NCH; h += 2) {
+                    for (int h = grp & 1; h < p.NCHR; h += 2) {
                         float v[16];
                         tmem_ld8x2(taddr + (uint32_t)(2 * pr * p.NP + h * 8), (uint32_t)p.NP, v);
                         float m[4];
@@ -527,7 +547,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_rows_kernel(const Con
                     // column: the even lane finishes pooled row 0, the odd lane pooled row 1.
                     const int yo = (y >> 1) + odd;
                     const long long opos = ((long long)(yo + 1) * p.Wpo + ((c - 1) >> 1) + 1) * 16;
-                    for (int h = 0; h < p.NCH; ++h) {
+                    for (int h = 0; h < p.NCHR; ++h) {
                         float v[32];
                         tmem_ld8x4(taddr + (uint32_t)(h * 8), (uint32_t)p.NP, v);
                         float m[8];
@@ -576,10 +596,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_rows_kernel(const Con
                                 }
                             }
                             if (valid) {
-                                *reinterpret_cast<uint4 *>(out_n + (long long)(2 * ng) * p.out_plane + pos) =
-                                    make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                                *reinterpret_cast<uint4 *>(out_n + (long long)(2 * ng + 1) * p.out_plane + pos) =
-                                    make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                                if (2 * ng < p.NCHR)
+                                    *reinterpret_cast<uint4 *>(out_n + (long long)(2 * ng) * p.out_plane + pos) =
+                                        make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                                if (2 * ng + 1 < p.NCHR)
+                                    *reinterpret_cast<uint4 *>(out_n + (long long)(2 * ng + 1) * p.out_plane + pos) =
+                                        make_uint4(pk[4], pk[5], pk[6], pk[7]);
                             }
                         }
                     }
@@ -798,7 +820,13 @@ __device__ __forceinline__ void l0t_finish8(const L0Params &p, const float *lut,
 }
 
 // bf16 hi + lo split of 8 values -> the 16-byte K-major rows of the two A parts
-__device__ __forceinline__ void l0t_store8(uint8_t *a_buf, int c, int i, const float *v) {
+__device__ __forceinline__ void l0t_store8(uint8_t *a_buf, int c, int i, const float *vin) {
+    // K element 15 (image row y0 + 14) is outside every tap window (R0 <= 12): it carries the constant 1
+    // that multiplies the bias row of the weight matrix, so the MMA adds the bias.
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = vin[k];
+    if (c == 1) v[7] = 1.0f;
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -853,6 +881,69 @@ __device__ __forceinline__ void l0t_convert(const L0TcParams &q, uint8_t *a_buf,
     }
 }
 
+// The same converter specialised for u8 pixels with prepare = x / 255 (MODE 1: a table look-up of the
+// correctly rounded quotient), with the row clamps and masks dropped for tiles that do not touch the top
+// or bottom image border.  (MODE 2, fp32 pixels as they are, measured slower than the generic loop.)
+template <int MODE>
+__device__ __forceinline__ void l0t_convert_fast(const L0TcParams &q, uint8_t *a_buf, const float *lut, uint64_t *a_ready,
+                                                 uint64_t *a_free, int n_tiles, int cw) {
+    const L0Params &p = q.b;
+    const int lane = threadIdx.x & 31;
+    const bool off = (q.dbg & 2) != 0;
+    const uint8_t *xu = reinterpret_cast<const uint8_t *>(p.x);
+    const float *xf = reinterpret_cast<const float *>(p.x);
+    const unsigned img = (unsigned)(p.Hin * p.Win);
+    int k = cw;
+    for (int t = blockIdx.x + cw * (int)gridDim.x; t < n_tiles; t += L0T_PROD_WARPS * (int)gridDim.x, k += L0T_PROD_WARPS) {
+        const int gt = t / q.TY, ty = t - gt * q.TY;
+        const int g0 = gt * 128 - 1;
+        const int y0 = ty * q.R0 - 1;
+        const bool interior = y0 >= 0 && y0 + 15 < p.H;     // warp-uniform
+        mbar_wait(a_free, (uint32_t)(((k / L0T_PROD_WARPS) & 1) ^ 1));
+#pragma unroll 1
+        for (int batch = 0; batch < 3; ++batch) {
+            uint32_t raw[3][8];
+            bool ok[3];
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int item = lane + 32 * (3 * batch + u);
+                const int c = item >= 130 ? 1 : 0, i = item - 130 * c;
+                const int g = g0 + i;
+                const unsigned gc = (unsigned)max(g, 0);
+                const unsigned s = __umulhi(gc, q.wp_magic);
+                const int x = (int)(gc - s * (unsigned)p.Wp) - 1;
+                ok[u] = item < 260 && !off && g >= 0 && (int)s < p.n && x >= 0 && x < p.W;
+                const unsigned base = min(s, (unsigned)p.n - 1u) * img + (unsigned)min(max(x, 0), p.W - 1);
+                const int yb = y0 + 8 * c;
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const int yc = interior ? yb + kk : min(max(yb + kk, 0), p.H - 1);
+                    const unsigned o = base + (unsigned)(yc * p.Win);
+                    raw[u][kk] = 0u;
+                    if (ok[u]) raw[u][kk] = MODE == 1 ? (uint32_t)xu[o] : __float_as_uint(xf[o]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int item = lane + 32 * (3 * batch + u);
+                const int c = item >= 130 ? 1 : 0, i = item - 130 * c;
+                const int yb = y0 + 8 * c;
+                float v[8];
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    float f = MODE == 1 ? lut[raw[u][kk]] : __uint_as_float(raw[u][kk]);
+                    const bool row_ok = interior || (yb + kk >= 0 && yb + kk < p.H);
+                    v[kk] = (ok[u] && row_ok) ? f : 0.f;
+                }
+                if (item < 260) l0t_store8(a_buf, c, i, v);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready);
+    }
+}
+
 template <int C>
 __global__ void __launch_bounds__(L0T_THREADS, 1) l0_tc_kernel(const L0TcParams q) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -890,7 +981,9 @@ __global__ void __launch_bounds__(L0T_THREADS, 1) l0_tc_kernel(const L0TcParams 
 
     if (warp < L0T_PROD_WARPS) {
         // ================= converters: A row i <-> raster column g0 - 1 + i; K element k <-> image row y0 - 1 + k
-        if (p.prepare == ASR_PREP_SCALE_HALF)
+        if (p.prepare == ASR_PREP_SCALE && p.x_u8)
+            l0t_convert_fast<1>(q, a_sm + warp * ABUF, lut_sm, &a_ready[warp], &a_free[warp], n_tiles, warp);
+        else if (p.prepare == ASR_PREP_SCALE_HALF)
             l0t_convert<4>(q, a_sm + warp * ABUF, lut_sm, &a_ready[warp], &a_free[warp], n_tiles, warp);
         else
             l0t_convert<1>(q, a_sm + warp * ABUF, lut_sm, &a_ready[warp], &a_free[warp], n_tiles, warp);
@@ -925,9 +1018,6 @@ __global__ void __launch_bounds__(L0T_THREADS, 1) l0_tc_kernel(const L0TcParams 
         // ================= drain: lane = raster column; group g takes rows g, g + 4, ...
         const int ew = warp - L0T_EPI_WARP0;
         const int quarter = warp & 3, grp = ew >> 2;
-        float bias_r[C];
-#pragma unroll
-        for (int ch = 0; ch < C; ++ch) bias_r[ch] = bias_sm[ch];
         int k = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++k) {
             const int slot = k & 1;
@@ -952,8 +1042,8 @@ __global__ void __launch_bounds__(L0T_THREADS, 1) l0_tc_kernel(const L0TcParams 
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int ch = c0 + 2 * j;
-                        const float r0 = ch < C ? elu_f(v[2 * j] + bias_r[ch < C ? ch : 0]) : 0.f;
-                        const float r1 = ch + 1 < C ? elu_f(v[2 * j + 1] + bias_r[ch + 1 < C ? ch + 1 : 0]) : 0.f;
+                        const float r0 = ch < C ? elu_f(v[2 * j]) : 0.f;          // bias already added by the MMA
+                        const float r1 = ch + 1 < C ? elu_f(v[2 * j + 1]) : 0.f;
                         const __nv_bfloat162 h = __floats2bfloat162_rn(r0, r1);
                         pk[j] = *reinterpret_cast<const uint32_t *>(&h);
                     }
@@ -1415,6 +1505,14 @@ int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *d, int max_b
                                 wb[((((size_t)dx * 2 + 0) * 2 + k / 8) * NPAD + nn) * 8 + (k & 7)] = hi;
                                 wb[((((size_t)dx * 2 + 1) * 2 + k / 8) * NPAD + nn) * 8 + (k & 7)] = lo;
                             }
+                for (int r = 0; r < R0; ++r)            // K row 15 of dx = 0: the bias (the A tile holds 1 there)
+                    for (int co = 0; co < C; ++co) {
+                        const float b = w0[(size_t)C * 9 + co];
+                        const bf16 hi = __float2bfloat16_rn(b);
+                        const bf16 lo = __float2bfloat16_rn(b - __bfloat162float(hi));
+                        wb[((((size_t)0 * 2 + 0) * 2 + 1) * NPAD + r * C + co) * 8 + 7] = hi;
+                        wb[((((size_t)0 * 2 + 1) * 2 + 1) * NPAD + r * C + co) * 8 + 7] = lo;
+                    }
                 float *bb = reinterpret_cast<float *>(blob.data() + bbytes);
                 for (int co = 0; co < C; ++co) bb[co] = w0[(size_t)C * 9 + co];
                 const unsigned Wp = (unsigned)g.W + 2;
@@ -1582,6 +1680,7 @@ int asr_encoder_embed(asr_encoder_t *e, const void *x_dev, int x_dtype, int64_t 
             ConvParams p;
             p.in = in; p.out = out; p.wblob = e->wblob[l]; p.n_samples = (int)nn;
             p.H = g.H; p.W = g.W; p.Wp = g.W + 2; p.Hp = g.H + 2; p.KC = g.cinp / 8; p.NP = g.coutp; p.NCH = g.coutp / 8;
+            p.KCL = (g.cin + 7) / 8; p.NCHR = (g.cout + 7) / 8;
             p.TH = pl.TH; p.bands = pl.bands; p.MT = pl.MT; p.pool = g.pool; p.cout = g.cout;
             p.Ho = g.Ho; p.Wo = g.Wo; p.Wpo = g.Wo + 2;
             p.in_plane = e->act_plane[l - 1]; p.in_sample = e->act_sample[l - 1];

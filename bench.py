@@ -289,18 +289,18 @@ def main():
     ms_step = float(ms_total.item()) / args.steps
     value = world * n / (ms_step * 1e-3)
 
-    # roofline of the dominant kernel: conv3x3_tc_kernel (7 launches per embed call)
+    # roofline of the dominant kernel family: the tcgen05 convolutions of layers 1-7 (7 launches per embed call)
     conv_flops_pair = flops_pair - 2.0 * 9 * 12 * (160 * 200 + 92 * 42) - 2.0 * 48 * 32 * (10 * 12 + 5 * 2)
     conv_ms = t1["ms_conv_tc"] + t2["ms_conv_tc"]
     conv_launches = 7 * (t1["calls"] + t2["calls"])
     achieved = conv_flops_pair * n * args.steps / (conv_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "conv3x3_tc_kernel (tcgen05 implicit GEMM, layers 1-7 of both branches)",
+    roofline = {"bound": "tensor", "kernel": "conv3x3_rows_kernel + conv3x3_tc_kernel (tcgen05 implicit GEMM, layers 1-7 of both branches)",
                 "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
                 "peak_source": pk["src"] + ", sustained figure (kernel timed inside a long step)",
                 "traffic": None, "avg_launch_ms": conv_ms / max(conv_launches, 1), "launches": conv_launches,
                 "algorithmic_flops_per_pair": conv_flops_pair,
                 "share_of_step": conv_ms / (ms_step * args.steps),
-                "other_ms_per_step": {"layer0_cuda_cores": (t1["ms_layer0"] + t2["ms_layer0"]) / args.steps,
+                "other_ms_per_step": {"layer0_tcgen05_toeplitz": (t1["ms_layer0"] + t2["ms_layer0"]) / args.steps,
                                       "head": (t1["ms_head"] + t2["ms_head"]) / args.steps}}
 
     # ---- e2e: host buffers through the C-ABI entry the wrapper uses ----
