@@ -753,6 +753,7 @@ constexpr int L0T_SLOT_COLS = 256;
 struct L0TcParams {
     L0Params b;                 // input description (x, dtype, prepare, sizes), output pointers
     const uint8_t *blob;        // [dx][part: hi, lo][K chunk][NPAD][8] bf16, then C fp32 biases
+    int int_pixels;             // u8 input with prepare = x/255: A = integer pixels (hi part only), blob carries w/255
     int R0, NPAD;               // output rows per tile, padded N = R0 * C rounded up to 16
     int TY;                     // row tiles per sample
     int GT;                     // 128-column tiles over n * Wp raster columns
@@ -881,9 +882,10 @@ __device__ __forceinline__ void l0t_convert(const L0TcParams &q, uint8_t *a_buf,
     }
 }
 
-// The same converter specialised for u8 pixels with prepare = x / 255 (MODE 1: a table look-up of the
-// correctly rounded quotient), with the row clamps and masks dropped for tiles that do not touch the top
-// or bottom image border.  (MODE 2, fp32 pixels as they are, measured slower than the generic loop.)
+// The same converter specialised for u8 pixels with prepare = x / 255 (MODE 1): the integer pixel is exact
+// in bf16, so A has no lo part and 1/255 is folded into the weight matrix (blob_u8); the row clamps and
+// masks are dropped for tiles that do not touch the top or bottom image border.  (MODE 2, fp32 pixels as
+// they are, measured slower than the generic loop.)
 template <int MODE>
 __device__ __forceinline__ void l0t_convert_fast(const L0TcParams &q, uint8_t *a_buf, const float *lut, uint64_t *a_ready,
                                                  uint64_t *a_free, int n_tiles, int cw) {
@@ -931,11 +933,24 @@ __device__ __forceinline__ void l0t_convert_fast(const L0TcParams &q, uint8_t *a
                 float v[8];
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {
-                    float f = MODE == 1 ? lut[raw[u][kk]] : __uint_as_float(raw[u][kk]);
+                    // MODE 1: the integer pixel itself (exact in bf16; 1/255 lives in the weight matrix)
+                    float f = MODE == 1 ? (float)raw[u][kk] : __uint_as_float(raw[u][kk]);
                     const bool row_ok = interior || (yb + kk >= 0 && yb + kk < p.H);
                     v[kk] = (ok[u] && row_ok) ? f : 0.f;
                 }
-                if (item < 260) l0t_store8(a_buf, c, i, v);
+                if (MODE == 1) {
+                    if (c == 1) v[7] = 1.0f;             // the constant-one K row (bias)
+                    uint32_t hi[4];
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * kk], v[2 * kk + 1]);
+                        hi[kk] = *reinterpret_cast<const uint32_t *>(&h);
+                    }
+                    if (item < 260)
+                        *reinterpret_cast<uint4 *>(a_buf + (c * L0T_AROWS + i) * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                } else if (item < 260) {
+                    l0t_store8(a_buf, c, i, v);
+                }
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -981,7 +996,7 @@ __global__ void __launch_bounds__(L0T_THREADS, 1) l0_tc_kernel(const L0TcParams 
 
     if (warp < L0T_PROD_WARPS) {
         // ================= converters: A row i <-> raster column g0 - 1 + i; K element k <-> image row y0 - 1 + k
-        if (p.prepare == ASR_PREP_SCALE && p.x_u8)
+        if (q.int_pixels)
             l0t_convert_fast<1>(q, a_sm + warp * ABUF, lut_sm, &a_ready[warp], &a_free[warp], n_tiles, warp);
         else if (p.prepare == ASR_PREP_SCALE_HALF)
             l0t_convert<4>(q, a_sm + warp * ABUF, lut_sm, &a_ready[warp], &a_free[warp], n_tiles, warp);
@@ -1007,7 +1022,7 @@ __global__ void __launch_bounds__(L0T_THREADS, 1) l0_tc_kernel(const L0TcParams 
                     const uint64_t bh = umma_desc(b0 + (dx * 2) * b_part, q.NPAD * 16, 128);
                     const uint64_t bl = umma_desc(b0 + (dx * 2 + 1) * b_part, q.NPAD * 16, 128);
                     tc_mma_bf16(d, ah, bh, idesc, dx > 0 ? 1u : 0u);
-                    tc_mma_bf16(d, al, bh, idesc, 1u);
+                    if (!q.int_pixels) tc_mma_bf16(d, al, bh, idesc, 1u);
                     tc_mma_bf16(d, ah, bl, idesc, 1u);
                 }
                 tc_commit(&acc_full[slot]);
@@ -1032,7 +1047,7 @@ __global__ void __launch_bounds__(L0T_THREADS, 1) l0_tc_kernel(const L0TcParams 
             const int nrows = (q.dbg & 1) ? 0 : min(q.R0, p.H - y0);
             mbar_wait(&acc_full[slot], (uint32_t)((k >> 1) & 1));
             tc_fence_after();
-            for (int r = grp; r < nrows; r += 4) {
+            for (int r = grp; r < nrows; r += L0T_EPI_WARPS / 4) {
                 uint8_t *o = out_px + (long long)r * p.Wp * 16;
 #pragma unroll
                 for (int c0 = 0; c0 < C; c0 += 16) {
@@ -1225,6 +1240,7 @@ struct asr_encoder {
     float *l0_w = nullptr;          // [C0*9 + C0] (device copy, unused by the product path)
     L0Weights l0_host;              // folded layer-0 weights, passed by value at launch
     uint8_t *l0_blob = nullptr;     // tensor-core layer 0: banded hi/lo weight matrices + biases
+    uint8_t *l0_blob_u8 = nullptr;  // same with w/255 in the pixel rows (u8 input, prepare = x/255: A = integer pixels)
     int l0_R0 = 0, l0_NPAD = 0;
     unsigned l0_wp_magic = 0;
     bf16 *wblob[8] = {nullptr};     // layers 1..7
@@ -1379,7 +1395,7 @@ extern "C" {
 
 int asr_encoder_destroy(asr_encoder_t *e) {
     if (!e) return ASR_OK;
-    cudaFree(e->l0_w); cudaFree(e->l0_blob);
+    cudaFree(e->l0_w); cudaFree(e->l0_blob); cudaFree(e->l0_blob_u8);
     for (int l = 0; l < 8; ++l) {
         cudaFree(e->wblob[l]); cudaFree(e->act[l]); cudaFree(e->ref_w[l]); cudaFree(e->ref_bn[l]); cudaFree(e->ref_act[l]);
     }
@@ -1492,29 +1508,28 @@ int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *d, int max_b
                 // banded weight matrices of l0_tc_kernel: B_dx[k][(r, co)] = w[co][dy = k - r][dx], split hi + lo
                 const int C = g.cout, R0 = C == 12 ? 12 : 8, NPAD = R0 * C;
                 const size_t bbytes = (size_t)3 * 2 * 2 * NPAD * 16;
-                std::vector<uint8_t> blob(bbytes + C * 4, 0);
-                bf16 *wb = reinterpret_cast<bf16 *>(blob.data());
-                for (int dx = 0; dx < 3; ++dx)
-                    for (int r = 0; r < R0; ++r)
-                        for (int dy = 0; dy < 3; ++dy)
-                            for (int co = 0; co < C; ++co) {
-                                const int k = r + dy, nn = r * C + co;
-                                const float w = w0[(size_t)co * 9 + dy * 3 + dx];
-                                const bf16 hi = __float2bfloat16_rn(w);
-                                const bf16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
-                                wb[((((size_t)dx * 2 + 0) * 2 + k / 8) * NPAD + nn) * 8 + (k & 7)] = hi;
-                                wb[((((size_t)dx * 2 + 1) * 2 + k / 8) * NPAD + nn) * 8 + (k & 7)] = lo;
-                            }
-                for (int r = 0; r < R0; ++r)            // K row 15 of dx = 0: the bias (the A tile holds 1 there)
-                    for (int co = 0; co < C; ++co) {
-                        const float b = w0[(size_t)C * 9 + co];
-                        const bf16 hi = __float2bfloat16_rn(b);
-                        const bf16 lo = __float2bfloat16_rn(b - __bfloat162float(hi));
-                        wb[((((size_t)0 * 2 + 0) * 2 + 1) * NPAD + r * C + co) * 8 + 7] = hi;
-                        wb[((((size_t)0 * 2 + 1) * 2 + 1) * NPAD + r * C + co) * 8 + 7] = lo;
-                    }
-                float *bb = reinterpret_cast<float *>(blob.data() + bbytes);
-                for (int co = 0; co < C; ++co) bb[co] = w0[(size_t)C * 9 + co];
+                auto make_blob = [&](double pixel_scale) {
+                    std::vector<uint8_t> blob(bbytes + C * 4, 0);
+                    bf16 *wb = reinterpret_cast<bf16 *>(blob.data());
+                    auto put = [&](int dx, int k, int nn, float w) {
+                        const bf16 hi = __float2bfloat16_rn(w);
+                        const bf16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+                        wb[((((size_t)dx * 2 + 0) * 2 + k / 8) * NPAD + nn) * 8 + (k & 7)] = hi;
+                        wb[((((size_t)dx * 2 + 1) * 2 + k / 8) * NPAD + nn) * 8 + (k & 7)] = lo;
+                    };
+                    for (int dx = 0; dx < 3; ++dx)
+                        for (int r = 0; r < R0; ++r)
+                            for (int dy = 0; dy < 3; ++dy)
+                                for (int co = 0; co < C; ++co)
+                                    put(dx, r + dy, r * C + co, (float)((double)w0[(size_t)co * 9 + dy * 3 + dx] * pixel_scale));
+                    for (int r = 0; r < R0; ++r)            // K row 15 of dx = 0: the bias (the A tile holds 1 there)
+                        for (int co = 0; co < C; ++co) put(0, 15, r * C + co, w0[(size_t)C * 9 + co]);
+                    float *bb = reinterpret_cast<float *>(blob.data() + bbytes);
+                    for (int co = 0; co < C; ++co) bb[co] = w0[(size_t)C * 9 + co];
+                    return blob;
+                };
+                const std::vector<uint8_t> blob = make_blob(1.0);
+                const std::vector<uint8_t> blob_u8 = make_blob(1.0 / 255.0);
                 const unsigned Wp = (unsigned)g.W + 2;
                 const unsigned magic = (unsigned)((0x100000000ull + Wp - 1) / Wp);
                 bool exact = true;
@@ -1523,6 +1538,10 @@ int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *d, int max_b
                 if (exact) {
                     E_CUDA(cudaMalloc(&e->l0_blob, blob.size()));
                     E_CUDA(cudaMemcpy(e->l0_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+                    if (d->prepare == ASR_PREP_SCALE) {
+                        E_CUDA(cudaMalloc(&e->l0_blob_u8, blob_u8.size()));
+                        E_CUDA(cudaMemcpy(e->l0_blob_u8, blob_u8.data(), blob_u8.size(), cudaMemcpyHostToDevice));
+                    }
                     e->l0_R0 = R0; e->l0_NPAD = NPAD; e->l0_wp_magic = magic;
                 }
             }
@@ -1653,7 +1672,8 @@ int asr_encoder_embed(asr_encoder_t *e, const void *x_dev, int x_dtype, int64_t 
             p.out_plane = e->act_plane[0]; p.out_sample = e->act_sample[0]; p.n = (int)nn;
             if (e->l0_blob) {
                 L0TcParams q;
-                q.b = p; q.blob = e->l0_blob; q.R0 = e->l0_R0; q.NPAD = e->l0_NPAD;
+                q.int_pixels = (p.x_u8 && p.prepare == ASR_PREP_SCALE && e->l0_blob_u8) ? 1 : 0;
+                q.b = p; q.blob = q.int_pixels ? e->l0_blob_u8 : e->l0_blob; q.R0 = e->l0_R0; q.NPAD = e->l0_NPAD;
                 q.TY = (g.H + q.R0 - 1) / q.R0;
                 q.GT = (int)(((long long)nn * p.Wp + 127) / 128);
                 q.wp_magic = e->l0_wp_magic;
