@@ -166,3 +166,40 @@ def test_flip_filters_switch_changes_result():
     onet = OracleNet("mutopia_ccal_cont_rsz", load_param_list(PKL["mutopia_ccal_cont_rsz"]), flip_filters=True)
     assert _cos(b, onet.compute_view_2(X2)).min() >= COS_TOL
     assert _cos(a, b).min() < 0.999
+
+
+@pytest.mark.parametrize("model_name", ["mutopia_ccal_cont_rsz", "mutopia_ccal_cont"])
+@pytest.mark.parametrize("dtype", ["u8", "f32"])
+@pytest.mark.parametrize("mode", ["none", "scale", "scale_half"])
+def test_layer0_tensor_core_all_input_forms(model_name, dtype, mode):
+    """Layer 0 on the tensor cores (banded-Toeplitz GEMM) for every input dtype x prepare mode -- the
+    integer-pixel form (u8, x/255), the generic hi/lo converter and the 2x2 box filter -- against the
+    fp32 CUDA-core path on the same device: layer-0 activations to bf16 round-off, codes to COS_TOL."""
+    from audio_sheet_retrieval_b200 import _lib
+    model, net = _net(model_name, max_batch=16)
+    prep = {"none": _lib.PREP_NONE, "scale": _lib.PREP_SCALE, "scale_half": _lib.PREP_SCALE_HALF}[mode]
+    rng = np.random.RandomState(11)
+    enc = net.encoder(1, prep)      # raw input size follows the mode (the box filter halves it)
+    X = rng.randint(0, 256, size=(5, 1, enc.in_h, enc.in_w)).astype(np.uint8 if dtype == "u8" else np.float32)
+    c_tc = enc.embed_host(X, path=_lib.PATH_TCGEN05)
+    a_tc = enc.debug_activation(0, 5, path=_lib.PATH_TCGEN05)
+    c_fp = enc.embed_host(X, path=_lib.PATH_FP32)
+    a_fp = enc.debug_activation(0, 5, path=_lib.PATH_FP32)
+    scale = np.abs(a_fp).max()
+    assert np.abs(a_tc - a_fp).max() <= 2.0 ** -7 * scale + 1e-3        # one bf16 ulp of the largest activation
+    assert _cos(c_tc, c_fp).min() >= COS_TOL
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 17])
+def test_small_and_ragged_batches(n):
+    """Batch sizes around the tile edges of the raster-over-samples layer-0 GEMM and the persistent conv
+    grids (fewer items than SMs): every row must equal the row of a larger batch."""
+    from audio_sheet_retrieval_b200 import _lib
+    model, net = _net("mutopia_ccal_cont", max_batch=16)
+    X1, X2 = synth_inputs(20, seed=9)
+    e1 = net.encoder(1, model.prepare.asr_prepare_mode)
+    e2 = net.encoder(2, _lib.PREP_NONE)
+    full1, full2 = e1.embed_host(X1[:16].astype(np.uint8)), e2.embed_host(X2[:16])
+    m = min(n, 16)
+    got1, got2 = e1.embed_host(X1[:n].astype(np.uint8)), e2.embed_host(X2[:n])
+    assert (got1[:m] == full1[:m]).all() and (got2[:m] == full2[:m]).all()
