@@ -56,6 +56,7 @@ struct ConvPlan {
     unsigned wp_magic, wo_magic;
     int Hc;
     int rows, JT;       // rows != 0: conv3x3_rows_kernel (4 output rows stacked along N)
+    int SPT, SP, RP;
 };
 
 struct ConvParams {
@@ -73,6 +74,8 @@ struct ConvParams {
     int Hc;              // conv rows that are needed (H, or 2*Ho for a pooled layer)
     int JT;              // row-stacked kernel: 128-pixel tiles across one image row
     int coop;            // row-stacked kernel: all epilogue groups drain every tile together
+    int SPT, SP, RP;     // row-stacked kernel: samples per tile row, per-sample pitch (even), smem row pitch (positions)
+    unsigned sp_magic;   // ceil(2^32 / SP)
     int KCL;             // input chunks that hold real channels: the others are never loaded (zeroed in smem once)
     int NCHR;            // output chunks that hold real channels: the others are never stored (buffers are pre-zeroed)
     int dbg;             // diagnostics only (env ASR_CONV_DEBUG): 1 = epilogue releases slots without draining, 2 = no MMAs
@@ -358,7 +361,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(const ConvP
 constexpr int RS_R = 4;
 
 __device__ __forceinline__ int rows_band_tiles(const ConvParams &p, int y0) {
-    return (min(p.TH, p.Hc - y0) >> 2) * p.JT;
+    return ((min(p.TH, p.Hc - y0) + RS_R - 1) >> 2) * p.JT;
 }
 
 template <int KPAIRS>
@@ -398,9 +401,42 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_rows_kernel(const Con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    const int n_items = p.n_samples * p.bands;
+    // narrow images: SPT samples side by side in one tile row (smem row = [sample 0 | sample 1 | ...], pitch SP each)
+    const int n_sgroups = (p.n_samples + p.SPT - 1) / p.SPT;
+    const int n_items = n_sgroups * p.bands;
 
-    if (warp == 0) {
+    if (warp == 0 && p.SPT > 1) {
+        // ================= TMA producer, gather form: one bulk copy per (input row, sample, chunk) =================
+        if (lane == 0) {
+            mbar_expect_tx(w_full, (uint32_t)(p.wbytes + p.NP * 4));
+            tma_bulk_g2s(w_sm, p.wblob, (uint32_t)p.wbytes, w_full);
+            tma_bulk_g2s(bias_sm, reinterpret_cast<const uint8_t *>(p.wblob) + p.wbytes, (uint32_t)(p.NP * 4), w_full);
+        }
+        const uint32_t row_bytes = (uint32_t)(p.Wp * 16);
+        int it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const int sg = item / p.bands, y0 = (item % p.bands) * p.TH;
+            const int s = it % p.n_stages;
+            const uint32_t ph = (uint32_t)((it / p.n_stages) & 1);
+            const int rows_in = min(p.TH + 2, p.Hp - y0);
+            const int ns = min(p.SPT, p.n_samples - sg * p.SPT);
+            const int per_chunk = rows_in * ns;
+            const int total = per_chunk * p.KCL;
+            if (lane == 0) {
+                mbar_wait(&in_empty[s], ph ^ 1u);
+                mbar_expect_tx(&in_full[s], (uint32_t)total * row_bytes);
+            }
+            __syncwarp();
+            uint8_t *dst0 = stage_sm + (size_t)s * p.stage_bytes + 16;
+            for (int i = lane; i < total; i += 32) {
+                const int kc = i / per_chunk, rem = i - kc * per_chunk;
+                const int r = rem / ns, u = rem - r * ns;
+                const uint8_t *src = reinterpret_cast<const uint8_t *>(p.in) + (long long)(sg * p.SPT + u) * p.in_sample +
+                                     (long long)kc * p.in_plane + (long long)(y0 + r) * row_bytes;
+                tma_bulk_g2s(dst0 + (size_t)kc * p.sps + ((size_t)r * p.RP + (size_t)u * p.SP) * 16, src, row_bytes, &in_full[s]);
+            }
+        }
+    } else if (warp == 0) {
         // ================= TMA producer (same bands as conv3x3_tc_kernel) =================
         if (lane == 0) {
             mbar_expect_tx(w_full, (uint32_t)(p.wbytes + p.NP * 4));
@@ -436,7 +472,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_rows_kernel(const Con
         const uint32_t kstep_a = (uint32_t)(2 * p.sps) >> 4;
         const uint32_t slot_mask = (uint32_t)p.n_slots - 1u;
         const uint32_t slot_shift = (uint32_t)__ffs(p.n_slots) - 1u;
-        const uint32_t wp = (uint32_t)p.Wp;
+        const uint32_t wp = (uint32_t)p.RP;          // smem row pitch in positions
         const uint32_t jt = (uint32_t)p.JT;
         mbar_wait(w_full, 0);
         int it = 0;
@@ -502,9 +538,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_rows_kernel(const Con
         const int n_groups16 = (p.cout + 3) >> 2;
         const int odd = lane & 1;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-            const int n = item / p.bands, y0 = (item % p.bands) * p.TH;
+            const int sg = item / p.bands, y0 = (item % p.bands) * p.TH;
             const int mtb = rows_band_tiles(p, y0);
-            uint8_t *out_n = reinterpret_cast<uint8_t *>(p.out) + (long long)n * p.out_sample;
             const int mt0 = coop ? 0 : (int)(((uint32_t)grp - tc0) & (uint32_t)(N_EPI_GROUPS - 1));
             for (int mt = mt0; mt < mtb; mt += coop ? 1 : N_EPI_GROUPS) {
                 const uint32_t tc = tc0 + (uint32_t)mt;
@@ -513,9 +548,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_rows_kernel(const Con
                 mbar_wait(&acc_full[slot], sph);
                 tc_fence_after();
                 const int rg = mt / p.JT, j = mt - rg * p.JT;
-                const int c = 1 + 128 * j + quarter * 32 + lane;     // padded column
+                // the lane's output position in the tile row: sample u of the group, padded column c
+                const int pos_row = 1 + 128 * j + quarter * 32 + lane;
+                const int u = p.SPT > 1 ? (int)__umulhi((unsigned)pos_row, p.sp_magic) : 0;
+                const int c = pos_row - u * p.SP;
+                const int n = sg * p.SPT + u;
                 const int y = y0 + RS_R * rg;                        // first of the four conv rows
-                const bool valid = c <= p.W;
+                const bool valid = c >= 1 && c <= p.W && u < p.SPT && n < p.n_samples;
+                uint8_t *out_n = reinterpret_cast<uint8_t *>(p.out) + (long long)min(n, p.n_samples - 1) * p.out_sample;
                 const uint32_t taddr = tmem_base + slot * (uint32_t)p.slot_cols + ((uint32_t)(quarter * 32) << 16);
                 if (p.dbg & 1) {
                 } else if (p.pool && coop) {
@@ -540,7 +580,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_rows_kernel(const Con
                         const bool real = h * 2 + odd < n_groups16;       // padded channels stay exactly zero
                         const uint2 o2 = make_uint2(real ? *reinterpret_cast<uint32_t *>(&h0) : 0u,
                                                     real ? *reinterpret_cast<uint32_t *>(&h1) : 0u);
-                        if (valid) *reinterpret_cast<uint2 *>(out_n + (long long)h * p.out_plane + opos) = o2;
+                        if (valid && yo < p.Ho && ((c - 1) >> 1) < p.Wo)
+                            *reinterpret_cast<uint2 *>(out_n + (long long)h * p.out_plane + opos) = o2;
                     }
                 } else if (p.pool) {
                     // rows (0,1) and (2,3) pool vertically inside the thread; lanes (2k, 2k+1) are one pooled
@@ -571,7 +612,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_rows_kernel(const Con
                                 pk[2 * q4 + 1] = 0u;
                             }
                         }
-                        if (valid)
+                        if (valid && yo < p.Ho && ((c - 1) >> 1) < p.Wo)
                             *reinterpret_cast<uint4 *>(out_n + (long long)h * p.out_plane + opos) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }
                 } else {
@@ -1340,18 +1381,31 @@ static bool plan_rows(const LayerGeom &g, ConvPlan &pl) {
     // Pooled layers only: without the in-register pooling the variant merely ties with the raster kernel
     // (measured on layer 2: 184-209 us vs 180 us per 1024 samples); ASR_CONV_ROWS=2 forces it for those too.
     if (!enabled || (!g.pool && enabled < 2)) return false;
-    if (NP > 32 || (Hc % RS_R) != 0 || (g.pool && (g.W & 1)) || KC / 2 > 2) return false;
-    const int JT = (g.W + 127) / 128;
-    if (g.W * 10 < JT * 128 * 7) return false;                 // < 70 % of the MMA rows would be real pixels
+    if (NP > 48 || Hc < RS_R || (Hc & 1) || KC / 2 > 3 || (KC & 1)) return false;
     pl = ConvPlan();
-    pl.rows = 1; pl.JT = JT; pl.Hc = Hc;
+    // wide images: one sample per tile row, JT tiles across it, rows contiguous as in global memory;
+    // narrow images: SPT samples side by side (pitch SP, even so that pooling pairs stay lane-aligned)
+    const int SP = (Wp + 1) & ~1;
+    if (g.W >= 90 && (!g.pool || !(g.W & 1))) {
+        pl.SPT = 1; pl.SP = Wp; pl.RP = Wp; pl.JT = (g.W + 127) / 128;
+        if (g.W * 10 < pl.JT * 128 * 7) return false;             // < 70 % of the MMA rows would be real pixels
+    } else {
+        pl.SPT = 128 / SP; pl.SP = SP; pl.RP = pl.SPT * SP; pl.JT = 1;
+        // Measured on B200 (per 1024 samples): 40x50 48->48: 137 vs 142 us raster; 20x25: 61 vs 42; 92x42 12->12:
+        // 83 vs 81; 23x10: 72 vs 39 -- the many small bulk copies and the 4-row bands (1.5x halo) eat the MMA
+        // saving, so the side-by-side form stays off unless ASR_CONV_ROWS_MULTI=1.
+        static const int multi = getenv("ASR_CONV_ROWS_MULTI") ? atoi(getenv("ASR_CONV_ROWS_MULTI")) : 0;
+        if (!multi || pl.SPT < 2 || pl.SPT * g.W * 10 < 128 * 6) return false;
+    }
+    pl.rows = 1; pl.Hc = Hc;
     pl.wbytes = 3 * KC * RS_R * NP * 16;
-    pl.slot_cols = RS_R * NP;
+    pl.slot_cols = RS_R * NP <= 64 ? 64 : (RS_R * NP <= 128 ? 128 : 256);
     pl.n_slots = std::min(MAX_SLOTS, 512 / pl.slot_cols);
     pl.tmem_cols = 512;
     pl.TH = 0;
-    for (int th = RS_R; th <= std::min(Hc, 64); th += RS_R) {
-        long long sps = (long long)(th + 2) * Wp * 16;
+    const int Hc4 = (Hc + RS_R - 1) / RS_R * RS_R;
+    for (int th = RS_R; th <= std::min(Hc4, 64); th += RS_R) {
+        long long sps = (long long)(th + 2) * pl.RP * 16;
         long long stage = 16 + KC * sps + TAIL_SLACK;
         long long tot = pl.wbytes + NP * 4 + 128 + 2 * stage + 128 + 256 + 256;
         if (sps / 16 >= 16384 || tot > SMEM_LIMIT) continue;
@@ -1360,8 +1414,8 @@ static bool plan_rows(const LayerGeom &g, ConvPlan &pl) {
     if (!pl.TH) return false;
     pl.n_stages = 2;
     pl.bands = (Hc + pl.TH - 1) / pl.TH;
-    pl.MT = pl.TH / RS_R * JT;
-    pl.sps = (pl.TH + 2) * Wp * 16;
+    pl.MT = pl.TH / RS_R * pl.JT;
+    pl.sps = (pl.TH + 2) * pl.RP * 16;
     pl.stage_bytes = ((16 + KC * pl.sps + TAIL_SLACK) + 127) / 128 * 128;
     pl.staging_bytes = 0;
     int off = pl.wbytes;
@@ -1371,8 +1425,8 @@ static bool plan_rows(const LayerGeom &g, ConvPlan &pl) {
     pl.off_bar = off; off += 256;
     pl.smem_bytes = off;
     pl.wp_magic = pl.wo_magic = 0;
-    // the last view of the last tile reads up to (TH + 1) * Wp + 128 * JT + 2 positions
-    if ((long long)((pl.TH + 1) * Wp + 128 * JT + 2) * 16 > (long long)pl.sps + TAIL_SLACK) return false;
+    // the last view of the last tile reads up to (TH + 1) * RP + 128 * JT + 2 positions
+    if ((long long)((pl.TH + 1) * pl.RP + 128 * pl.JT + 2) * 16 > (long long)pl.sps + TAIL_SLACK) return false;
     return off <= SMEM_LIMIT;
 }
 
@@ -1555,7 +1609,7 @@ int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *d, int max_b
                 const ConvPlan &pl = e->plan[l];
                 fprintf(stderr, "[asr] layer %d: %dx%d cin %d->%d (pad %d->%d) pool %d | %s TH %d bands %d MT %d stages %d slots %d x %d cols "
                         "smem %d B (w %d, stage %d, staging %d)\n", l, g.H, g.W, g.cin, g.cout, g.cinp, g.coutp, g.pool,
-                        pl.rows ? "rows" : "raster", pl.TH,
+                        pl.rows ? (pl.SPT > 1 ? "rows-multi" : "rows") : "raster", pl.TH,
                         pl.bands, pl.MT, pl.n_stages, pl.n_slots, pl.slot_cols, pl.smem_bytes, pl.wbytes, pl.stage_bytes,
                         pl.staging_bytes);
             }
@@ -1615,6 +1669,7 @@ int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *d, int max_b
         E_CUDA(cudaFuncSetAttribute(l0_tc_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         E_CUDA(cudaFuncSetAttribute(conv3x3_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         E_CUDA(cudaFuncSetAttribute(conv3x3_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        E_CUDA(cudaFuncSetAttribute(conv3x3_rows_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         E_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         E_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         E_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
@@ -1710,13 +1765,18 @@ int asr_encoder_embed(asr_encoder_t *e, const void *x_dev, int x_dtype, int64_t 
             p.off_bias = pl.off_bias; p.off_stage = pl.off_stage; p.off_staging = pl.off_staging; p.off_bar = pl.off_bar;
             p.wp_magic = pl.wp_magic; p.wo_magic = pl.wo_magic; p.Hc = pl.Hc; p.JT = pl.JT;
             p.coop = pl.rows && pl.n_slots < 8;
+            p.SPT = pl.rows ? pl.SPT : 1; p.SP = pl.SP; p.RP = pl.RP;
+            p.sp_magic = pl.rows && pl.SPT > 1 ? (unsigned)((0x100000000ull + (unsigned)pl.SP - 1) / (unsigned)pl.SP) : 0u;
             static const int conv_dbg = getenv("ASR_CONV_DEBUG") ? atoi(getenv("ASR_CONV_DEBUG")) : 0;
             p.dbg = conv_dbg;
             const int items = (int)nn * pl.bands;
             const int grid = std::min(items, sm_count());
             if (pl.rows) {
-                if (p.KC / 2 == 1) conv3x3_rows_kernel<1><<<grid, CONV_THREADS, pl.smem_bytes, st>>>(p);
-                else conv3x3_rows_kernel<2><<<grid, CONV_THREADS, pl.smem_bytes, st>>>(p);
+                const int sgroups = ((int)nn + pl.SPT - 1) / pl.SPT;
+                const int rgrid = std::min(sgroups * pl.bands, sm_count());
+                if (p.KC / 2 == 1) conv3x3_rows_kernel<1><<<rgrid, CONV_THREADS, pl.smem_bytes, st>>>(p);
+                else if (p.KC / 2 == 2) conv3x3_rows_kernel<2><<<rgrid, CONV_THREADS, pl.smem_bytes, st>>>(p);
+                else conv3x3_rows_kernel<3><<<rgrid, CONV_THREADS, pl.smem_bytes, st>>>(p);
                 ASR_LAUNCH_CHECK();
                 return ASR_OK;
             }

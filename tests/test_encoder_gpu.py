@@ -203,3 +203,45 @@ def test_small_and_ragged_batches(n):
     m = min(n, 16)
     got1, got2 = e1.embed_host(X1[:n].astype(np.uint8)), e2.embed_host(X2[:n])
     assert (got1[:m] == full1[:m]).all() and (got2[:m] == full2[:m]).all()
+
+
+_VARIANT_SNIPPET = r"""
+import sys, numpy as np
+sys.path.insert(0, {root!r})
+import importlib
+from oracle.encoders import synth_inputs
+from audio_sheet_retrieval_b200 import _lib, network
+from audio_sheet_retrieval_b200.params import load_params
+out = {{}}
+for name, pkl in {pkl!r}.items():
+    model = importlib.import_module("audio_sheet_retrieval_b200.models." + name)
+    layers = model.build_model(show_model=False)
+    net = layers[0].net
+    net.max_batch = 16
+    network.set_all_param_values(layers, load_params(pkl))
+    X1, X2 = synth_inputs(7, seed=21)
+    out[name + "_1"] = net.encoder(1, model.prepare.asr_prepare_mode).embed_host(X1.astype(np.uint8))
+    out[name + "_2"] = net.encoder(2, _lib.PREP_NONE).embed_host(X2)
+np.savez({dst!r}, **out)
+"""
+
+
+@pytest.mark.parametrize("env", [{}, {"ASR_CONV_ROWS": "0"}, {"ASR_L0_TC": "0"}, {"ASR_CONV_ROWS_MULTI": "1"},
+                                 {"ASR_CONV_ROWS": "2"}])
+def test_kernel_variants_agree(env, tmp_path):
+    """The kernel-selection switches are read once per process, so each variant runs in its own interpreter:
+    raster-only conv, CUDA-core layer 0, side-by-side narrow tiles and row-stacked non-pooled layers must all
+    reproduce the oracle to the same tolerance as the default selection."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dst = str(tmp_path / "codes.npz")
+    e = dict(os.environ)
+    e.update(env)
+    subprocess.run([sys.executable, "-c", _VARIANT_SNIPPET.format(root=root, dst=dst, pkl=PKL)], check=True, env=e, cwd=root, timeout=600)
+    got = np.load(dst)
+    X1, X2 = synth_inputs(7, seed=21)
+    for name in ("mutopia_ccal_cont", "mutopia_ccal_cont_rsz"):
+        onet = OracleNet(name, load_param_list(PKL[name]))
+        assert _cos(got[name + "_1"], onet.compute_view_1(X1)).min() >= COS_TOL, (env, name, 1)
+        assert _cos(got[name + "_2"], onet.compute_view_2(X2)).min() >= COS_TOL, (env, name, 2)
