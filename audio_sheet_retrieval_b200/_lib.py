@@ -76,6 +76,9 @@ def _load():
     lib.asr_cca_accumulate.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.asr_cca_solve.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_double, c_double, c_double, c_int,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.asr_contrastive_loss.argtypes = [c_void_p, c_void_p, c_int64, c_float, c_float, c_int, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p]
+    lib.asr_contrastive_loss.restype = c_int
     for name in ("asr_encoder_create", "asr_encoder_destroy", "asr_encoder_set_cca", "asr_encoder_embed",
                  "asr_encoder_embed_host", "asr_encoder_debug_activation", "asr_encoder_set_timing",
                  "asr_encoder_get_timing", "asr_db_create", "asr_db_destroy",

@@ -178,6 +178,17 @@ int asr_cosine_distances(const float *a_dev, int r, const float *b_dev, int c, d
 int asr_dtw(const double *dist_dev, int r, int c, double *acc_dev, int32_t *path_i_dev, int32_t *path_j_dev,
             int32_t *path_len_dev, void *stream);
 
+/* ------------------------------------------------------------------------- *
+ * Training objective (SURVEY 8f "next" row 4, first slice).  Replaces the Theano graph of
+ * get_contrastive_cos_loss(weight, gamma, symmetric) (asr/models/objectives.py:30-69) and the
+ * gradient Theano derives from it.
+ * ------------------------------------------------------------------------- */
+/* lv1_dev, lv2_dev (n,32) float32 codes of matching pairs (row i of one view belongs to row i of the other).
+ * loss_dev: 1 float.  grad1_dev / grad2_dev: (n,32) float32 d loss / d lv1, d loss / d lv2, or NULL.
+ * scratch_dev: n doubles.  2 <= n <= 8192.  Deterministic (fixed reduction order). */
+int asr_contrastive_loss(const float *lv1_dev, const float *lv2_dev, int64_t n, float weight, float gamma, int symmetric,
+                         double *scratch_dev, float *loss_dev, float *grad1_dev, float *grad2_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -151,3 +151,34 @@ def test_dtw_matches_reference(golden):
                                    np.arange(90) * 2 + 10, "pydtw")
     assert (r["aligned_sheet_idxs"] == golden["al_aligned"]).all()
     np.testing.assert_allclose([m[k] for k in sorted(m)], golden["al_map_v"], atol=1e-12)
+
+
+def _loss_cases():
+    import os
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_contrastive_loss.npz"))
+    for ci in range(4):
+        lv1, lv2 = d["c%d_lv1" % ci], d["c%d_lv2" % ci]
+        for weight, gamma, sym in ((1.0, 0.7, False), (1.0, 0.7, True), (0.35, 0.2, True)):
+            yield lv1, lv2, weight, gamma, sym, float(d["c%d_w%g_g%g_s%d" % (ci, weight, gamma, int(sym))])
+
+
+def test_contrastive_loss_matches_reference():
+    """Oracle forward vs the value the reference's own get_contrastive_cos_loss computes (objectives.py:30-69)."""
+    from oracle.objectives import contrastive_cos_loss_ref
+    for lv1, lv2, weight, gamma, sym, want in _loss_cases():
+        got = contrastive_cos_loss_ref(lv1, lv2, weight, gamma, sym)
+        assert abs(got - want) <= 1e-6 * max(1.0, abs(want)), (weight, gamma, sym, got, want)
+
+
+def test_contrastive_loss_gradient_is_the_derivative_of_the_pinned_forward():
+    from oracle.objectives import contrastive_cos_grads_ref, contrastive_cos_loss_ref
+    rng = np.random.RandomState(5)
+    for lv1, lv2, weight, gamma, sym, _ in list(_loss_cases())[:6]:
+        g1, g2 = contrastive_cos_grads_ref(lv1, lv2, weight, gamma, sym)
+        for _ in range(6):          # directional central differences (the hinge is piecewise linear)
+            e1, e2 = rng.randn(*lv1.shape), rng.randn(*lv2.shape)
+            h = 1e-6
+            num = (contrastive_cos_loss_ref(lv1 + h * e1, lv2 + h * e2, weight, gamma, sym) -
+                   contrastive_cos_loss_ref(lv1 - h * e1, lv2 - h * e2, weight, gamma, sym)) / (2 * h)
+            ana = (g1 * e1).sum() + (g2 * e2).sum()
+            assert abs(num - ana) <= 1e-5 * max(1.0, abs(ana)) + 2e-6, (num, ana)
