@@ -311,7 +311,7 @@ def main():
     torch.cuda.synchronize()
     e1.embed_host(h1[:mb * 4]); e2.embed_host(h2[:mb * 4])          # warm the staging buffers / streams
     barrier()
-    k_e2e = max(1, min(args.steps, 3))
+    k_e2e = max(1, args.steps)
     t0 = time.perf_counter()
     for _ in range(k_e2e):
         c1h = e1.embed_host(h1)
@@ -322,9 +322,19 @@ def main():
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_value = world * n_e2e / float(dt.item())
     same = bool(np.array_equal(c1h, codes1[:n_e2e].cpu().numpy()) and np.array_equal(c2h, codes2[:n_e2e].cpu().numpy()))
+    # what the host link gives a plain pinned copy of the same bytes (explains e2e vs value)
+    hv = h1.view(-1)[:min(h1.numel(), 1 << 30)]
+    dv = torch.empty_like(hv, device=dev)
+    dv.copy_(hv, non_blocking=True); torch.cuda.synchronize()
+    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0.record(); dv.copy_(hv, non_blocking=True); l1.record(); torch.cuda.synchronize()
+    link_gbs = hv.numel() / (l0.elapsed_time(l1) * 1e-3) / 1e9
+    del dv
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_e2e * (160 * 200 + 92 * 42 * 4),
            "d2h_bytes_per_step": n_e2e * 2 * 32 * 4, "steps": k_e2e,
-           "api": "asr_encoder_embed_host (what RetrievalWrapper.compute_view_1/2 call)", "codes_equal_device_path": same}
+           "api": "asr_encoder_embed_host (what RetrievalWrapper.compute_view_1/2 call)", "codes_equal_device_path": same,
+           "h2d_gbs_used": n_e2e * (160 * 200 + 92 * 42 * 4) / float(dt.item()) / 1e9,
+           "h2d_gbs_plain_pinned_copy": link_gbs}
     del h1, h2
 
     line = {
