@@ -297,7 +297,10 @@ def main():
     roofline = {"bound": "tensor", "kernel": "conv3x3_rows_kernel + conv3x3_tc_kernel (tcgen05 implicit GEMM, layers 1-7 of both branches)",
                 "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
                 "peak_source": pk["src"] + ", sustained figure (kernel timed inside a long step)",
-                "traffic": None, "avg_launch_ms": conv_ms / max(conv_launches, 1), "launches": conv_launches,
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the 14 conv launches of one
+                # 1024-pair chunk: ncu capture profiles/r1_launches_final.csv (3397 MB / 14); other chunk sizes: not captured
+                "traffic": 242.6e6 if mb == 1024 else None,
+                "avg_launch_ms": conv_ms / max(conv_launches, 1), "launches": conv_launches,
                 "algorithmic_flops_per_pair": conv_flops_pair,
                 "share_of_step": conv_ms / (ms_step * args.steps),
                 "other_ms_per_step": {"layer0_tcgen05_toeplitz": (t1["ms_layer0"] + t2["ms_layer0"]) / args.steps,
@@ -358,7 +361,10 @@ def main():
             line["retrieval"] = r
             line["roofline_retrieval"] = {"bound": "hbm", "kernel": "topk_stream_kernel (Q=1, k=25, %d-row fp32 DB)" % args.db_rows,
                                           "achieved": r["q1"]["algorithmic_gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
-                                          "frac": r["q1"]["hbm_frac"], "traffic": None}
+                                          "frac": r["q1"]["hbm_frac"],
+                                          # ncu dram__bytes_read.sum of one launch over the 10^7-row DB = 1.280 GB,
+                                          # exactly the algorithmic bytes (profiles/r1_topk_ncu_summary.md)
+                                          "traffic": 1.28e9 if args.db_rows == 10000000 else None}
             line["piece_identification"] = piece_id_leg(torch, dev, rank, world)
         except Exception as ex:  # report, never hide
             line["retrieval_error"] = repr(ex)
