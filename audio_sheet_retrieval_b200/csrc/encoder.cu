@@ -1950,10 +1950,12 @@ int asr_encoder_embed_host(asr_encoder_t *e, const void *x_host, int x_dtype, in
     cudaGetLastError();
     if (!pinned && !e->pin_in[0])
         for (int b = 0; b < 2; ++b) ASR_CUDA(cudaMallocHost(&e->pin_in[b], max_bytes));
-    int64_t ci = 0;
-    for (int64_t s0 = 0; s0 < n; s0 += e->max_batch, ++ci) {
+    // Chunk sizes ramp up (512, 1024, ... max_batch): the first host->device copy is the only one that no
+    // compute hides, so it is kept short; every later copy overlaps the chunk before it.
+    int64_t ci = 0, cur = std::min<int64_t>(e->max_batch, 512), nb = 0;
+    for (int64_t s0 = 0; s0 < n; s0 += nb, ++ci, cur = std::min<int64_t>(2 * cur, e->max_batch)) {
         const int b = (int)(ci & 1);
-        const int64_t nb = std::min<int64_t>(e->max_batch, n - s0);
+        nb = std::min<int64_t>(cur, n - s0);
         const uint8_t *src = reinterpret_cast<const uint8_t *>(x_host) + (size_t)s0 * sample_bytes;
         if (ci >= 2) ASR_CUDA(cudaStreamWaitEvent(e->s_copy, e->ev_done[b], 0));
         if (!pinned) {

@@ -117,7 +117,7 @@ def cpu_reference_pairs_per_s(n_sample, steps=1, warmup=0):
 def run_reference(args, rank):
     if rank != 0:
         return
-    n_sample = args.cpu_sample
+    n_sample = args.cpu_sample or 1024
     v, dt, cores = cpu_reference_pairs_per_s(n_sample, steps=args.steps, warmup=min(args.warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -210,8 +210,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=100000, help="pairs per GPU per step")
-    ap.add_argument("--max-batch", type=int, default=1024)
-    ap.add_argument("--cpu-sample", type=int, default=256, help="pairs in the CPU baseline sample")
+    ap.add_argument("--max-batch", type=int, default=4096, help="samples per launch (activation arena: ~2.7 MB per pair)")
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="pairs per CPU step (default: 1024 per step for --impl reference, 4096 for the cpu_baseline leg)")
     ap.add_argument("--db-rows", type=int, default=10000000)
     ap.add_argument("--skip-extras", action="store_true", help="only the headline leg (used under ncu)")
     args = ap.parse_args()
@@ -298,8 +299,9 @@ def main():
                 "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
                 "peak_source": pk["src"] + ", sustained figure (kernel timed inside a long step)",
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the 14 conv launches of one
-                # 1024-pair chunk: ncu capture profiles/r1_launches_final.csv (3397 MB / 14); other chunk sizes: not captured
-                "traffic": 242.6e6 if mb == 1024 else None,
+                # chunk pair: ncu captures profiles/r1_launches_mb4096.csv (14945 MB / 14) and r1_launches_final.csv
+                # (1024-pair chunks, 3397 MB / 14); other chunk sizes: not captured
+                "traffic": {4096: 1067.5e6, 1024: 242.6e6}.get(mb),
                 "avg_launch_ms": conv_ms / max(conv_launches, 1), "launches": conv_launches,
                 "algorithmic_flops_per_pair": conv_flops_pair,
                 "share_of_step": conv_ms / (ms_step * args.steps),
@@ -370,9 +372,11 @@ def main():
             line["retrieval_error"] = repr(ex)
     if rank == 0 and world == 1 and not args.skip_extras:
         try:
-            v, dt_cpu, cores = cpu_reference_pairs_per_s(args.cpu_sample, steps=1, warmup=1)
+            cpu_n = args.cpu_sample or 4096             # ~10-15 s of CPU work on 16 cores
+            cpu_reference_pairs_per_s(128, steps=1, warmup=0)   # warm the thread pool / allocator on a small sample
+            v, dt_cpu, cores = cpu_reference_pairs_per_s(cpu_n, steps=1, warmup=0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "%d pairs (%.1f s), torch-CPU fp32 oracle port of the reference path" % (args.cpu_sample, dt_cpu)}
+                                    "sample": "%d pairs (%.1f s), torch-CPU fp32 oracle port of the reference path" % (cpu_n, dt_cpu)}
         except Exception as ex:
             line["cpu_baseline"] = {"error": repr(ex)}
     if rank == 0:
