@@ -218,7 +218,7 @@ topk_stream_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int t
             float v[32];
 #pragma unroll
             for (int kk = 0; kk < 32; ++kk) v[kk] = tid < nq_tile ? q[(int64_t)(q0 + tid) * 32 + kk] : 0.f;
-            if (normalise && tid < nq_tile) normalise32(v);
+            if ((normalise & 1) && tid < nq_tile) normalise32(v);
 #pragma unroll
             for (int kk = 0; kk < 32; ++kk) sm.q[tid][kk] = v[kk];
             sm.qcount[tid] = 0;
@@ -264,7 +264,7 @@ topk_stream_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int t
             if (tid == 0 && it > 1) sm.flush_flag[(it - 2) % 3] = 0;
             const int64_t row = (tile0 + it) * TK_ROWS + tid;
             const bool valid = row < n_db;
-            if (normalise) normalise32(d);
+            if (normalise & 2) normalise32(d);       // bit 1 clear: the rows come from the pinned-normalised copy
             int overflow = 0;
             if (QT == 1) {
                 float s = score32(sm.q[0], d);
@@ -300,12 +300,18 @@ topk_stream_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int t
 // Merge n_lists sorted lists (each k long) per query into the final top-k.  One CTA of four
 // warps per query: warp w folds lists w, w+4, ... into its own list, warp 0 folds the four.
 // Input either (uint32 local rows + idx_base) or int64 global indices.
-constexpr int MG_WARPS = 4;
+// MG_WARPS warps per query fold the per-slice lists (few lists per query, or 64-bit indices after the
+// multi-GPU all-gather); see topk_merge_select_kernel for the many-lists case.
+template <int MG_WARPS>
 __global__ void __launch_bounds__(MG_WARPS * 32)
 topk_merge_kernel(const float *__restrict__ in_s, const uint32_t *__restrict__ in_i32, const int64_t *__restrict__ in_i64,
                   int64_t idx_base, int n_lists, int k, float *__restrict__ out_s, int64_t *__restrict__ out_i) {
-    __shared__ float ls[MG_WARPS][2][ASR_MAX_K];
-    __shared__ int64_t li[MG_WARPS][2][ASR_MAX_K];
+    extern __shared__ __align__(16) uint8_t mg_raw[];
+    // [warp][2][k] int64 indices, then [warp][2][k] float scores
+    int64_t *li_base = reinterpret_cast<int64_t *>(mg_raw);
+    float *ls_base = reinterpret_cast<float *>(mg_raw + (size_t)MG_WARPS * 2 * k * sizeof(int64_t));
+    auto LS = [&](int w, int c) { return ls_base + ((size_t)w * 2 + c) * k; };
+    auto LI = [&](int w, int c) { return li_base + ((size_t)w * 2 + c) * k; };
     __shared__ int wlen[MG_WARPS], wcur[MG_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t qi = blockIdx.x;
@@ -317,11 +323,11 @@ topk_merge_kernel(const float *__restrict__ in_s, const uint32_t *__restrict__ i
         if (alive && len == k) alive = beats_t<int64_t>(cs, ci, thr_s, thr_i);
         const unsigned mask = __ballot_sync(0xffffffffu, alive);
         if (mask == 0u) return;
-        warp_merge_batch<int64_t>(ls[w][cur], li[w][cur], ls[w][cur ^ 1], li[w][cur ^ 1], len, k, cs, ci, alive, mask,
+        warp_merge_batch<int64_t>(LS(w, cur), LI(w, cur), LS(w, cur ^ 1), LI(w, cur ^ 1), len, k, cs, ci, alive, mask,
                                   (int64_t)INT64_MAX, lane);
         len = min(k, len + __popc(mask));
         cur ^= 1;
-        if (len == k) { thr_s = ls[w][cur][k - 1]; thr_i = li[w][cur][k - 1]; }
+        if (len == k) { thr_s = LS(w, cur)[k - 1]; thr_i = LI(w, cur)[k - 1]; }
         __syncwarp();
     };
     // phase 1: each warp folds its lists; candidates are taken position-major across lists so the
@@ -358,16 +364,134 @@ topk_merge_kernel(const float *__restrict__ in_s, const uint32_t *__restrict__ i
             for (int b = 0; b < n; b += 32) {
                 int c = b + lane;
                 bool alive = c < n;
-                float cs = alive ? ls[w][c2][c] : -CUDART_INF_F;
-                int64_t ci = alive ? li[w][c2][c] : INT64_MAX;
+                float cs = alive ? LS(w, c2)[c] : -CUDART_INF_F;
+                int64_t ci = alive ? LI(w, c2)[c] : INT64_MAX;
                 fold(cs, ci, alive, 0);
             }
         }
         for (int j = lane; j < k; j += 32) {
             bool v = j < len;
-            out_s[(size_t)qi * k + j] = v ? ls[0][cur][j] : -CUDART_INF_F;
-            out_i[(size_t)qi * k + j] = v ? li[0][cur][j] : -1;
+            out_s[(size_t)qi * k + j] = v ? LS(0, cur)[j] : -CUDART_INF_F;
+            out_i[(size_t)qi * k + j] = v ? LI(0, cur)[j] : -1;
         }
+    }
+}
+
+// Merge for few queries and MANY lists (the streaming-server case: one query, one list per CTA of the stream
+// kernel = 444 lists): the fold above is a chain of dependent global loads (62 us measured at 444 x 25).  Here
+// every candidate becomes a unique 64-bit key (order-preserving score bits | ~row: larger = better, i.e. score
+// descending then row ascending), each thread keeps its keys in registers, an 8-pass byte-wise radix select finds
+// the k-th largest key exactly, and the k survivors are ranked by counting.  Deterministic, no overflow case.
+constexpr int MS_THREADS = 512, MS_KPT = 24;      // up to 12288 candidates per query
+__device__ __forceinline__ uint32_t f2ord(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t o) {
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+__global__ void __launch_bounds__(MS_THREADS)
+topk_merge_select_kernel(const float *__restrict__ in_s, const uint32_t *__restrict__ in_i32, int64_t idx_base, int n_cand,
+                         int k, float *__restrict__ out_s, int64_t *__restrict__ out_i) {
+    __shared__ unsigned hist[256];
+    __shared__ unsigned long long sel[ASR_MAX_K];
+    __shared__ unsigned long long prefix_sm;
+    __shared__ int krem_sm, nsel, nvalid_sm;
+    const int tid = threadIdx.x;
+    const size_t base = (size_t)blockIdx.x * n_cand;
+    unsigned long long key[MS_KPT];
+    int mine = 0;
+#pragma unroll
+    for (int j = 0; j < MS_KPT; ++j) {
+        const int c = tid + j * MS_THREADS;
+        key[j] = 0ull;                                   // 0 = "no candidate" (a real key has ~row != 0 or score bits != 0)
+        // both loads unconditional (clamped) so that all 48 of a thread are in flight together
+        const size_t o = base + (size_t)min(c, n_cand - 1);
+        const uint32_t r = in_i32[o];
+        const float sc = in_s[o];
+        if (c < n_cand && r != 0xffffffffu) { key[j] = ((unsigned long long)f2ord(sc) << 32) | (unsigned long long)(~r); ++mine; }
+    }
+    if (tid == 0) { nvalid_sm = 0; nsel = 0; prefix_sm = 0ull; }
+    __syncthreads();
+    if (mine) atomicAdd(&nvalid_sm, mine);
+    __syncthreads();
+    const int k_eff = min(k, nvalid_sm);
+    if (tid == 0) krem_sm = k_eff;
+    // radix select of the k_eff-th largest key, most significant byte first
+    for (int pass = 7; pass >= 0 && k_eff > 0; --pass) {
+        if (tid < 256) hist[tid] = 0u;
+        __syncthreads();
+        const unsigned long long prefix = prefix_sm;
+#pragma unroll
+        for (int j = 0; j < MS_KPT; ++j) {
+            const unsigned long long kk = key[j];
+            const bool match = kk != 0ull && (pass == 7 || (kk >> (8 * (pass + 1))) == prefix);
+            const unsigned bin = match ? ((unsigned)(kk >> (8 * pass)) & 255u) : 256u;
+            if (pass >= 5) {
+                // leading bytes of cosine scores are nearly all equal: aggregate per warp, plain atomics would serialise
+                const unsigned peers = __match_any_sync(0xffffffffu, bin);
+                if (match && (int)(__ffs(peers) - 1) == (tid & 31)) atomicAdd(&hist[bin], (unsigned)__popc(peers));
+            } else if (match) {
+                // by now only the keys near the threshold still match the prefix, spread over many bins
+                atomicAdd(&hist[bin], 1u);
+            }
+        }
+        __syncthreads();
+        if (tid < 32) {      // warp 0 walks the histogram from the top: lane l owns bins 255 - 8 l ... 248 - 8 l
+            unsigned h[8], tot = 0u;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { h[i] = hist[255 - 8 * tid - i]; tot += h[i]; }
+            unsigned inc = tot;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, inc, off);
+                if (tid >= off) inc += t;
+            }
+            const unsigned exc = inc - tot, rem = (unsigned)krem_sm;
+            __syncwarp();
+            if (exc < rem && rem <= inc) {            // the wanted key lies in this lane's bins (exactly one lane)
+                unsigned r = rem - exc;
+                int i = 0;
+                for (; i < 7; ++i) {
+                    if (h[i] >= r) break;
+                    r -= h[i];
+                }
+                krem_sm = (int)r;
+                prefix_sm = (prefix << 8) | (unsigned long long)(255 - 8 * tid - i);
+            }
+        }
+        __syncthreads();
+    }
+    const unsigned long long T = prefix_sm;             // the k_eff-th largest key (keys are unique)
+    if (k_eff > 0) {
+#pragma unroll
+        for (int j = 0; j < MS_KPT; ++j) {
+            if (key[j] != 0ull && key[j] >= T) sel[atomicAdd(&nsel, 1)] = key[j];
+        }
+    }
+    __syncthreads();
+    for (int j = tid; j < k; j += MS_THREADS) {
+        if (j < k_eff) {
+            const unsigned long long mk = sel[j];
+            int rank = 0;
+            for (int t = 0; t < k_eff; ++t) rank += sel[t] > mk ? 1 : 0;
+            out_s[(size_t)blockIdx.x * k + rank] = ord2f((uint32_t)(mk >> 32));
+            out_i[(size_t)blockIdx.x * k + rank] = (int64_t)(~(uint32_t)mk) + idx_base;
+        } else {
+            out_s[(size_t)blockIdx.x * k + j] = -CUDART_INF_F;
+            out_i[(size_t)blockIdx.x * k + j] = -1;
+        }
+    }
+}
+
+// few queries over many per-slice lists: radix-select merge; otherwise the 4-warp fold
+static void launch_merge(const float *in_s, const uint32_t *in_i32, const int64_t *in_i64, int64_t idx_base, int n_lists, int k,
+                         float *out_s, int64_t *out_i, int64_t nq, cudaStream_t st) {
+    if (in_i32 && nq <= 8 && n_lists >= 64 && (int64_t)n_lists * k <= (int64_t)MS_THREADS * MS_KPT) {
+        topk_merge_select_kernel<<<(unsigned)nq, MS_THREADS, 0, st>>>(in_s, in_i32, idx_base, n_lists * k, k, out_s, out_i);
+    } else {
+        const size_t smem = (size_t)4 * 2 * k * (sizeof(int64_t) + sizeof(float));
+        topk_merge_kernel<4><<<(unsigned)nq, 4 * 32, smem, st>>>(in_s, in_i32, in_i64, idx_base, n_lists, k, out_s, out_i);
     }
 }
 
@@ -963,6 +1087,7 @@ int asr_db_create(asr_db_t **out, const float *codes_dev, int64_t n, int64_t idx
         ASR_CUDA(cudaFuncSetAttribute(rank_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)sizeof(RkSmem) + 1024));
         ASR_CUDA(cudaFuncSetAttribute(topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcSmem)));
+
         attr_done = true;
     }
     *out = db;
@@ -1000,21 +1125,30 @@ static void plan_grid(const asr_db *db, int64_t nq, int qt, int ctas_per_sm, int
 
 static float *g_tc_dbg = nullptr;   // set by asr_debug_tc_scores
 
+// First cosine query of a DB: a copy of its rows normalised with the pinned definition (the same function
+// the kernels apply per row, so every later result is bit-identical) + its tensor map.  Halves the dependent
+// add chain per row of the streaming kernel and is the B operand of the tensor-core pre-filter.  The DB
+// contents must not change after asr_db_create.
+static int ensure_normalised_copy(asr_db *db, cudaStream_t st) {
+    if (db->codes_n) return ASR_OK;
+    ASR_CUDA(cudaMalloc(&db->codes_n, (size_t)db->n * 128));
+    normalise_rows_kernel<<<(unsigned)((db->n + 255) / 256), 256, 0, st>>>(db->codes, db->n, db->codes_n);
+    ASR_LAUNCH_CHECK();
+    cuuint64_t gdim[2] = {32, (cuuint64_t)db->n};
+    cuuint64_t gstr[1] = {128};
+    cuuint32_t box[2] = {32, (cuuint32_t)TC_ROWS};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = get_encode_fn()(&db->tmap_n, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, db->codes_n, gdim, gstr, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (normalised copy) failed"); return ASR_ERR_CUDA; }
+    return ASR_OK;
+}
+
 static int topk_tc(asr_db *db, const float *q_dev, int64_t nq, int k, float *out_score_dev, int64_t *out_idx_dev,
                    cudaStream_t st) {
-    if (!db->codes_n) {     // first use: pinned-normalised copy + tensor map (not on the steady-state path)
-        ASR_CUDA(cudaMalloc(&db->codes_n, (size_t)db->n * 128));
-        normalise_rows_kernel<<<(unsigned)((db->n + 255) / 256), 256, 0, st>>>(db->codes, db->n, db->codes_n);
-        ASR_LAUNCH_CHECK();
-        cuuint64_t gdim[2] = {32, (cuuint64_t)db->n};
-        cuuint64_t gstr[1] = {128};
-        cuuint32_t box[2] = {32, (cuuint32_t)TC_ROWS};
-        cuuint32_t estr[2] = {1, 1};
-        CUresult r = get_encode_fn()(&db->tmap_n, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, db->codes_n, gdim, gstr, box, estr,
-                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (normalised copy) failed"); return ASR_ERR_CUDA; }
-    }
+    int rcn = ensure_normalised_copy(db, st);
+    if (rcn) return rcn;
     if (db->qn_cap < nq) {
         cudaFree(db->qn);
         db->qn = nullptr;
@@ -1050,8 +1184,7 @@ static int topk_tc(asr_db *db, const float *q_dev, int64_t nq, int k, float *out
         topk_tc_kernel<<<grid, TC_THREADS, sizeof(TcSmem), st>>>(db->tmap_n, db->n, tps, n_slices, db->qn + q0 * 32, (int)nqc,
                                                                  k, 0.00390625f, ps, pi, counter, g_tc_dbg);
         ASR_LAUNCH_CHECK();
-        topk_merge_kernel<<<(unsigned)nqc, MG_WARPS * 32, 0, st>>>(ps, pi, nullptr, db->idx_base, n_slices, k,
-                                                                  out_score_dev + q0 * k, out_idx_dev + q0 * k);
+        launch_merge(ps, pi, nullptr, db->idx_base, n_slices, k, out_score_dev + q0 * k, out_idx_dev + q0 * k, nqc, st);
         ASR_LAUNCH_CHECK();
     }
     return ASR_OK;
@@ -1071,6 +1204,13 @@ int asr_topk(asr_db_t *db, const float *q_dev, int64_t nq, int k, int normalise,
     // measured crossover (1e7 rows, k = 25): the exact QT=16 kernel wins up to ~24 queries
     const bool want_tc = force ? (strcmp(force, "tc") == 0) : (nq > 24);
     if (want_tc && normalise && k <= TC_KMAX) return topk_tc(db, q_dev, nq, k, out_score_dev, out_idx_dev, st);
+    // cosine queries stream the pinned-normalised copy (kernel flag bit 0: normalise queries, bit 1: normalise rows)
+    if (normalise) {
+        int rcn = ensure_normalised_copy(db, st);
+        if (rcn) return rcn;
+    }
+    const CUtensorMap &tm = normalise ? db->tmap_n : db->tmap;
+    const int nflag = normalise ? 1 : 0;
     const int qt = nq <= 2 ? 1 : (nq <= 8 ? 4 : 16);
     const int occ = qt == 1 ? 3 : (qt == 4 ? 2 : 1);
     int n_slices, tps, qg0;
@@ -1087,16 +1227,15 @@ int asr_topk(asr_db_t *db, const float *q_dev, int64_t nq, int k, int normalise,
         dim3 grid(n_slices, qg);
         if (qt == 1)
             topk_stream_kernel<1, 2, 3><<<grid, TK_THREADS, sizeof(TkSmem<1, 2>) + 1024, st>>>(
-                db->tmap, db->n, tps, q_dev + q0 * 32, (int)nqc, k, normalise, ps, pi);
+                tm, db->n, tps, q_dev + q0 * 32, (int)nqc, k, nflag, ps, pi);
         else if (qt == 4)
             topk_stream_kernel<4, 2, 2><<<grid, TK_THREADS, sizeof(TkSmem<4, 2>) + 1024, st>>>(
-                db->tmap, db->n, tps, q_dev + q0 * 32, (int)nqc, k, normalise, ps, pi);
+                tm, db->n, tps, q_dev + q0 * 32, (int)nqc, k, nflag, ps, pi);
         else
             topk_stream_kernel<16, 3, 1><<<grid, TK_THREADS, sizeof(TkSmem<16, 3>) + 1024, st>>>(
-                db->tmap, db->n, tps, q_dev + q0 * 32, (int)nqc, k, normalise, ps, pi);
+                tm, db->n, tps, q_dev + q0 * 32, (int)nqc, k, nflag, ps, pi);
         ASR_LAUNCH_CHECK();
-        topk_merge_kernel<<<(unsigned)nqc, MG_WARPS * 32, 0, st>>>(ps, pi, nullptr, db->idx_base, n_slices, k,
-                                                                  out_score_dev + q0 * k, out_idx_dev + q0 * k);
+        launch_merge(ps, pi, nullptr, db->idx_base, n_slices, k, out_score_dev + q0 * k, out_idx_dev + q0 * k, nqc, st);
         ASR_LAUNCH_CHECK();
     }
     return ASR_OK;
@@ -1127,8 +1266,7 @@ int asr_topk_merge(const float *score_dev, const int64_t *idx_dev, int64_t nq, i
     ASR_CHECK_ARG(k >= 1 && k <= ASR_MAX_K && n_lists >= 1, "bad k / n_lists");
     if (nq == 0) return ASR_OK;
     ASR_CHECK_ARG(score_dev && idx_dev && out_score_dev && out_idx_dev, "NULL buffer");
-    topk_merge_kernel<<<(unsigned)nq, MG_WARPS * 32, 0, (cudaStream_t)stream>>>(score_dev, nullptr, idx_dev, 0, n_lists, k,
-                                                                               out_score_dev, out_idx_dev);
+    launch_merge(score_dev, nullptr, idx_dev, 0, n_lists, k, out_score_dev, out_idx_dev, nq, (cudaStream_t)stream);
     ASR_LAUNCH_CHECK();
     return ASR_OK;
 }

@@ -187,3 +187,25 @@ def test_topk_near_ties_within_prefilter_margin(monkeypatch, path):
     s_ref, i_ref = clib.topk(Q, D, 25)
     s, i = EmbeddingDB(D).topk(Q, 25)
     assert (i == i_ref).all() and (s == s_ref).all()
+
+
+@pytest.mark.parametrize("nq,k", [(1, 25), (3, 27), (8, 1), (2, 25)])
+def test_many_slices_select_merge_ties_and_degenerate_rows(nq, k):
+    """Few queries over a DB large enough for one list per resident CTA (444 slices): the radix-select
+    merge.  Duplicated rows (ties resolve by index), zero rows (NaN -> -inf, never selected), an index
+    base, and a DB of identical rows (every score equal: pure index order)."""
+    from audio_sheet_retrieval_b200.retrieval import EmbeddingDB
+    n = 400000
+    D = _db(n, 31)
+    D[123456] = D[7] = D[399999] = D[250000]      # exact duplicates across slices
+    D[1000:1100] = 0
+    Q = np.concatenate([D[250000:250001], _db(nq, 32, unit=False)])[:nq]
+    s_ref, i_ref = clib.topk(Q, D, k)
+    db = EmbeddingDB(D, idx_base=1 << 33)
+    s, i = db.topk(Q, k)
+    assert (i - (1 << 33) == i_ref).all() and (s.view(np.uint32) == s_ref.view(np.uint32)).all()
+    if k >= 4:
+        assert list(i[0, :4] - (1 << 33)) == [7, 123456, 250000, 399999]
+    E = np.tile(_db(1, 33), (n, 1))
+    s2, i2 = EmbeddingDB(E).topk(Q[:1], k)
+    assert list(i2[0]) == list(range(k)) and (s2[0] == s2[0, 0]).all()
