@@ -382,7 +382,7 @@ topk_merge_kernel(const float *__restrict__ in_s, const uint32_t *__restrict__ i
 // every candidate becomes a unique 64-bit key (order-preserving score bits | ~row: larger = better, i.e. score
 // descending then row ascending), each thread keeps its keys in registers, an 8-pass byte-wise radix select finds
 // the k-th largest key exactly, and the k survivors are ranked by counting.  Deterministic, no overflow case.
-constexpr int MS_THREADS = 512, MS_KPT = 24;      // up to 12288 candidates per query
+constexpr int MS_THREADS = 1024, MS_KPT = 12;     // up to 12288 candidates per query
 __device__ __forceinline__ uint32_t f2ord(float f) {
     const uint32_t u = __float_as_uint(f);
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
@@ -418,7 +418,9 @@ topk_merge_select_kernel(const float *__restrict__ in_s, const uint32_t *__restr
     const int k_eff = min(k, nvalid_sm);
     if (tid == 0) krem_sm = k_eff;
     // radix select of the k_eff-th largest key, most significant byte first
-    for (int pass = 7; pass >= 0 && k_eff > 0; --pass) {
+#pragma unroll
+    for (int pass = 7; pass >= 0; --pass) {             // unrolled: the 64-bit shifts become register selects
+        if (k_eff == 0) break;
         if (tid < 256) hist[tid] = 0u;
         __syncthreads();
         const unsigned long long prefix = prefix_sm;
