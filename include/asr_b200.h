@@ -13,7 +13,8 @@
  *     cudaStream_t passed as void* (NULL = legacy default stream).  No call
  *     synchronises the host unless its name ends in `_host`.
  *   - opaque handles own only what they allocate at create time (weights,
- *     activation arena, per-CTA scratch); nothing is allocated on the hot path.
+ *     activation arena, per-CTA scratch) or on first use (the DB's normalised
+ *     copy, host-entry staging buffers); nothing is allocated in steady state.
  *   - sm_100a only.  There is no CPU fallback: without a CUDA device every compute
  *     entry point fails with ASR_ERR_CUDA.
  */
@@ -121,7 +122,9 @@ double asr_encoder_flops_per_sample(const asr_encoder_t *enc);
  * ------------------------------------------------------------------------- */
 typedef struct asr_db asr_db_t;
 
-/* codes_dev: (n, 32) float32 row-major, 128-byte aligned, caller-owned and kept alive.
+/* codes_dev: (n, 32) float32 row-major, 128-byte aligned, caller-owned, kept alive and NOT modified while the
+ * handle exists: the first cosine query makes a device copy of the rows normalised with the pinned definition
+ * (n * 128 bytes, owned by the handle) and every later query streams that copy.
  * idx_base: global index of row 0 (this shard's offset in a sharded DB). */
 int asr_db_create(asr_db_t **out, const float *codes_dev, int64_t n, int64_t idx_base);
 int asr_db_destroy(asr_db_t *db);
