@@ -8,10 +8,12 @@
 //   audio_sheet_retrieval/retrieval_wrapper.py:33-38,47-77 ; audio_sheet_retrieval/refine_cca.py:86-89
 //
 // Product path (ASR_PATH_TCGEN05)
-//   layer 0 (Cin = 1, K = 9: not a tensor-core problem) runs on CUDA cores fused with `prepare`
-//   and writes bf16 activations in the "P8" layout below; layers 1..7 are implicit GEMMs on
-//   tcgen05 with fp32 accumulators in TMEM; BatchNorm is folded into the bf16 weights + an fp32
-//   bias, ELU and the 2x2 max-pool run in the epilogue; the head stays in fp32.
+//   layer 0 (Cin = 1) is a banded-Toeplitz GEMM on tcgen05 fused with `prepare` (l0_tc_kernel; the
+//   CUDA-core l0_conv_kernel remains for other channel counts) and writes bf16 activations in the
+//   "P8" layout below; layers 1..7 are implicit GEMMs on tcgen05 with fp32 accumulators in TMEM --
+//   conv3x3_rows_kernel (four output rows stacked along N, pooling in registers) for the wide pooled
+//   layers, conv3x3_tc_kernel (raster tiles) for the rest; BatchNorm is folded into the bf16 weights
+//   + an fp32 bias, ELU and the 2x2 max-pool run in the epilogue; the head stays in fp32.
 //
 // P8 activation layout (bf16):  [sample][channel chunk of 8][(H+2) x (W+2) padded positions][8]
 //   - one padded position of one chunk = 16 bytes = one row of a UMMA "core matrix"; a run of
