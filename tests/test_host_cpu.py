@@ -35,6 +35,10 @@ def test_library_is_sm100a_with_tcgen05_and_tma():
     assert "UTCHMMA" in sass, "no tcgen05.mma in SASS"
     assert "LDTM" in sass, "no tcgen05.ld in SASS"
     assert "UBLKCP" in sass and "UTMALDG" in sass, "no TMA bulk / tensor loads in SASS"
+    # every hot kernel of the path is in the binary
+    for kernel in ("l0_tc_kernel", "conv3x3_rows_kernel", "conv3x3_tc_kernel", "head_kernel", "topk_stream_kernel",
+                   "topk_tc_kernel", "topk_merge_select_kernel", "cca_solve_kernel", "contrastive_rows_kernel"):
+        assert kernel in sass, kernel
 
 
 @pytest.mark.skipif(not NO_GPU, reason="checks the no-GPU failure mode")
@@ -54,6 +58,12 @@ def test_compute_calls_fail_loudly_without_gpu(shipped_params):
     h = ctypes.c_void_p()
     assert _lib.lib.asr_db_create(ctypes.byref(h), None, 4, 0) != 0
     assert b"no CUDA device" in _lib.lib.asr_last_error()
+    # training objective: CPU tensors are refused by the mirror, the C entry itself fails without a device
+    import torch
+    from audio_sheet_retrieval_b200.models.objectives import get_contrastive_cos_loss
+    with pytest.raises(_lib.AsrError, match="no CPU path"):
+        get_contrastive_cos_loss(1.0, 0.7)(torch.zeros(4, 32), torch.zeros(4, 32))
+    assert _lib.lib.asr_contrastive_loss(None, None, 4, 1.0, 0.7, 0, None, None, None, None, None) != 0
 
 
 def test_product_never_imports_oracle():
