@@ -1203,8 +1203,10 @@ int asr_topk(asr_db_t *db, const float *q_dev, int64_t nq, int k, int normalise,
     ASR_CHECK_ARG(q_dev && out_score_dev && out_idx_dev, "NULL buffer");
     cudaStream_t st = (cudaStream_t)stream;
     const char *force = getenv("ASR_TOPK_PATH");       // "exact" | "tc" (tests exercise both)
-    // measured crossover (1e7 rows, k = 25): the exact QT=16 kernel wins up to ~24 queries
-    const bool want_tc = force ? (strcmp(force, "tc") == 0) : (nq > 24);
+    // measured crossovers (k = 25): the exact QT=16 kernel wins up to ~24 queries, and for small problems
+    // whatever the query count: exact ~ 0.05 ms + 7.3 ms per 1e9 scores, pre-filter ~ 1.15 ms + 0.55 ms per 1e9
+    // (profiles/r1_configs_3_5.json: its work items are at least 128 tiles long) -> equal at 1.6e8 scores
+    const bool want_tc = force ? (strcmp(force, "tc") == 0) : (nq > 24 && (double)nq * (double)db->n >= 1.6e8);
     if (want_tc && normalise && k <= TC_KMAX) return topk_tc(db, q_dev, nq, k, out_score_dev, out_idx_dev, st);
     // cosine queries stream the pinned-normalised copy (kernel flag bit 0: normalise queries, bit 1: normalise rows)
     if (normalise) {
