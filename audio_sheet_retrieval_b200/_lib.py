@@ -6,10 +6,12 @@ raises, and every compute entry point fails without a CUDA device.
 """
 import ctypes
 import os
+import subprocess
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
 
 from . import build as _build
 
+ABI_VERSION = 2
 N_LAYERS = 9
 DIM = 32
 MAX_K = 128
@@ -38,12 +40,20 @@ class EncoderDesc(ctypes.Structure):
 
 
 def _load():
-    so = _build.SO
-    if not os.path.exists(so) or os.environ.get("ASR_REBUILD"):
+    # build() rebuilds only when a source or the header is newer than the .so (mtime check), so a stale
+    # library is never loaded with newer argtypes; without nvcc (a deployment box) the shipped .so is used.
+    try:
         so = _build.build(force=bool(os.environ.get("ASR_REBUILD")))
+    except (OSError, RuntimeError, subprocess.CalledProcessError):
+        if not os.path.exists(_build.SO):
+            raise
+        so = _build.SO
     lib = ctypes.CDLL(so)
     lib.asr_last_error.restype = c_char_p
     lib.asr_abi_version.restype = c_int
+    if lib.asr_abi_version() != ABI_VERSION:
+        raise AsrError("libasr_b200.so has ABI version %d, this binding expects %d: rebuild with "
+                       "`python -m audio_sheet_retrieval_b200.build --force`" % (lib.asr_abi_version(), ABI_VERSION))
     lib.asr_launch_count.restype = c_int64
     lib.asr_encoder_create.argtypes = [POINTER(c_void_p), POINTER(EncoderDesc), c_int]
     lib.asr_encoder_destroy.argtypes = [c_void_p]
@@ -62,6 +72,10 @@ def _load():
     lib.asr_encoder_set_timing.argtypes = [c_void_p, c_int]
     lib.asr_encoder_get_timing.argtypes = [c_void_p, POINTER(c_double), POINTER(c_double), POINTER(c_double),
                                            POINTER(c_int64)]
+    lib.asr_encoder_set_fusion.argtypes = [c_void_p, c_int]
+    lib.asr_encoder_set_fusion.restype = c_int
+    lib.asr_encoder_get_fusion.argtypes = [c_void_p]
+    lib.asr_encoder_get_fusion.restype = c_int
     lib.asr_encoder_flops_per_sample.argtypes = [c_void_p]
     lib.asr_encoder_flops_per_sample.restype = c_double
     lib.asr_db_create.argtypes = [POINTER(c_void_p), c_void_p, c_int64, c_int64]

@@ -46,7 +46,7 @@ int sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
 extern "C" {
 
 const char *asr_last_error(void) { return asr::g_err.c_str(); }
-int asr_abi_version(void) { return 1; }
+int asr_abi_version(void) { return 2; }
 int64_t asr_launch_count(void) { return asr::g_launches; }
 
 }

@@ -222,6 +222,33 @@ __device__ __forceinline__ void tmem_ld8x4(uint32_t taddr, uint32_t stride, floa
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 12 consecutive columns (8 + 4) in one round trip: the 12 channels of one layer-0 output row
+__device__ __forceinline__ void tmem_ld12(uint32_t taddr, float *v) {
+    uint32_t r[12];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11])
+                 : "r"(taddr + 8u)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 12; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory progress counters (producer: red.release after its stores; consumer: ld.acquire poll)
+__device__ __forceinline__ uint32_t ld_acquire_shared(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_shared_add(uint32_t *p, uint32_t v) {
+    asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // 32 lanes x 64 consecutive fp32 columns -> 64 registers per thread (one round trip instead of four)
 __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float *v) {
     uint32_t r[64];

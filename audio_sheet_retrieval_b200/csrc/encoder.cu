@@ -1122,6 +1122,8 @@ __global__ void __launch_bounds__(L0T_THREADS, 1) l0_tc_kernel(const L0TcParams 
     if (warp == L0T_PROD_WARPS) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * L0T_SLOT_COLS); }
 }
 
+#include "encoder_fused.cuh"
+
 // --------------------------------------------------------------------------------------
 // head: spatial mean -> 1x1 conv + BN (folded) -> latent -> (latent - mean) . P -> unit norm
 // --------------------------------------------------------------------------------------
@@ -1286,6 +1288,12 @@ struct asr_encoder {
     uint8_t *l0_blob_u8 = nullptr;  // same with w/255 in the pixel rows (u8 input, prepare = x/255: A = integer pixels)
     int l0_R0 = 0, l0_NPAD = 0;
     unsigned l0_wp_magic = 0;
+    // layers 0 + 1 fused (l01_fused_kernel): Toeplitz blobs with 8 output rows per tile, launch constants
+    uint8_t *f01_blob = nullptr, *f01_blob_u8 = nullptr;
+    bool f01_ok = false;
+    int fuse_mask = 0;              // bit 0: layers 0 + 1 run fused (asr_encoder_set_fusion)
+    F01Params f01;                  // geometry / shared-memory layout, filled at create
+    int f01_smem = 0, f01_smem_int = 0;
     bf16 *wblob[8] = {nullptr};     // layers 1..7
     ConvPlan plan[8];
     bf16 *act[8] = {nullptr};       // P8 activations (output of layer l)
@@ -1451,7 +1459,7 @@ extern "C" {
 
 int asr_encoder_destroy(asr_encoder_t *e) {
     if (!e) return ASR_OK;
-    cudaFree(e->l0_w); cudaFree(e->l0_blob); cudaFree(e->l0_blob_u8);
+    cudaFree(e->l0_w); cudaFree(e->l0_blob); cudaFree(e->l0_blob_u8); cudaFree(e->f01_blob); cudaFree(e->f01_blob_u8);
     for (int l = 0; l < 8; ++l) {
         cudaFree(e->wblob[l]); cudaFree(e->act[l]); cudaFree(e->ref_w[l]); cudaFree(e->ref_bn[l]); cudaFree(e->ref_act[l]);
     }
@@ -1564,28 +1572,41 @@ int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *d, int max_b
                 // banded weight matrices of l0_tc_kernel: B_dx[k][(r, co)] = w[co][dy = k - r][dx], split hi + lo
                 const int C = g.cout, R0 = C == 12 ? 12 : 8, NPAD = R0 * C;
                 const size_t bbytes = (size_t)3 * 2 * 2 * NPAD * 16;
-                auto make_blob = [&](double pixel_scale) {
-                    std::vector<uint8_t> blob(bbytes + C * 4, 0);
+                auto make_blob = [&](int R0b, double pixel_scale) {
+                    const int NPADb = R0b * C;
+                    const size_t bb_bytes = (size_t)3 * 2 * 2 * NPADb * 16;
+                    std::vector<uint8_t> blob(bb_bytes + C * 4, 0);
                     bf16 *wb = reinterpret_cast<bf16 *>(blob.data());
                     auto put = [&](int dx, int k, int nn, float w) {
                         const bf16 hi = __float2bfloat16_rn(w);
                         const bf16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
-                        wb[((((size_t)dx * 2 + 0) * 2 + k / 8) * NPAD + nn) * 8 + (k & 7)] = hi;
-                        wb[((((size_t)dx * 2 + 1) * 2 + k / 8) * NPAD + nn) * 8 + (k & 7)] = lo;
+                        wb[((((size_t)dx * 2 + 0) * 2 + k / 8) * NPADb + nn) * 8 + (k & 7)] = hi;
+                        wb[((((size_t)dx * 2 + 1) * 2 + k / 8) * NPADb + nn) * 8 + (k & 7)] = lo;
                     };
                     for (int dx = 0; dx < 3; ++dx)
-                        for (int r = 0; r < R0; ++r)
+                        for (int r = 0; r < R0b; ++r)
                             for (int dy = 0; dy < 3; ++dy)
                                 for (int co = 0; co < C; ++co)
                                     put(dx, r + dy, r * C + co, (float)((double)w0[(size_t)co * 9 + dy * 3 + dx] * pixel_scale));
-                    for (int r = 0; r < R0; ++r)            // K row 15 of dx = 0: the bias (the A tile holds 1 there)
+                    for (int r = 0; r < R0b; ++r)           // K row 15 of dx = 0: the bias (the A tile holds 1 there)
                         for (int co = 0; co < C; ++co) put(0, 15, r * C + co, w0[(size_t)C * 9 + co]);
-                    float *bb = reinterpret_cast<float *>(blob.data() + bbytes);
+                    float *bb = reinterpret_cast<float *>(blob.data() + bb_bytes);
                     for (int co = 0; co < C; ++co) bb[co] = w0[(size_t)C * 9 + co];
                     return blob;
                 };
-                const std::vector<uint8_t> blob = make_blob(1.0);
-                const std::vector<uint8_t> blob_u8 = make_blob(1.0 / 255.0);
+                const std::vector<uint8_t> blob = make_blob(R0, 1.0);
+                const std::vector<uint8_t> blob_u8 = make_blob(R0, 1.0 / 255.0);
+                (void)bbytes;
+                if (C == F_C0 && d->prepare != ASR_PREP_SCALE_HALF) {     // blobs of the fused layer-0 + layer-1 kernel (8 rows per tile)
+                    const std::vector<uint8_t> fb = make_blob(F_R0, 1.0);
+                    E_CUDA(cudaMalloc(&e->f01_blob, fb.size()));
+                    E_CUDA(cudaMemcpy(e->f01_blob, fb.data(), fb.size(), cudaMemcpyHostToDevice));
+                    if (d->prepare == ASR_PREP_SCALE) {
+                        const std::vector<uint8_t> fb8 = make_blob(F_R0, 1.0 / 255.0);
+                        E_CUDA(cudaMalloc(&e->f01_blob_u8, fb8.size()));
+                        E_CUDA(cudaMemcpy(e->f01_blob_u8, fb8.data(), fb8.size(), cudaMemcpyHostToDevice));
+                    }
+                }
                 const unsigned Wp = (unsigned)g.W + 2;
                 const unsigned magic = (unsigned)((0x100000000ull + Wp - 1) / Wp);
                 bool exact = true;
@@ -1647,8 +1668,48 @@ int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *d, int max_b
         }
         e->act_plane[l] = (long long)(g.Ho + 2) * (g.Wo + 2) * 16;
         e->act_sample[l] = e->act_plane[l] * (g.coutp / 8);
-        E_CUDA(cudaMalloc(&e->act[l], (size_t)e->act_sample[l] * B));
-        E_CUDA(cudaMemset(e->act[l], 0, (size_t)e->act_sample[l] * B));
+        if (l > 0) {      // layer 0's buffer: ensure_act0 (first unfused call; never when layers 0 + 1 run fused)
+            E_CUDA(cudaMalloc(&e->act[l], (size_t)e->act_sample[l] * B));
+            E_CUDA(cudaMemset(e->act[l], 0, (size_t)e->act_sample[l] * B));
+        }
+    }
+    {   // layers 0 + 1 fused: eligibility, geometry and shared-memory layout of l01_fused_kernel
+        const LayerGeom &g0 = e->g[0], &g1 = e->g[1];
+        const ConvPlan &p1 = e->plan[1];
+        F01Params &f = e->f01;
+        memset(&f, 0, sizeof(f));
+        const int Wp = g0.W + 2;
+        bool ok = e->f01_blob && e->l0_blob && g0.cout == F_C0 && g0.W >= 126 && g0.H % F_R0 == 0 && g1.pool &&
+                  g1.cinp == 16 && g1.coutp == F_NP1 && p1.rows && p1.SPT == 1 && p1.Hc == g0.H && g0.H % RS_R == 0;
+        if (ok) {
+            f.H = g0.H; f.W = g0.W; f.Wp = Wp;
+            f.NB = g0.H / F_R0; f.NG = g0.H / RS_R; f.T0 = (f.NB * Wp + 127) / 128; f.JT = p1.JT;
+            f.wp_magic = (unsigned)((0x100000000ull + (unsigned)Wp - 1) / (unsigned)Wp);
+            for (unsigned gg = 0; gg < (unsigned)f.T0 * 128u + 256u && ok; ++gg)
+                ok = (unsigned)(((unsigned long long)gg * f.wp_magic) >> 32) == gg / (unsigned)Wp;
+            f.ring_plane = (F_ZROW + 1) * Wp * 16;
+            f.Ho = g1.Ho; f.Wo = g1.Wo; f.Wpo = g1.Wo + 2; f.cout1 = g1.cout;
+            f.out_plane = e->act_plane[1]; f.out_sample = e->act_sample[1];
+            auto layout = [&](int abuf) {
+                int off = 3 * 2 * 2 * F_NPAD0 * 16;
+                f.off_w1 = off; off += F_W1BYTES + F_NP1 * 4; off = (off + 127) / 128 * 128;
+                f.off_a = off; off += F_CW * abuf; off = (off + 127) / 128 * 128;
+                f.off_ring = off; off += 2 * f.ring_plane + F_TAIL; off = (off + 127) / 128 * 128;
+                f.off_lut = off; off += 256 * 4;
+                f.off_bar = off; off += 256;
+                return off;
+            };
+            e->f01_smem_int = layout(2 * F_AROWS * 16);          // integer pixels: hi part only
+            e->f01_smem = layout(2 * 2 * F_AROWS * 16);          // hi + lo A parts (fp32 pixels); f keeps these offsets
+            // a view of the last tile of a row may read up to 128 JT + 2 positions of a ring row
+            ok = ok && e->f01_smem <= SMEM_LIMIT && (128 * f.JT + 2 - Wp) * 16 <= F_TAIL;
+        }
+        e->f01_ok = ok;
+        static const int fuse_env = getenv("ASR_FUSE01") ? atoi(getenv("ASR_FUSE01")) : 1;
+        e->fuse_mask = (ok && fuse_env) ? 1 : 0;
+        if (getenv("ASR_DEBUG_PLAN"))
+            fprintf(stderr, "[asr] layers 0+1 fused: %s (NB %d NG %d T0 %d JT %d smem %d / %d B)\n", ok ? "available" : "no", f.NB,
+                    f.NG, f.T0, f.JT, e->f01_smem, e->f01_smem_int);
     }
     {   // head: A[j][c] = W8[j][c] * scale8[j]; b[j] = beta8 - mean8*scale8
         const int C = e->head_c;
@@ -1670,6 +1731,8 @@ int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *d, int max_b
         E_CUDA(cudaFuncSetAttribute(l0_tc_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         E_CUDA(cudaFuncSetAttribute(l0_tc_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         E_CUDA(cudaFuncSetAttribute(conv3x3_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        E_CUDA(cudaFuncSetAttribute(l01_fused_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        E_CUDA(cudaFuncSetAttribute(l01_fused_kernel<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         E_CUDA(cudaFuncSetAttribute(conv3x3_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         E_CUDA(cudaFuncSetAttribute(conv3x3_rows_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         E_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
@@ -1686,6 +1749,13 @@ int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *d, int max_b
 }
 
 double asr_encoder_flops_per_sample(const asr_encoder_t *e) { return e ? e->flops : 0.0; }
+
+static int ensure_act0(asr_encoder *e) {
+    if (e->act[0]) return ASR_OK;
+    ASR_CUDA(cudaMalloc(&e->act[0], (size_t)e->act_sample[0] * e->max_batch));
+    ASR_CUDA(cudaMemset(e->act[0], 0, (size_t)e->act_sample[0] * e->max_batch));
+    return ASR_OK;
+}
 
 static int ensure_ref_buffers(asr_encoder *e) {
     if (e->ref_in) return ASR_OK;
@@ -1794,9 +1864,38 @@ int asr_encoder_embed(asr_encoder_t *e, const void *x_dev, int x_dtype, int64_t 
             ASR_LAUNCH_CHECK();
             return ASR_OK;
         };
+        auto launch_fused01 = [&]() -> int {
+            F01Params f = e->f01;
+            f.x = x_dev; f.x_u8 = x_dtype == ASR_IN_U8; f.prepare = d.prepare; f.n = (int)n;
+            f.int_pixels = (f.x_u8 && d.prepare == ASR_PREP_SCALE && e->f01_blob_u8) ? 1 : 0;
+            f.blob0 = f.int_pixels ? e->f01_blob_u8 : e->f01_blob;
+            f.wblob1 = reinterpret_cast<const uint8_t *>(e->wblob[1]);
+            f.out = e->act[1];
+            f.abuf = (f.int_pixels ? 2 : 4) * F_AROWS * 16;
+            int smem = e->f01_smem;
+            if (f.int_pixels) {       // same order of regions, smaller A buffers
+                const int delta = F_CW * 2 * F_AROWS * 16;
+                f.off_ring -= delta; f.off_lut -= delta; f.off_bar -= delta;
+                smem = e->f01_smem_int;
+            }
+            const int grid = (int)std::min<int64_t>(n, sm_count());
+            static const int variant = getenv("ASR_F01_VARIANT") ? atoi(getenv("ASR_F01_VARIANT")) : 0;
+            if (variant == 1) l01_fused_kernel<3, 3><<<grid, 32 * (F_DRAIN_WARP0 + 4 * 6), smem, st>>>(f);
+            else l01_fused_kernel<2, 3><<<grid, 32 * (F_DRAIN_WARP0 + 4 * 5), smem, st>>>(f);
+            ASR_LAUNCH_CHECK();
+            return ASR_OK;
+        };
+        const bool fused01 = (e->fuse_mask & 1) != 0;
+        if (fused01) {
+            mark(e, st, 1, true);
+            if ((rc = launch_fused01())) return rc;
+            mark(e, st, 1, false);
+        } else if ((rc = ensure_act0(e))) {
+            return rc;
+        }
         // Layers 0 and 1 can run over sub-chunks that reuse one region of the layer-0 buffer (see create).
         const int64_t sub = e->l01_chunk > 0 ? e->l01_chunk : n;
-        for (int64_t n0 = 0; n0 < n; n0 += sub) {
+        for (int64_t n0 = 0; n0 < n && !fused01; n0 += sub) {
             const int64_t nn = std::min<int64_t>(sub, n - n0);
             mark(e, st, 0, true);
             if ((rc = launch_l0(n0, nn, e->act[0]))) return rc;
@@ -1851,6 +1950,14 @@ int asr_encoder_set_timing(asr_encoder_t *e, int enable) {
     return ASR_OK;
 }
 
+int asr_encoder_set_fusion(asr_encoder_t *e, int mask) {
+    ASR_CHECK_ARG(e != nullptr, "NULL handle");
+    e->fuse_mask = (mask & 1) && e->f01_ok ? 1 : 0;
+    return ASR_OK;
+}
+
+int asr_encoder_get_fusion(const asr_encoder_t *e) { return e ? e->fuse_mask : 0; }
+
 int asr_encoder_get_timing(asr_encoder_t *e, double *ms_layer0, double *ms_conv_tc, double *ms_head, int64_t *n_calls) {
     ASR_CHECK_ARG(e != nullptr, "NULL handle");
     double a = 0, b = 0, c = 0;
@@ -1874,6 +1981,8 @@ int asr_encoder_debug_activation(asr_encoder_t *e, int layer, int path, int64_t 
     ASR_CHECK_ARG(e && layer >= 0 && layer < 8 && n >= 1 && n <= e->max_batch, "bad argument");
     ASR_CHECK_ARG(!(layer == 0 && path == ASR_PATH_TCGEN05 && e->l01_chunk > 0 && n > e->l01_chunk),
                   "layer-0 activations are only kept for the last sub-chunk");
+    ASR_CHECK_ARG(!(layer == 0 && path == ASR_PATH_TCGEN05 && out_host && (e->fuse_mask & 1)),
+                  "layer-0 activations never reach memory while layers 0 + 1 run fused (asr_encoder_set_fusion(enc, 0))");
     const LayerGeom &g = e->g[layer];
     if (c) *c = g.cout;
     if (h) *h = g.Ho;

@@ -1,0 +1,378 @@
+// Layer 0 + layer 1 of the sheet branch in ONE persistent kernel (included by encoder.cu, namespace asr).
+//
+// Replaces, for the full-resolution model (audio_sheet_retrieval/models/mutopia_ccal_cont.py:75-79):
+//   prepare (x / 255) -> conv3x3 1->12 + BN + ELU -> conv3x3 12->12 + BN + ELU -> 2x2 max-pool
+// The unfused path writes the 160x200x16 bf16 output of layer 0 to HBM (1 MB per sample) and reads it
+// back in layer 1; here it never leaves the SM:
+//   converters   global pixels -> K-major A tiles of the banded-Toeplitz GEMM (as l0_tc_kernel)
+//   MMA 0        tcgen05: 8 output rows x 12 channels (N = 96) per 128 raster positions -> TMEM
+//   drain        TMEM -> ELU -> bf16 -> a RING of layer-0 output rows in shared memory, P8 layout
+//                (3 blocks of 8 rows + one all-zero row that stands for the rows outside the image)
+//   MMA 1        tcgen05, row-stacked as conv3x3_rows_kernel: its A views are descriptors into the ring
+//   epilogue     TMEM -> 2x2 max in registers -> bias + ELU -> bf16 -> global (pooled P8 activations)
+// The layer-0 GEMM rasterises over (row block, padded column) of a sample, so every A row is a real
+// position (no 128-column tile padding); a tile may straddle two row blocks.
+// Flow control: ring block "written" = a shared-memory counter of finished (position, row) units
+// (release-add by the drain warps, acquire-poll by the MMA-1 warps; a tile straddles blocks, so
+// arrival counts per block are not fixed and an mbarrier does not fit); ring block "free" = an mbarrier
+// that the two MMA-1 warps commit to after the last row group of their parity that reads the block.
+#pragma once
+
+constexpr int F_R0 = 8;                       // layer-0 output rows per tile = rows per ring block
+constexpr int F_RB = 3;                       // ring blocks
+constexpr int F_ZROW = F_R0 * F_RB;           // index of the all-zero ring row
+constexpr int F_CW = 4;                       // converter warps = A buffers
+constexpr int F_AROWS = 136;                  // 130 raster positions of a tile + slack
+constexpr int F_C0 = 12;                      // layer-0 channels
+constexpr int F_NPAD0 = F_R0 * F_C0;          // 96
+constexpr int F_SLOT0 = 128, F_SLOT1 = 64;    // TMEM columns per accumulator slot (layer 0: 2 slots, layer 1: 4)
+constexpr int F_NP1 = 16;                     // padded layer-1 channels
+constexpr int F_W1BYTES = 3 * 2 * RS_R * F_NP1 * 16;
+constexpr int F_TAIL = 2176;
+constexpr int F_MMA0_WARP = F_CW, F_MMA1_WARP0 = F_CW + 1, F_DRAIN_WARP0 = 8;
+
+struct F01Params {
+    const void *x;              // (n, 1, H, W) u8 or f32
+    int x_u8, prepare, int_pixels;
+    int H, W, Wp, n;
+    const uint8_t *blob0;       // [dx][part hi, lo][K chunk][96][8] bf16
+    const uint8_t *wblob1;      // rows-kernel blob of layer 1: [dx][K chunk][4 blocks][16][8] bf16, then 16 fp32 biases
+    bf16 *out;
+    long long out_plane, out_sample;
+    int Ho, Wo, Wpo, cout1;
+    int NB, NG, T0, JT;         // ring blocks / layer-1 row groups / layer-0 tiles per sample, 128-pixel tiles per row
+    unsigned wp_magic;          // ceil(2^32 / Wp), exact for every g < T0 * 128 + 128
+    int ring_plane;             // (F_ZROW + 1) * Wp * 16 bytes per 8-channel chunk
+    int abuf;                   // bytes per A buffer
+    int off_w1, off_a, off_ring, off_lut, off_bar;
+};
+
+// One converter warp builds whole A tiles: 260 items (K chunk c, tile row i) = 9 per lane in batches of three.
+// A row i <-> raster position g = 128 t - 1 + i = rbl * Wp + xp; K element kk <-> image row 8 rbl - 1 + kk
+// (kk = 0..9 are used by the 8 output rows of the block, kk = 15 carries the constant 1 of the bias row).
+template <bool INT_PIXELS>
+__device__ __forceinline__ void f01_convert_tile(const F01Params &p, uint8_t *a_buf, const float *lut, long long sample_off, int t) {
+    const int lane = threadIdx.x & 31;
+    const uint8_t *xu = reinterpret_cast<const uint8_t *>(p.x) + sample_off;
+    const float *xf = reinterpret_cast<const float *>(p.x) + sample_off;
+    const int g0 = 128 * t - 1;
+#pragma unroll 1
+    for (int batch = 0; batch < 3; ++batch) {
+        uint32_t raw[3][8];
+        bool ok[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int item = lane + 32 * (3 * batch + u);
+            const int c = item >= 130 ? 1 : 0, i = item - 130 * c;
+            const int g = g0 + i;
+            const unsigned gc = (unsigned)max(g, 0);
+            const unsigned rbl = __umulhi(gc, p.wp_magic);
+            const int x = (int)(gc - rbl * (unsigned)p.Wp) - 1;
+            ok[u] = item < 260 && g >= 0 && (int)rbl < p.NB && x >= 0 && x < p.W;
+            const int yb = (int)rbl * F_R0 - 1 + 8 * c;
+            const unsigned base = (unsigned)min(max(x, 0), p.W - 1);
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                const int y = yb + kk;
+                const bool in = ok[u] && y >= 0 && y < p.H && (c == 0 || kk < 2);
+                const unsigned o = base + (unsigned)(min(max(y, 0), p.H - 1) * p.W);
+                raw[u][kk] = 0u;
+                if (in) raw[u][kk] = p.x_u8 ? (uint32_t)xu[o] : __float_as_uint(xf[o]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int item = lane + 32 * (3 * batch + u);
+            const int c = item >= 130 ? 1 : 0, i = item - 130 * c;
+            float v[8];
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                if (INT_PIXELS) {
+                    v[kk] = (float)raw[u][kk];            // exact in bf16; 1/255 lives in the weight matrix
+                } else {
+                    float f = p.x_u8 ? (float)raw[u][kk] : __uint_as_float(raw[u][kk]);
+                    if (p.prepare == ASR_PREP_SCALE) f = p.x_u8 ? lut[(int)raw[u][kk]] : f / 255.0f;
+                    v[kk] = f;                             // raw = 0 where the position is outside the image
+                }
+            }
+            if (c == 1) v[7] = 1.0f;
+            if (item < 260) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * kk], v[2 * kk + 1]);
+                    hi[kk] = *reinterpret_cast<const uint32_t *>(&h);
+                    if (!INT_PIXELS) {
+                        const float2 hf = __bfloat1622float2(h);
+                        const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * kk] - hf.x, v[2 * kk + 1] - hf.y);
+                        lo[kk] = *reinterpret_cast<const uint32_t *>(&l);
+                    }
+                }
+                *reinterpret_cast<uint4 *>(a_buf + (c * F_AROWS + i) * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                if (!INT_PIXELS)
+                    *reinterpret_cast<uint4 *>(a_buf + ((2 + c) * F_AROWS + i) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void f01_wait_count(const uint32_t *cnt, uint32_t target) {
+    if (ld_acquire_shared(cnt) >= target) return;
+    const uint64_t t0 = globaltimer_ns();
+    while (ld_acquire_shared(cnt) < target) {
+        if (globaltimer_ns() - t0 > 4000000000ull) {
+            printf("asr: ring counter timeout block %d thread %d target %u have %u\n", blockIdx.x, threadIdx.x, target,
+                   ld_acquire_shared(cnt));
+            __trap();
+        }
+    }
+}
+
+template <int DG, int EG>   // drain groups (layer 0) and epilogue groups (layer 1), four warps each
+__global__ void __launch_bounds__(32 * (F_DRAIN_WARP0 + 4 * (DG + EG)), 1) l01_fused_kernel(const F01Params p) {
+    constexpr int NTHREADS = 32 * (F_DRAIN_WARP0 + 4 * (DG + EG));
+    constexpr int EPI_WARP0_F = F_DRAIN_WARP0 + 4 * DG;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t *b0_sm = smem;
+    uint8_t *w1_sm = smem + p.off_w1;
+    float *bias1_sm = reinterpret_cast<float *>(w1_sm + F_W1BYTES);
+    uint8_t *a_sm = smem + p.off_a;
+    uint8_t *ring = smem + p.off_ring;
+    float *lut_sm = reinterpret_cast<float *>(smem + p.off_lut);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + p.off_bar);
+    uint64_t *a_ready = bars;             // [F_CW]  converters -> MMA 0
+    uint64_t *a_free = bars + 4;          // [F_CW]  MMA 0 done reading the A buffer
+    uint64_t *acc0_full = bars + 8;       // [2]
+    uint64_t *acc0_empty = bars + 10;     // [2]
+    uint64_t *mid_free = bars + 12;       // [F_RB]  MMA 1 done reading the ring block
+    uint64_t *acc1_full = bars + 15;      // [4]
+    uint64_t *acc1_empty = bars + 19;     // [4]
+    uint32_t *mid_cnt = reinterpret_cast<uint32_t *>(bars + 23);   // [F_RB] finished (position, row) units, monotonic
+    uint32_t *tmem_ptr = mid_cnt + 4;
+
+    constexpr int B0BYTES = 3 * 2 * 2 * F_NPAD0 * 16;
+    for (int i = tid; i < B0BYTES / 16; i += NTHREADS)
+        reinterpret_cast<uint4 *>(b0_sm)[i] = reinterpret_cast<const uint4 *>(p.blob0)[i];
+    for (int i = tid; i < (F_W1BYTES + F_NP1 * 4) / 16; i += NTHREADS)
+        reinterpret_cast<uint4 *>(w1_sm)[i] = reinterpret_cast<const uint4 *>(p.wblob1)[i];
+    for (int i = tid; i < (2 * p.ring_plane + F_TAIL) / 16; i += NTHREADS)      // zero row, tail slack (and a defined start)
+        reinterpret_cast<uint4 *>(ring)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid < 256) lut_sm[tid] = (float)tid / 255.0f;
+    if (tid == 0) {
+        for (int s = 0; s < F_CW; ++s) { mbar_init(&a_ready[s], 1); mbar_init(&a_free[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc0_full[s], 1); mbar_init(&acc0_empty[s], 4 * DG); }
+        for (int s = 0; s < F_RB; ++s) { mbar_init(&mid_free[s], 2); mid_cnt[s] = 0u; }
+        for (int s = 0; s < 4; ++s) { mbar_init(&acc1_full[s], 1); mbar_init(&acc1_empty[s], 4); }
+        mbar_fence_init();
+    }
+    if (warp == F_MMA0_WARP) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const int n_it = (int)blockIdx.x < p.n ? (p.n - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int total0 = n_it * p.T0;                       // layer-0 tiles of this CTA
+    const uint32_t block_units = (uint32_t)(p.Wp * F_R0);
+
+    if (warp < F_CW) {
+        // ================= converters =================
+        uint8_t *a_buf = a_sm + warp * p.abuf;
+        for (int k = warp; k < total0; k += F_CW) {
+            const int it = k / p.T0, t = k - it * p.T0;
+            const long long n = (long long)blockIdx.x + (long long)it * gridDim.x;
+            mbar_wait(&a_free[warp], (uint32_t)((((k / F_CW) & 1)) ^ 1));
+            if (p.int_pixels) f01_convert_tile<true>(p, a_buf, lut_sm, n * p.H * p.W, t);
+            else f01_convert_tile<false>(p, a_buf, lut_sm, n * p.H * p.W, t);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_ready[warp]);
+        }
+    } else if (warp == F_MMA0_WARP) {
+        // ================= MMA 0: per dx (A_hi, B_hi) [, (A_lo, B_hi)], (A_hi, B_lo) =================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(F_NPAD0);
+            const uint32_t b0 = smem_u32(b0_sm), b_part = 2 * F_NPAD0 * 16;
+            for (int k = 0; k < total0; ++k) {
+                const int buf = k & (F_CW - 1), slot = k & 1;
+                mbar_wait(&a_ready[buf], (uint32_t)((k / F_CW) & 1));
+                mbar_wait(&acc0_empty[slot], (uint32_t)(((k >> 1) & 1) ^ 1));
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(a_sm + buf * p.abuf);
+                const uint32_t d = tmem_base + (uint32_t)slot * F_SLOT0;
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const uint64_t ah = umma_desc(a0 + dx * 16, F_AROWS * 16, 128);
+                    const uint64_t al = umma_desc(a0 + 2 * F_AROWS * 16 + dx * 16, F_AROWS * 16, 128);
+                    const uint64_t bh = umma_desc(b0 + (dx * 2) * b_part, F_NPAD0 * 16, 128);
+                    const uint64_t bl = umma_desc(b0 + (dx * 2 + 1) * b_part, F_NPAD0 * 16, 128);
+                    tc_mma_bf16(d, ah, bh, idesc, dx > 0 ? 1u : 0u);
+                    if (!p.int_pixels) tc_mma_bf16(d, al, bh, idesc, 1u);
+                    tc_mma_bf16(d, ah, bl, idesc, 1u);
+                }
+                tc_commit(&acc0_full[slot]);
+                tc_commit(&a_free[buf]);
+            }
+        }
+    } else if (warp < F_MMA1_WARP0 + 2) {
+        // ================= MMA 1: row groups of this warp's parity, both 128-pixel tiles of a group =================
+        const int w = warp - F_MMA1_WARP0;
+        const uint32_t leader = elect_one() ? 1u : 0u;
+        uint32_t idesc[RS_R + 1];
+#pragma unroll
+        for (int k = 1; k <= RS_R; ++k) idesc[k] = umma_idesc_bf16(F_NP1 * k);
+        const uint32_t a_lbo = ((uint32_t)p.ring_plane >> 4) << 16;
+        const uint32_t w_lo = ((smem_u32(w1_sm) & 0x3FFFFu) >> 4) | ((uint32_t)(RS_R * F_NP1) << 16);   // LBO = 4 * 16 * 16 B
+        const uint32_t ring_lo = ((smem_u32(ring) & 0x3FFFFu) >> 4) | a_lbo;
+        for (int it = 0; it < n_it; ++it) {
+            const int B0 = it * p.NB;
+            for (int rg = w; rg < p.NG; rg += 2) {
+                const int j_lo = rg ? (4 * rg - 1) >> 3 : 0;
+                const int j_hi = min(p.NB - 1, (4 * rg + 4) >> 3);
+                f01_wait_count(&mid_cnt[(B0 + j_lo) % F_RB], (uint32_t)((B0 + j_lo) / F_RB + 1) * block_units);
+                f01_wait_count(&mid_cnt[(B0 + j_hi) % F_RB], (uint32_t)((B0 + j_hi) / F_RB + 1) * block_units);
+                fence_proxy_async();
+                uint32_t vrow[RS_R + 2];                    // ring position (16-byte units) of input row 4 rg - 1 + v, column 0
+#pragma unroll
+                for (int v = 0; v < RS_R + 2; ++v) {
+                    const int m = 4 * rg - 1 + v;
+                    const int rr = (m < 0 || m >= p.H) ? F_ZROW : ((B0 + (m >> 3)) % F_RB) * F_R0 + (m & 7);
+                    vrow[v] = (uint32_t)(rr * p.Wp);
+                }
+                for (int j = 0; j < p.JT; ++j) {
+                    const uint32_t tc1 = (uint32_t)((it * p.NG + rg) * p.JT + j);
+                    const uint32_t slot = tc1 & 3u, sph = (tc1 >> 2) & 1u;
+                    mbar_wait(&acc1_empty[slot], sph ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + 2 * F_SLOT0 + slot * F_SLOT1;
+                    const uint32_t tile_lo = ring_lo + 128u * (uint32_t)j;
+#pragma unroll
+                    for (int i = 0; i < RS_R + 2; ++i) {
+                        constexpr int order[6] = {2, 0, 1, 3, 4, 5};
+                        const int v = order[i];
+                        const int zs = v < 2 ? 2 - v : 0;
+                        const int db = v > 2 ? v - 2 : 0;
+                        const int nb = v < 2 ? v + 1 : (v > 3 ? 6 - v : 3);
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const bool first = (i == 0 && dx == 0);
+                            const uint32_t a_lo = tile_lo + vrow[v] + (uint32_t)dx;
+                            const uint32_t b_lo = w_lo + (uint32_t)(dx * 2) * (RS_R * F_NP1) + (uint32_t)zs * F_NP1;
+                            tc_mma_bf16_pred(d_tmem + (uint32_t)db * F_NP1, a_lo, b_lo, UMMA_DESC_HI, idesc[first ? RS_R : nb],
+                                             first ? 0u : 1u, leader);
+                        }
+                    }
+                    tc_commit_pred(&acc1_full[slot], leader);
+                }
+                // free the ring blocks for which this was the last row group of this warp's parity
+                for (int jb = j_lo; jb <= j_hi; ++jb)
+                    if (rg + 2 >= p.NG || rg > 2 * jb) tc_commit_pred(&mid_free[(B0 + jb) % F_RB], leader);
+            }
+        }
+    } else if (warp >= F_DRAIN_WARP0 && warp < EPI_WARP0_F) {
+        // ================= drain: TMEM -> ELU -> bf16 -> ring (lane = raster position, group g: rows g, g + DG, ..) =================
+        const int q = warp & 3, grp = (warp - F_DRAIN_WARP0) >> 2;
+        const int rows_mine = (F_R0 - grp + DG - 1) / DG;
+        for (int k = 0; k < total0; ++k) {
+            const int it = k / p.T0, t = k - it * p.T0, slot = k & 1;
+            const int B0 = it * p.NB;
+            const unsigned gw0 = (unsigned)(128 * t + 32 * q);
+            const int rb_first = (int)__umulhi(gw0, p.wp_magic), rb_last = (int)__umulhi(gw0 + 31u, p.wp_magic);
+            const unsigned g = gw0 + (unsigned)lane;
+            const int rbl = (int)__umulhi(g, p.wp_magic);
+            const int xp = (int)(g - (unsigned)rbl * (unsigned)p.Wp);
+            if (rb_first < p.NB) mbar_wait(&mid_free[(B0 + rb_first) % F_RB], (uint32_t)((((B0 + rb_first) / F_RB) & 1) ^ 1));
+            if (rb_last != rb_first && rb_last < p.NB)
+                mbar_wait(&mid_free[(B0 + rb_last) % F_RB], (uint32_t)((((B0 + rb_last) / F_RB) & 1) ^ 1));
+            mbar_wait(&acc0_full[slot], (uint32_t)((k >> 1) & 1));
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (uint32_t)slot * F_SLOT0 + ((uint32_t)(q * 32) << 16);
+            const bool col_real = xp >= 1 && xp <= p.W;
+            uint8_t *dst = ring + ((size_t)(((B0 + rbl) % F_RB) * F_R0) * p.Wp + xp) * 16;
+#pragma unroll 1
+            for (int r = grp; r < F_R0; r += DG) {
+                float v[12];
+                tmem_ld12(taddr + (uint32_t)(r * F_C0), v);
+                uint32_t pk[6];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    const __nv_bfloat162 h = __floats2bfloat162_rn(elu_f(v[2 * j]), elu_f(v[2 * j + 1]));   // bias added by the MMA
+                    pk[j] = col_real ? *reinterpret_cast<const uint32_t *>(&h) : 0u;
+                }
+                if (rbl < p.NB && rbl * F_R0 + r < p.H) {
+                    *reinterpret_cast<uint4 *>(dst + (size_t)r * p.Wp * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    *reinterpret_cast<uint4 *>(dst + (size_t)r * p.Wp * 16 + p.ring_plane) = make_uint4(pk[4], pk[5], 0u, 0u);
+                }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&acc0_empty[slot]);
+                if (rb_first < p.NB) {
+                    const int n1 = min(32, (rb_first + 1) * p.Wp - (int)gw0);
+                    red_release_shared_add(&mid_cnt[(B0 + rb_first) % F_RB], (uint32_t)(n1 * rows_mine));
+                    if (rb_last != rb_first && rb_last < p.NB)
+                        red_release_shared_add(&mid_cnt[(B0 + rb_last) % F_RB], (uint32_t)((32 - n1) * rows_mine));
+                }
+            }
+        }
+    } else if (warp >= EPI_WARP0_F) {
+        // ================= epilogue: TMEM -> 2x2 max -> bias + ELU -> bf16 -> global =================
+        const int q = warp & 3, grp = (warp - EPI_WARP0_F) >> 2;
+        const int odd = lane & 1;
+        const int total1 = n_it * p.NG * p.JT;
+        const int n_groups16 = (p.cout1 + 3) >> 2;
+        const int nchr = (p.cout1 + 7) >> 3;
+        for (int tc1 = grp; tc1 < total1; tc1 += EG) {
+            const uint32_t slot = (uint32_t)tc1 & 3u, sph = ((uint32_t)tc1 >> 2) & 1u;
+            const int G = tc1 / p.JT, j = tc1 - G * p.JT;
+            const int it = G / p.NG, rg = G - it * p.NG;
+            const long long n = (long long)blockIdx.x + (long long)it * gridDim.x;
+            mbar_wait(&acc1_full[slot], sph);
+            tc_fence_after();
+            const int c = 1 + 128 * j + q * 32 + lane;            // padded column of this lane
+            const bool valid = c <= p.W;
+            uint8_t *out_n = reinterpret_cast<uint8_t *>(p.out) + n * p.out_sample;
+            const uint32_t taddr = tmem_base + 2 * F_SLOT0 + slot * F_SLOT1 + ((uint32_t)(q * 32) << 16);
+            // rows (0,1) and (2,3) pool vertically inside the thread; lanes (2k, 2k+1) are one pooled column:
+            // the even lane finishes pooled row 0, the odd lane pooled row 1
+            const int yo = 2 * rg + odd;
+            const long long opos = ((long long)(yo + 1) * p.Wpo + ((c - 1) >> 1) + 1) * 16;
+            for (int h = 0; h < nchr; ++h) {
+                float v[32];
+                tmem_ld8x4(taddr + (uint32_t)(h * 8), (uint32_t)F_NP1, v);
+                float m[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float top = fmaxf(v[k], v[8 + k]), bot = fmaxf(v[16 + k], v[24 + k]);
+                    const float other = __shfl_xor_sync(0xffffffffu, odd ? top : bot, 1);
+                    m[k] = fmaxf(odd ? bot : top, other);
+                }
+                uint32_t pk[4];
+#pragma unroll
+                for (int q4 = 0; q4 < 2; ++q4) {
+                    if (h * 2 + q4 < n_groups16) {     // warp-uniform: padded channels stay exactly zero
+                        const float4 b4 = *reinterpret_cast<const float4 *>(&bias1_sm[h * 8 + 4 * q4]);
+                        __nv_bfloat162 h0 = __floats2bfloat162_rn(elu_f(m[4 * q4] + b4.x), elu_f(m[4 * q4 + 1] + b4.y));
+                        __nv_bfloat162 h1 = __floats2bfloat162_rn(elu_f(m[4 * q4 + 2] + b4.z), elu_f(m[4 * q4 + 3] + b4.w));
+                        pk[2 * q4] = *reinterpret_cast<uint32_t *>(&h0);
+                        pk[2 * q4 + 1] = *reinterpret_cast<uint32_t *>(&h1);
+                    } else {
+                        pk[2 * q4] = 0u;
+                        pk[2 * q4 + 1] = 0u;
+                    }
+                }
+                if (valid && yo < p.Ho && ((c - 1) >> 1) < p.Wo)
+                    *reinterpret_cast<uint4 *>(out_n + (long long)h * p.out_plane + opos) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc1_empty[slot]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == F_MMA0_WARP) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}

@@ -146,6 +146,15 @@ class Encoder(object):
                                               _lib.dptr(latents), path, _lib.stream_ptr(stream)))
         return codes, latents
 
+    def set_fusion(self, mask):
+        """Bit 0: layers 0 + 1 as one kernel (asr_encoder_set_fusion).  Returns the mask in effect."""
+        _lib.check(_lib.lib.asr_encoder_set_fusion(self.handle, int(mask)))
+        return self.fusion
+
+    @property
+    def fusion(self):
+        return int(_lib.lib.asr_encoder_get_fusion(self.handle))
+
     def set_timing(self, enable):
         _lib.check(_lib.lib.asr_encoder_set_timing(self.handle, int(bool(enable))))
 

@@ -17,7 +17,7 @@ from . import network
 from .config.settings import EXP_ROOT
 from .network import CCALayer as CCALayer1
 from .params import load_params, save_params
-from .run_train import compile_tag, select_data, select_model
+from .run_train import SYNTHETIC_BANNER, compile_tag, is_synthetic, select_data, select_model
 from .utils.batch_iterators import batch_compute1
 from .utils.cca import CCA
 
@@ -50,7 +50,7 @@ def refit(layers, X1, X2, prepare, group=None, verbose=True):
 def main(argv=None):
     parser = argparse.ArgumentParser(description='Train model.')
     parser.add_argument('--model', help='model parameters for evaluation.', default="mutopia_ccal_cont_rsz")
-    parser.add_argument('--data', help='select evaluation data.', type=str, default="mutopia")
+    parser.add_argument('--data', help="select evaluation data ('mutopia' = MSMD, 'synthetic').", type=str, default="mutopia")
     parser.add_argument('--n_train', help='number of train samples used for projection.', type=int, default=1000)
     parser.add_argument('--seed', help='query direction.', type=int, default=23)
     parser.add_argument('--train_split', help='path to train split file.', type=str, default=None)
@@ -85,12 +85,16 @@ def main(argv=None):
 
     model.EXP_NAME += "_est_UV"
     out_path = os.path.join(os.path.join(EXP_ROOT), model.EXP_NAME)
+    if is_synthetic(args.data):      # never overwrite a real refit with one made on synthetic pairs
+        dump_file_name = dump_file_name.replace(".pkl", "_synthetic.pkl")
     dump_file = args.out_file or os.path.join(out_path, dump_file_name)
     if rank == 0 and not os.path.exists(os.path.dirname(dump_file)):
         os.makedirs(os.path.dirname(dump_file))
 
     print("\nLoading data...")
     data = select_data(args.data, args.train_split, args.config, args.seed)
+    if is_synthetic(args.data) and rank == 0:
+        print(SYNTHETIC_BANNER)
     lo, hi = args.n_train * rank // world, args.n_train * (rank + 1) // world
     print("Computing train output...")
     X1, X2 = data['train'][lo:hi]

@@ -18,7 +18,7 @@ import yaml
 from . import network
 from .config.settings import EXP_ROOT
 from .params import load_params
-from .run_train import compile_tag, select_data, select_model
+from .run_train import SYNTHETIC_BANNER, compile_tag, is_synthetic, select_data, select_model
 from .utils.batch_iterators import batch_compute2
 from .utils.train_dcca_pool import eval_retrieval, retrieval_ranks
 
@@ -34,7 +34,7 @@ def flip_variables(v1, v2):
 def main(argv=None):
     parser = argparse.ArgumentParser(description='Evaluate cross-modality retrieval model.')
     parser.add_argument('--model', help='select model to evaluate.')
-    parser.add_argument('--data', help='select evaluation data.', type=str)
+    parser.add_argument('--data', help="select evaluation data ('mutopia' = MSMD, 'synthetic').", type=str)
     parser.add_argument('--show', help='show evaluation plots.', action='store_true')
     parser.add_argument('--n_test', help='number of test samples used.', type=int, default=None)
     parser.add_argument('--V2_to_V1', help='query direction.', action='store_true')
@@ -72,6 +72,8 @@ def main(argv=None):
 
     print("\nLoading data...")
     data = select_data(args.data, args.train_split, args.config, args.seed, test_only=True)
+    if is_synthetic(args.data):
+        print(SYNTHETIC_BANNER)
 
     print("\nCompiling prediction functions...")
     l_view1, l_view2, l_v1latent, l_v2latent = layers
@@ -125,8 +127,12 @@ def main(argv=None):
 
     results = {"map": float(map_), 'med_rank': float(med_rank_te),
                'recall_at_k': dict(("%d" % k, v) for k, v in recall_at_k.items())}
+    if is_synthetic(args.data):
+        results["data"] = "synthetic"
     if args.dump_results:
         ret_dir = "A2S" if args.V2_to_V1 else "S2A"
+        if is_synthetic(args.data):
+            ret_dir += "_synthetic"
         res_file = dump_file.replace("params_", "eval_").replace(".pkl", "_%s.yaml")
         res_file = res_file % ret_dir
         with open(res_file, 'w') as fp:

@@ -18,11 +18,27 @@ def select_model(model_path):
 
 
 def select_data(data_name, split_file, config_file, seed=23, test_only=False):
-    """ select train data (run_train.py:32-41) """
-    if str(data_name) in ("mutopia", "synthetic"):
+    """ select train data (run_train.py:32-41)
+
+    'mutopia' is the MSMD data set of the reference and needs its `msmd` package (absent from this image);
+    it is never silently replaced: only the explicit name 'synthetic' returns the seeded synthetic pools
+    (same pool protocol, utils/mutopia_data.py), and results computed on them are tagged as such.
+    """
+    if str(data_name) == "synthetic":
         return mutopia_data.load_audio_score_retrieval(split_file=split_file, config_file=config_file,
                                                        test_only=test_only, seed=seed)
-    raise ValueError("unknown data set %r" % (data_name,))
+    if str(data_name) == "mutopia":
+        return mutopia_data.load_msmd_audio_score_retrieval(split_file=split_file, config_file=config_file,
+                                                            test_only=test_only)
+    raise ValueError("unknown data set %r (known: 'mutopia' = MSMD via the msmd package, 'synthetic')" % (data_name,))
+
+
+def is_synthetic(data_name):
+    return str(data_name) == "synthetic"
+
+
+SYNTHETIC_BANNER = ("\n" + "!" * 78 + "\n!! --data synthetic: seeded SYNTHETIC pairs, not MSMD.  Numbers and refitted projections\n"
+                    "!! computed here say nothing about real data; output files carry the tag 'synthetic'.\n" + "!" * 78 + "\n")
 
 
 def compile_tag(train_split, config):

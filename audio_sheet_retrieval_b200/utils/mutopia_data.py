@@ -72,3 +72,17 @@ def load_audio_score_retrieval(split_file=None, config_file=None, test_only=Fals
     if test_only:
         return dict(train=None, valid=None, test=test)
     return dict(train=SyntheticPairPool(n_train, seed=seed), valid=SyntheticPairPool(n_valid, seed=seed + 1), test=test)
+
+
+def load_msmd_audio_score_retrieval(split_file=None, config_file=None, test_only=False):
+    """The reference's loader (mutopia_data.py:47-98) goes through the `msmd` package and its data set.  Neither
+    ships with this repo; when `msmd` is importable the real pools would be built here -- until then this raises
+    instead of handing out synthetic data under the real data set's name."""
+    try:
+        import msmd  # noqa: F401
+    except ImportError:
+        raise RuntimeError("--data mutopia needs the MSMD data set and the `msmd` package "
+                           "(audio_sheet_retrieval/utils/mutopia_data.py:8-13), which are not installed.  "
+                           "Use --data synthetic for the seeded synthetic pools (results are tagged 'synthetic').")
+    raise NotImplementedError("MSMD loading is out of scope of the hot path (SURVEY.md 2.1 #17): plug the reference's "
+                              "load_audio_score_retrieval in here; it must return dict(train, valid, test) of pools")

@@ -110,6 +110,12 @@ int asr_encoder_debug_activation(asr_encoder_t *enc, int layer, int path, int64_
  * get_timing synchronises on the last event, returns the summed milliseconds and resets. */
 int asr_encoder_set_timing(asr_encoder_t *enc, int enable);
 int asr_encoder_get_timing(asr_encoder_t *enc, double *ms_layer0, double *ms_conv_tc, double *ms_head, int64_t *n_calls);
+/* Kernel fusion switches (bit mask).  Bit 0: layers 0 + 1 run as ONE kernel whose layer-0 output stays in shared
+ * memory (default on where the geometry qualifies: 12 first-layer channels, width >= 126, no box filter -- the
+ * sheet branch of asr/models/mutopia_ccal_cont.py:75-79).  Switching it off restores one launch per layer (and
+ * makes layer 0 visible to asr_encoder_debug_activation).  get_fusion returns the mask in effect. */
+int asr_encoder_set_fusion(asr_encoder_t *enc, int mask);
+int asr_encoder_get_fusion(const asr_encoder_t *enc);
 /* algorithmic FLOPs per sample of this branch (2*MACs of the nine convolutions) */
 double asr_encoder_flops_per_sample(const asr_encoder_t *enc);
 

@@ -79,8 +79,25 @@ def test_tcgen05_path_per_layer_vs_fp32_path(model_name, view):
     X = X1 if view == 1 else X2
     mode = model.prepare.asr_prepare_mode if view == 1 else _lib.PREP_NONE
     enc = net.encoder(view, mode)
+    fused = enc.fusion
+    c_fused, l_fused = enc.embed_host(X, want="both", path=_lib.PATH_TCGEN05)
+    a1_fused = enc.debug_activation(1, 5, path=_lib.PATH_TCGEN05)
+    enc.set_fusion(0)            # one launch per layer: every activation reaches memory
     c_tc, l_tc = enc.embed_host(X, want="both", path=_lib.PATH_TCGEN05)
     acts_tc = [enc.debug_activation(l, 5, path=_lib.PATH_TCGEN05) for l in range(8)]
+    if fused:
+        # layers 0 + 1 in one kernel: same arithmetic up to the accumulation order inside the tensor core
+        # (8 instead of 12 rows per Toeplitz tile), so a few layer-1 outputs round to the neighbouring bf16
+        assert model_name == "mutopia_ccal_cont" and view == 1
+        d = np.abs(a1_fused - acts_tc[1])
+        assert d.max() <= 2.0 ** -7 * np.abs(acts_tc[1]).max() + 1e-3, d.max()
+        assert (d > 0).mean() < 0.02, (d > 0).mean()
+        assert _cos(c_fused, c_tc).min() > 0.9999
+        enc.set_fusion(1)
+        enc.embed_host(X, path=_lib.PATH_TCGEN05)
+        with pytest.raises(Exception):
+            enc.debug_activation(0, 5, path=_lib.PATH_TCGEN05)     # never materialised when fused
+        enc.set_fusion(0)
     c_fp, l_fp = enc.embed_host(X, want="both", path=_lib.PATH_FP32)
     for l in range(8):
         ref = enc.debug_activation(l, 5, path=_lib.PATH_FP32)
@@ -181,7 +198,11 @@ def test_layer0_tensor_core_all_input_forms(model_name, dtype, mode):
     rng = np.random.RandomState(11)
     enc = net.encoder(1, prep)      # raw input size follows the mode (the box filter halves it)
     X = rng.randint(0, 256, size=(5, 1, enc.in_h, enc.in_w)).astype(np.uint8 if dtype == "u8" else np.float32)
+    c_fused = enc.embed_host(X, path=_lib.PATH_TCGEN05) if enc.fusion else None
+    enc.set_fusion(0)
     c_tc = enc.embed_host(X, path=_lib.PATH_TCGEN05)
+    if c_fused is not None:         # the fused layer-0 + layer-1 kernel takes the same input forms
+        assert _cos(c_fused, c_tc).min() > 0.9999
     a_tc = enc.debug_activation(0, 5, path=_lib.PATH_TCGEN05)
     c_fp = enc.embed_host(X, path=_lib.PATH_FP32)
     a_fp = enc.debug_activation(0, 5, path=_lib.PATH_FP32)
@@ -227,7 +248,7 @@ np.savez({dst!r}, **out)
 
 
 @pytest.mark.parametrize("env", [{}, {"ASR_CONV_ROWS": "0"}, {"ASR_L0_TC": "0"}, {"ASR_CONV_ROWS_MULTI": "1"},
-                                 {"ASR_CONV_ROWS": "2"}])
+                                 {"ASR_CONV_ROWS": "2"}, {"ASR_FUSE01": "0"}, {"ASR_F01_VARIANT": "1"}])
 def test_kernel_variants_agree(env, tmp_path):
     """The kernel-selection switches are read once per process, so each variant runs in its own interpreter:
     raster-only conv, CUDA-core layer 0, side-by-side narrow tiles and row-stacked non-pooled layers must all

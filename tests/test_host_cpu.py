@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.SO_PATH)
     for name in declared:
         assert hasattr(lib, name), "missing export " + name
-    assert _lib.lib.asr_abi_version() == 1
+    assert _lib.lib.asr_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_library_is_sm100a_with_tcgen05_and_tma():
@@ -36,7 +36,7 @@ def test_library_is_sm100a_with_tcgen05_and_tma():
     assert "LDTM" in sass, "no tcgen05.ld in SASS"
     assert "UBLKCP" in sass and "UTMALDG" in sass, "no TMA bulk / tensor loads in SASS"
     # every hot kernel of the path is in the binary
-    for kernel in ("l0_tc_kernel", "conv3x3_rows_kernel", "conv3x3_tc_kernel", "head_kernel", "topk_stream_kernel",
+    for kernel in ("l0_tc_kernel", "l01_fused_kernel", "conv3x3_rows_kernel", "conv3x3_tc_kernel", "head_kernel", "topk_stream_kernel",
                    "topk_tc_kernel", "topk_merge_select_kernel", "cca_solve_kernel", "contrastive_rows_kernel"):
         assert kernel in sass, kernel
 
@@ -138,7 +138,11 @@ def test_batch_compute_generic_path_matches_reference(golden):
 
 def test_synthetic_pool_protocol():
     from audio_sheet_retrieval_b200.run_train import select_data
-    data = select_data("mutopia", None, None, seed=23, test_only=True)
+    with pytest.raises(RuntimeError, match="msmd"):                   # the real data set is never faked
+        select_data("mutopia", None, None, seed=23, test_only=True)
+    with pytest.raises(ValueError):
+        select_data("imagenet", None, None)
+    data = select_data("synthetic", None, None, seed=23, test_only=True)
     pool = data["test"]
     assert pool.shape[0] == 2000 and data["train"] is None
     X1, X2 = pool[np.array([0, 7, 1999])]

@@ -49,7 +49,7 @@ def test_run_eval_metrics_vs_oracle(tmp_path, capsys):
     from audio_sheet_retrieval_b200 import run_eval
     from audio_sheet_retrieval_b200.utils.mutopia_data import SyntheticPairPool
     n = 300
-    res = run_eval.main(["--model", "mutopia_ccal_cont_rsz", "--data", "mutopia", "--n_test", str(n),
+    res = run_eval.main(["--model", "mutopia_ccal_cont_rsz", "--data", "synthetic", "--n_test", str(n),
                          "--param_file", PKL])
     out = capsys.readouterr().out
     assert "Median Rank" in out and "MAP" in out
@@ -69,10 +69,15 @@ def test_run_eval_yaml_schema(tmp_path):
     import shutil
     pf = tmp_path / "params_all_split_mutopia_full_aug.pkl"
     shutil.copy(PKL, pf)
-    run_eval.main(["--model", "mutopia_ccal_cont_rsz", "--data", "mutopia", "--n_test", "40", "--param_file", str(pf),
+    run_eval.main(["--model", "mutopia_ccal_cont_rsz", "--data", "synthetic", "--n_test", "40", "--param_file", str(pf),
                    "--dump_results", "--V2_to_V1", "--max_dim", "16"])
-    res = yaml.safe_load(open(tmp_path / "eval_all_split_mutopia_full_aug_A2S.yaml"))
+    # synthetic pairs never write under the real data set's file name and are tagged in the file
+    assert not (tmp_path / "eval_all_split_mutopia_full_aug_A2S.yaml").exists()
+    res = yaml.safe_load(open(tmp_path / "eval_all_split_mutopia_full_aug_A2S_synthetic.yaml"))
+    assert res.pop("data") == "synthetic"
     assert set(res) == {"map", "med_rank", "recall_at_k"} and set(res["recall_at_k"]) == {"1", "5", "10", "25"}
+    with pytest.raises(RuntimeError, match="msmd"):
+        run_eval.main(["--model", "mutopia_ccal_cont_rsz", "--data", "mutopia", "--n_test", "40", "--param_file", str(pf)])
 
 
 def test_refine_cca_roundtrip(tmp_path):
@@ -81,7 +86,7 @@ def test_refine_cca_roundtrip(tmp_path):
     from audio_sheet_retrieval_b200 import network, refine_cca
     from audio_sheet_retrieval_b200.params import load_params
     out = tmp_path / "out" / "params.pkl"
-    refine_cca.main(["--model", "mutopia_ccal_cont_rsz", "--data", "mutopia", "--n_train", "400", "--param_file", PKL,
+    refine_cca.main(["--model", "mutopia_ccal_cont_rsz", "--data", "synthetic", "--n_train", "400", "--param_file", PKL,
                      "--out_file", str(out)])
     old, new = load_params(PKL), load_params(str(out))
     assert len(new) == 97
