@@ -69,8 +69,9 @@ cca_gram_kernel(const float *__restrict__ h1, const float *__restrict__ h2, int6
 }
 
 // fixed-order reduction of the per-CTA partials, added to sums (ASR_CCA_NSUMS layout)
-__global__ void cca_reduce_kernel(const double *__restrict__ partial, int n_part, double *__restrict__ sums) {
+__global__ void cca_reduce_kernel(const double *__restrict__ partial, int n_part, double *__restrict__ sums, double n_rows) {
     int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o == ASR_CCA_NSUMS && n_rows > 0.0) sums[o] += n_rows;     // counted layout: the row count travels with the sums
     if (o >= ASR_CCA_NSUMS) return;
     int src;
     if (o < 64) src = o;                                      // sum x | sum y
@@ -223,7 +224,7 @@ cca_solve_kernel(const double *__restrict__ sums, double n_total, const float *_
     extern __shared__ __align__(16) uint8_t smem_raw[];
     SolveSmem &sm = *reinterpret_cast<SolveSmem *>(smem_raw);
     const int tid = threadIdx.x;
-    const double n = n_total;
+    const double n = n_total > 0.0 ? n_total : sums[ASR_CCA_NSUMS];     // counted layout: read the (all-reduced) row count
     if (tid < 32) {
         sm.mx[tid] = sums[tid] / n;
         sm.my[tid] = sums[32 + tid] / n;
@@ -329,7 +330,7 @@ cca_solve_kernel(const double *__restrict__ sums, double n_total, const float *_
     }
 }
 
-static double *g_partial = nullptr;
+static double *g_partial[ASR_MAX_DEVICES] = {nullptr};     // per device (allocated on first use)
 
 }  // namespace asr
 
@@ -337,22 +338,34 @@ using namespace asr;
 
 extern "C" {
 
-int asr_cca_accumulate(const float *h1_dev, const float *h2_dev, int64_t n, const float *shift1_dev,
-                       const float *shift2_dev, double *sums_dev, void *stream) {
+static int cca_accumulate(const float *h1_dev, const float *h2_dev, int64_t n, const float *shift1_dev,
+                          const float *shift2_dev, double *sums_dev, bool counted, void *stream) {
     int rc = ensure_device();
     if (rc) return rc;
     ASR_CHECK_ARG(h1_dev && h2_dev && sums_dev, "NULL buffer");
     ASR_CHECK_ARG(n >= 0, "n < 0");
     if (n == 0) return ASR_OK;
-    if (!g_partial) ASR_CUDA(cudaMalloc(&g_partial, sizeof(double) * CC_PART * CC_MAX_CTAS));
+    const int dev = current_device();
+    ASR_CHECK_ARG(dev >= 0 && dev < ASR_MAX_DEVICES, "device ordinal out of range");
+    if (!g_partial[dev]) ASR_CUDA(cudaMalloc(&g_partial[dev], sizeof(double) * CC_PART * CC_MAX_CTAS));
     cudaStream_t st = (cudaStream_t)stream;
     int64_t n_tiles = (n + CC_ROWS - 1) / CC_ROWS;
     int grid = (int)std::min<int64_t>(n_tiles, std::min(CC_MAX_CTAS, 2 * sm_count()));
-    cca_gram_kernel<<<grid, CC_THREADS, 0, st>>>(h1_dev, h2_dev, n, shift1_dev, shift2_dev, g_partial);
+    cca_gram_kernel<<<grid, CC_THREADS, 0, st>>>(h1_dev, h2_dev, n, shift1_dev, shift2_dev, g_partial[dev]);
     ASR_LAUNCH_CHECK();
-    cca_reduce_kernel<<<(ASR_CCA_NSUMS + 127) / 128, 128, 0, st>>>(g_partial, grid, sums_dev);
+    cca_reduce_kernel<<<(ASR_CCA_NSUMS + 1 + 127) / 128, 128, 0, st>>>(g_partial[dev], grid, sums_dev, counted ? (double)n : 0.0);
     ASR_LAUNCH_CHECK();
     return ASR_OK;
+}
+
+int asr_cca_accumulate(const float *h1_dev, const float *h2_dev, int64_t n, const float *shift1_dev,
+                       const float *shift2_dev, double *sums_dev, void *stream) {
+    return cca_accumulate(h1_dev, h2_dev, n, shift1_dev, shift2_dev, sums_dev, false, stream);
+}
+
+int asr_cca_accumulate_counted(const float *h1_dev, const float *h2_dev, int64_t n, const float *shift1_dev,
+                               const float *shift2_dev, double *sums_dev, void *stream) {
+    return cca_accumulate(h1_dev, h2_dev, n, shift1_dev, shift2_dev, sums_dev, true, stream);
 }
 
 int asr_cca_solve(const double *sums_dev, int64_t n_total, const float *shift1_dev, const float *shift2_dev, double r1,
@@ -361,13 +374,15 @@ int asr_cca_solve(const double *sums_dev, int64_t n_total, const float *shift1_d
     int rc = ensure_device();
     if (rc) return rc;
     ASR_CHECK_ARG(sums_dev && m1_dev && m2_dev && U_dev && V_dev && sigma_dev, "NULL buffer");
-    ASR_CHECK_ARG(n_total >= 2, "need at least 2 samples");
+    ASR_CHECK_ARG(n_total >= 2 || n_total == ASR_CCA_COUNT_ON_DEVICE, "need at least 2 samples");
     ASR_CHECK_ARG(mode == 0 || mode == 1, "mode must be 0 (svd) or 1 (layer)");
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[ASR_MAX_DEVICES] = {false};
+    const int dev = current_device();
+    ASR_CHECK_ARG(dev >= 0 && dev < ASR_MAX_DEVICES, "device ordinal out of range");
+    if (!attr_done[dev]) {
         ASR_CUDA(cudaFuncSetAttribute(cca_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)sizeof(SolveSmem)));
-        attr_done = true;
+        attr_done[dev] = true;
     }
     cca_solve_kernel<<<1, SV_THREADS, sizeof(SolveSmem), (cudaStream_t)stream>>>(
         sums_dev, (double)n_total, shift1_dev, shift2_dev, r1, r2, rT, mode, m1_dev, m2_dev, U_dev, V_dev, sigma_dev);

@@ -46,6 +46,12 @@ inline void count_launch(int n = 1) { g_launches += n; }
 
 int ensure_device();   // returns ASR_OK or ASR_ERR_CUDA (no device / not sm_100)
 int sm_count();
+// per-device one-time state (kernel attributes, scratch) is kept in arrays indexed by the device ordinal
+constexpr int ASR_MAX_DEVICES = 64;
+inline int current_device() {
+    int d = 0;
+    return cudaGetDevice(&d) == cudaSuccess ? d : -1;
+}
 
 // ------------------------------------------------------------------------------------
 // device-side PTX wrappers
@@ -93,6 +99,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
         if (globaltimer_ns() - t0 > 4000000000ull) {
             printf("asr: mbarrier timeout block %d thread %d parity %u\n", blockIdx.x, threadIdx.x, parity);
+            __trap();
+        }
+    }
+}
+
+// the same with a caller-supplied tag in the timeout message (which role waited, at which step)
+__device__ __forceinline__ void mbar_wait_tag(uint64_t *bar, uint32_t parity, int tag) {
+    if (mbar_try_wait(bar, parity)) return;
+    const uint64_t t0 = globaltimer_ns();
+    while (!mbar_try_wait(bar, parity)) {
+        if (globaltimer_ns() - t0 > 2000000000ull) {
+            if ((threadIdx.x & 31) == 0)
+                printf("asr: mbarrier timeout block %d warp %d parity %u tag %d\n", blockIdx.x, threadIdx.x >> 5, parity, tag);
             __trap();
         }
     }
@@ -169,6 +188,31 @@ __device__ __forceinline__ void tc_mma_bf16_pred(uint32_t d_tmem, uint32_t a_lo,
         "mov.b64 db, {%2, %3};\n\t"
         "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
         ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(leader)
+        : "memory");
+}
+// The same issued by ONE elected lane of a fully converged warp, with the election INSIDE the asm block: ptxas then
+// sees a tcgen05.mma guarded by elect.sync's own predicate and emits a single UTCHMMA on uniform registers (a handful
+// of UIADD3 / UMOV per MMA when the operands derive from kernel parameters, blockIdx and loop counters).  With a
+// predicate that went through a general register (tc_mma_bf16_pred) it must assume any subset of lanes and wraps every
+// MMA in an elect / broadcast / branch sequence of ~17 instructions.
+__device__ __forceinline__ void tc_mma_bf16_elect(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                                  uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint64_t *bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(smem_u32(bar))
         : "memory");
 }
 __device__ __forceinline__ void tc_commit_pred(uint64_t *bar, uint32_t leader) {

@@ -103,7 +103,10 @@ __device__ __forceinline__ int band_tiles(const ConvParams &p, int y0) {
 template <int KPAIRS>
 __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(const ConvParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // warp index through a lane-0 broadcast: the compiler then knows the role branches are warp-uniform and keeps the
+    // MMA issuers' descriptor arithmetic on the uniform datapath (see tc_mma_bf16_elect)
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     uint8_t *w_sm = smem;
     float *bias_sm = reinterpret_cast<float *>(smem + p.off_bias);
     uint8_t *stage_sm = smem + p.off_stage;
@@ -167,9 +170,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(const ConvP
         // ================= MMA issuers (4 warps, tile tc belongs to warp tc & 3) =================
         const uint32_t my = (uint32_t)(warp - 1);
         // The whole warp walks the (uniform, fully unrolled) issue sequence so that descriptors live in
-        // uniform registers; the tcgen05 instructions themselves are predicated on one elected lane.
-        // Descriptors advance by adding to their low word (start-address field, 16-byte units).
-        const uint32_t leader = elect_one() ? 1u : 0u;
+        // uniform registers; the tcgen05 instructions themselves are issued by one elected lane (elect.sync inside
+        // the asm block).  Descriptors advance by adding to their low word (start-address field, 16-byte units).
+        const bool no_mma = (p.dbg & 2) != 0;
         const uint32_t idesc = umma_idesc_bf16(p.NP);
         const uint32_t a_lbo = ((uint32_t)p.sps >> 4) << 16;                   // LBO = smem plane stride
         const uint32_t w_lo = ((smem_u32(w_sm) & 0x3FFFFu) >> 4) | ((uint32_t)p.NP << 16);   // LBO = NP*16 B
@@ -199,20 +202,21 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(const ConvP
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + slot * (uint32_t)p.slot_cols;
                 uint32_t b_lo = w_lo;
+                if (!no_mma) {
 #pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                    uint32_t a_lo = tile_lo + (uint32_t)(t / 3) * wp + (uint32_t)(t % 3);
+                    for (int t = 0; t < 9; ++t) {
+                        uint32_t a_lo = tile_lo + (uint32_t)(t / 3) * wp + (uint32_t)(t % 3);
 #pragma unroll
-                    for (int kp = 0; kp < KPAIRS; ++kp) {
-                        tc_mma_bf16_pred(d_tmem, a_lo, b_lo, UMMA_DESC_HI, idesc, (t | kp) != 0 ? 1u : 0u,
-                                         (p.dbg & 2) ? 0u : leader);
-                        a_lo += kstep_a;
-                        b_lo += kstep_b;
+                        for (int kp = 0; kp < KPAIRS; ++kp) {
+                            tc_mma_bf16_elect(d_tmem, a_lo, b_lo, UMMA_DESC_HI, idesc, (t | kp) != 0 ? 1u : 0u);
+                            a_lo += kstep_a;
+                            b_lo += kstep_b;
+                        }
                     }
                 }
-                tc_commit_pred(&acc_full[slot], leader);
+                tc_commit_elect(&acc_full[slot]);
             }
-            tc_commit_pred(&in_empty[s], leader);
+            tc_commit_elect(&in_empty[s]);
             tc0 += (uint32_t)mtb;
         }
     } else {
@@ -369,7 +373,8 @@ __device__ __forceinline__ int rows_band_tiles(const ConvParams &p, int y0) {
 template <int KPAIRS>
 __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_rows_kernel(const ConvParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // provably warp-uniform (see conv3x3_tc_kernel)
     uint8_t *w_sm = smem;
     float *bias_sm = reinterpret_cast<float *>(smem + p.off_bias);
     uint8_t *stage_sm = smem + p.off_stage;
@@ -463,8 +468,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_rows_kernel(const Con
     } else if (warp < EPI_WARP0) {
         // ================= MMA issuers =================
         const uint32_t my = (uint32_t)(warp - 1);
-        const uint32_t leader = (p.dbg & 2) ? 0u : (elect_one() ? 1u : 0u);
-        const uint32_t commit_leader = elect_one() ? 1u : 0u;
+        const bool no_mma = (p.dbg & 2) != 0;
         const uint32_t np = (uint32_t)p.NP;
         uint32_t idesc[RS_R + 1];
 #pragma unroll
@@ -498,6 +502,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_rows_kernel(const Con
                 const uint32_t d_tmem = tmem_base + slot * (uint32_t)p.slot_cols;
                 // input row v of the group: block list window [zs, zs + nb) -> accumulator blocks [db, db + nb)
                 //   v : 2 0 1 3 4 5   (v = 2 first: with a 4th, all-zero block it initialises every column)
+                if (!no_mma) {
 #pragma unroll
                 for (int i = 0; i < RS_R + 2; ++i) {
                     constexpr int order[6] = {2, 0, 1, 3, 4, 5};
@@ -512,16 +517,17 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_rows_kernel(const Con
 #pragma unroll
                         for (int kp = 0; kp < KPAIRS; ++kp) {
                             const bool first = (i == 0 && dx == 0 && kp == 0);
-                            tc_mma_bf16_pred(d_tmem + (uint32_t)db * np, a_lo, b_lo, UMMA_DESC_HI, idesc[first ? RS_R : nb],
-                                             first ? 0u : 1u, leader);
+                            tc_mma_bf16_elect(d_tmem + (uint32_t)db * np, a_lo, b_lo, UMMA_DESC_HI, idesc[first ? RS_R : nb],
+                                              first ? 0u : 1u);
                             a_lo += kstep_a;
                             b_lo += 2u * RS_R * np;
                         }
                     }
                 }
-                tc_commit_pred(&acc_full[slot], commit_leader);
+                }
+                tc_commit_elect(&acc_full[slot]);
             }
-            tc_commit_pred(&in_empty[s], commit_leader);
+            tc_commit_elect(&in_empty[s]);
             tc0 += (uint32_t)mtb;
         }
     } else {
@@ -1006,7 +1012,8 @@ template <int C>
 __global__ void __launch_bounds__(L0T_THREADS, 1) l0_tc_kernel(const L0TcParams q) {
     extern __shared__ __align__(128) uint8_t smem[];
     const L0Params &p = q.b;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // provably warp-uniform (see conv3x3_tc_kernel)
     const int bbytes = 3 * 2 * 2 * q.NPAD * 16;
     constexpr int ABUF = 2 * 2 * L0T_AROWS * 16;                    // [part][K chunk][L0T_AROWS][8] bf16
     uint8_t *b_sm = smem;
@@ -1046,30 +1053,33 @@ __global__ void __launch_bounds__(L0T_THREADS, 1) l0_tc_kernel(const L0TcParams 
         else
             l0t_convert<1>(q, a_sm + warp * ABUF, lut_sm, &a_ready[warp], &a_free[warp], n_tiles, warp);
     } else if (warp == L0T_PROD_WARPS) {
-        // ================= MMA issuer: per dx (A_hi, B_hi), (A_lo, B_hi), (A_hi, B_lo)
-        if (lane == 0) {
+        // ================= MMA issuer: per dx (A_hi, B_hi), (A_lo, B_hi), (A_hi, B_lo); whole warp, one elected lane issues
+        {
             const uint32_t idesc = umma_idesc_bf16(q.NPAD);
-            const uint32_t b0 = smem_u32(b_sm), b_part = 2 * q.NPAD * 16;
+            const uint32_t b_part = (uint32_t)(2 * q.NPAD);                                              // 16-byte units
+            const uint32_t b_lo0 = ((smem_u32(b_sm) & 0x3FFFFu) >> 4) | ((uint32_t)q.NPAD << 16);       // LBO = NPAD * 16 B
+            const uint32_t a_base = ((smem_u32(a_sm) & 0x3FFFFu) >> 4) | ((uint32_t)L0T_AROWS << 16);    // LBO = 136 * 16 B
+            const bool two_parts = !q.int_pixels, no_mma = (q.dbg & 4) != 0;
             int k = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++k) {
                 const int buf = k % L0T_NBUF, slot = k & 1;
                 mbar_wait(&a_ready[buf], (uint32_t)((k / L0T_NBUF) & 1));
                 mbar_wait(&acc_empty[slot], (uint32_t)(((k >> 1) & 1) ^ 1));
                 tc_fence_after();
-                const uint32_t a0 = smem_u32(a_sm + buf * ABUF);
+                const uint32_t a0 = a_base + (uint32_t)buf * (ABUF / 16);
                 const uint32_t d = tmem_base + (uint32_t)slot * L0T_SLOT_COLS;
+                if (!no_mma) {
 #pragma unroll
-                for (int dx = 0; dx < ((q.dbg & 4) ? 0 : 3); ++dx) {
-                    const uint64_t ah = umma_desc(a0 + dx * 16, L0T_AROWS * 16, 128);
-                    const uint64_t al = umma_desc(a0 + ABUF / 2 + dx * 16, L0T_AROWS * 16, 128);
-                    const uint64_t bh = umma_desc(b0 + (dx * 2) * b_part, q.NPAD * 16, 128);
-                    const uint64_t bl = umma_desc(b0 + (dx * 2 + 1) * b_part, q.NPAD * 16, 128);
-                    tc_mma_bf16(d, ah, bh, idesc, dx > 0 ? 1u : 0u);
-                    if (!q.int_pixels) tc_mma_bf16(d, al, bh, idesc, 1u);
-                    tc_mma_bf16(d, ah, bl, idesc, 1u);
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const uint32_t ah = a0 + (uint32_t)dx, al = a0 + (ABUF / 32) + (uint32_t)dx;
+                        const uint32_t bh = b_lo0 + (uint32_t)(dx * 2) * b_part, bl = b_lo0 + (uint32_t)(dx * 2 + 1) * b_part;
+                        tc_mma_bf16_elect(d, ah, bh, UMMA_DESC_HI, idesc, dx > 0 ? 1u : 0u);
+                        if (two_parts) tc_mma_bf16_elect(d, al, bh, UMMA_DESC_HI, idesc, 1u);
+                        tc_mma_bf16_elect(d, ah, bl, UMMA_DESC_HI, idesc, 1u);
+                    }
                 }
-                tc_commit(&acc_full[slot]);
-                tc_commit(&a_free[buf]);
+                tc_commit_elect(&acc_full[slot]);
+                tc_commit_elect(&a_free[buf]);
             }
         }
     } else {
@@ -1726,13 +1736,14 @@ int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *d, int max_b
         E_CUDA(cudaMemcpy(e->cca_mean, d->cca_mean, 32 * 4, cudaMemcpyHostToDevice));
         E_CUDA(cudaMemcpy(e->cca_proj, d->cca_proj, 1024 * 4, cudaMemcpyHostToDevice));
     }
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[ASR_MAX_DEVICES] = {false};     // cudaFuncSetAttribute is per device
+    const int attr_dev = std::max(0, std::min(current_device(), ASR_MAX_DEVICES - 1));
+    if (!attr_done[attr_dev]) {
         E_CUDA(cudaFuncSetAttribute(l0_tc_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         E_CUDA(cudaFuncSetAttribute(l0_tc_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         E_CUDA(cudaFuncSetAttribute(conv3x3_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        E_CUDA(cudaFuncSetAttribute(l01_fused_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        E_CUDA(cudaFuncSetAttribute(l01_fused_kernel<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        E_CUDA(cudaFuncSetAttribute(l01_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        E_CUDA(cudaFuncSetAttribute(l01_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         E_CUDA(cudaFuncSetAttribute(conv3x3_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         E_CUDA(cudaFuncSetAttribute(conv3x3_rows_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         E_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
@@ -1741,7 +1752,7 @@ int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *d, int max_b
         E_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         E_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         E_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        attr_done = true;
+        attr_done[attr_dev] = true;
     }
 #undef E_CUDA
     *out = e;
@@ -1878,10 +1889,12 @@ int asr_encoder_embed(asr_encoder_t *e, const void *x_dev, int x_dtype, int64_t 
                 f.off_ring -= delta; f.off_lut -= delta; f.off_bar -= delta;
                 smem = e->f01_smem_int;
             }
+            static const int f01_dbg = getenv("ASR_F01_DEBUG") ? atoi(getenv("ASR_F01_DEBUG")) : 0;
+            f.dbg = f01_dbg;
             const int grid = (int)std::min<int64_t>(n, sm_count());
             static const int variant = getenv("ASR_F01_VARIANT") ? atoi(getenv("ASR_F01_VARIANT")) : 0;
-            if (variant == 1) l01_fused_kernel<3, 3><<<grid, 32 * (F_DRAIN_WARP0 + 4 * 6), smem, st>>>(f);
-            else l01_fused_kernel<2, 3><<<grid, 32 * (F_DRAIN_WARP0 + 4 * 5), smem, st>>>(f);
+            if (variant == 1) l01_fused_kernel<1><<<grid, 32 * (F_DRAIN_WARP0 + 4 * (1 + F_EG)), smem, st>>>(f);
+            else l01_fused_kernel<2><<<grid, 32 * (F_DRAIN_WARP0 + 4 * (2 + F_EG)), smem, st>>>(f);
             ASR_LAUNCH_CHECK();
             return ASR_OK;
         };

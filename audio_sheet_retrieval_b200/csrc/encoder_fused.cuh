@@ -18,14 +18,18 @@
 // that the two MMA-1 warps commit to after the last row group of their parity that reads the block.
 #pragma once
 
-constexpr int F_R0 = 8;                       // layer-0 output rows per tile = rows per ring block
-constexpr int F_RB = 3;                       // ring blocks
+#ifndef ASR_F01_R0
+#define ASR_F01_R0 8
+#endif
+constexpr int F_R0 = ASR_F01_R0;              // layer-0 output rows per tile = rows per ring block (4 or 8)
+constexpr int F_R0_SHIFT = F_R0 == 8 ? 3 : 2;
+constexpr int F_RB = 24 / F_R0;               // ring blocks (24 rows: finer blocks = more of the ring usable as slack)
 constexpr int F_ZROW = F_R0 * F_RB;           // index of the all-zero ring row
 constexpr int F_CW = 4;                       // converter warps = A buffers
 constexpr int F_AROWS = 136;                  // 130 raster positions of a tile + slack
 constexpr int F_C0 = 12;                      // layer-0 channels
 constexpr int F_NPAD0 = F_R0 * F_C0;          // 96
-constexpr int F_SLOT0 = 128, F_SLOT1 = 64;    // TMEM columns per accumulator slot (layer 0: 2 slots, layer 1: 4)
+constexpr int F_SLOT0 = F_R0 == 8 ? 128 : 64, F_SLOT1 = 64;    // TMEM columns per accumulator slot (layer 0: 2 slots, layer 1: 4)
 constexpr int F_NP1 = 16;                     // padded layer-1 channels
 constexpr int F_W1BYTES = 3 * 2 * RS_R * F_NP1 * 16;
 constexpr int F_TAIL = 2176;
@@ -45,11 +49,13 @@ struct F01Params {
     int ring_plane;             // (F_ZROW + 1) * Wp * 16 bytes per 8-channel chunk
     int abuf;                   // bytes per A buffer
     int off_w1, off_a, off_ring, off_lut, off_bar;
+    int dbg;                    // diagnostics (env ASR_F01_DEBUG, bits): 1 no epilogue work, 2 no layer-1 MMAs, 4 no drain work,
+                                // 8 no layer-0 MMAs, 16 no converter work (results are garbage; for timing the roles apart)
 };
 
 // One converter warp builds whole A tiles: 260 items (K chunk c, tile row i) = 9 per lane in batches of three.
 // A row i <-> raster position g = 128 t - 1 + i = rbl * Wp + xp; K element kk <-> image row 8 rbl - 1 + kk
-// (kk = 0..9 are used by the 8 output rows of the block, kk = 15 carries the constant 1 of the bias row).
+// (kk = 0 .. F_R0 + 1 are used by the output rows of the block, kk = 15 carries the constant 1 of the bias row).
 template <bool INT_PIXELS>
 __device__ __forceinline__ void f01_convert_tile(const F01Params &p, uint8_t *a_buf, const float *lut, long long sample_off, int t) {
     const int lane = threadIdx.x & 31;
@@ -74,7 +80,7 @@ __device__ __forceinline__ void f01_convert_tile(const F01Params &p, uint8_t *a_
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
                 const int y = yb + kk;
-                const bool in = ok[u] && y >= 0 && y < p.H && (c == 0 || kk < 2);
+                const bool in = ok[u] && y >= 0 && y < p.H && 8 * c + kk < F_R0 + 2;     // K rows the block's taps reach
                 const unsigned o = base + (unsigned)(min(max(y, 0), p.H - 1) * p.W);
                 raw[u][kk] = 0u;
                 if (in) raw[u][kk] = p.x_u8 ? (uint32_t)xu[o] : __float_as_uint(xf[o]);
@@ -120,20 +126,96 @@ __device__ __forceinline__ void f01_wait_count(const uint32_t *cnt, uint32_t tar
     if (ld_acquire_shared(cnt) >= target) return;
     const uint64_t t0 = globaltimer_ns();
     while (ld_acquire_shared(cnt) < target) {
-        if (globaltimer_ns() - t0 > 4000000000ull) {
-            printf("asr: ring counter timeout block %d thread %d target %u have %u\n", blockIdx.x, threadIdx.x, target,
-                   ld_acquire_shared(cnt));
+        if (globaltimer_ns() - t0 > 2000000000ull) {
+            if ((threadIdx.x & 31) == 0)
+                printf("asr: ring counter timeout block %d warp %d target %u have %u\n", blockIdx.x, threadIdx.x >> 5, target,
+                       ld_acquire_shared(cnt));
             __trap();
         }
     }
 }
 
-template <int DG, int EG>   // drain groups (layer 0) and epilogue groups (layer 1), four warps each
-__global__ void __launch_bounds__(32 * (F_DRAIN_WARP0 + 4 * (DG + EG)), 1) l01_fused_kernel(const F01Params p) {
-    constexpr int NTHREADS = 32 * (F_DRAIN_WARP0 + 4 * (DG + EG));
+// MMA-1 issuer of parity W: row groups rg = W, W + 2, ..., both 128-pixel tiles of a group.  Everything that feeds a
+// tcgen05 operand is computed from kernel parameters, blockIdx and loop counters only (W is a template constant, the
+// TMEM base of a 512-column allocation is column 0 -- checked), so the compiler keeps descriptors in UNIFORM registers
+// and an MMA costs a few uniform instructions instead of an elect / broadcast sequence per operand.
+template <int W>
+__device__ __forceinline__ void f01_mma1(const F01Params &p, uint8_t *smem, int n_it, uint32_t block_units, uint32_t *mid_cnt,
+                                         uint64_t *acc1_full, uint64_t *acc1_empty, uint64_t *mid_free, uint32_t tmem_base) {
+    if (tmem_base != 0u) __trap();                         // one CTA per SM owns all 512 columns: the allocation starts at 0
+    const bool no_mma = (p.dbg & 2) != 0;
+    const uint32_t a_lbo = ((uint32_t)p.ring_plane >> 4) << 16;
+    const uint32_t w_lo = ((smem_u32(smem + p.off_w1) & 0x3FFFFu) >> 4) | ((uint32_t)(RS_R * F_NP1) << 16);   // LBO = 4 * 16 * 16 B
+    const uint32_t ring_lo = ((smem_u32(smem + p.off_ring) & 0x3FFFFu) >> 4) | a_lbo;
+    const uint32_t wp = (uint32_t)p.Wp;
+    uint32_t u = 0;                                     // this warp's running tile count
+    for (int it = 0; it < n_it; ++it) {
+        const int B0 = it * p.NB;
+        for (int rg = W; rg < p.NG; rg += 2) {
+            const int j_lo = rg ? (4 * rg - 1) >> F_R0_SHIFT : 0;
+            const int j_hi = min(p.NB - 1, (4 * rg + 4) >> F_R0_SHIFT);
+            for (int jb = j_lo; jb <= j_hi; ++jb)
+                f01_wait_count(&mid_cnt[(B0 + jb) % F_RB], (uint32_t)((B0 + jb) / F_RB + 1) * block_units);
+            fence_proxy_async();
+            uint32_t vrow[RS_R + 2];                    // ring position (16-byte units) of input row 4 rg - 1 + v, column 0
+#pragma unroll
+            for (int v = 0; v < RS_R + 2; ++v) {
+                const int m = 4 * rg - 1 + v;
+                const int rr = (m < 0 || m >= p.H) ? F_ZROW : ((B0 + (m >> F_R0_SHIFT)) % F_RB) * F_R0 + (m & (F_R0 - 1));
+                vrow[v] = (uint32_t)rr * wp;
+            }
+            for (int j = 0; j < p.JT; ++j, ++u) {
+                const uint32_t slot = 2u * (uint32_t)W + (u & 1u), sph = (u >> 1) & 1u;
+                mbar_wait_tag(&acc1_empty[slot], sph ^ 1u, 4000000 + (int)u);
+                tc_fence_after();
+                const uint32_t d_tmem = 2 * F_SLOT0 + slot * F_SLOT1;
+                const uint32_t tile_lo = ring_lo + 128u * (uint32_t)j;
+                if (!no_mma) {
+#pragma unroll
+                for (int i = 0; i < RS_R + 2; ++i) {
+                    constexpr int order[6] = {2, 0, 1, 3, 4, 5};
+                    const int v = order[i];
+                    const int zs = v < 2 ? 2 - v : 0;
+                    const int db = v > 2 ? v - 2 : 0;
+                    const int nb = v < 2 ? v + 1 : (v > 3 ? 6 - v : 3);
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const bool first = (i == 0 && dx == 0);
+                        const uint32_t a_lo = tile_lo + vrow[v] + (uint32_t)dx;
+                        const uint32_t b_lo = w_lo + (uint32_t)(dx * 2) * (RS_R * F_NP1) + (uint32_t)zs * F_NP1;
+                        tc_mma_bf16_elect(d_tmem + (uint32_t)db * F_NP1, a_lo, b_lo, UMMA_DESC_HI,
+                                          umma_idesc_bf16(F_NP1 * (first ? RS_R : nb)), first ? 0u : 1u);
+                    }
+                }
+                }
+                tc_commit_elect(&acc1_full[slot]);
+            }
+            // free the ring blocks for which this was the last row group of this warp's parity: those that the next
+            // group of the same parity (rg + 2, rows 4 rg + 7 ...) no longer reads.  Every block is read by groups of
+            // both parities, so each block use gets exactly two arrivals.
+            const int next_lo = (4 * rg + 7) >> F_R0_SHIFT;
+            for (int jb = j_lo; jb <= j_hi; ++jb)
+                if (rg + 2 >= p.NG || jb < next_lo) tc_commit_elect(&mid_free[(B0 + jb) % F_RB]);
+        }
+    }
+}
+
+
+// DG drain groups (layer 0) and four epilogue groups (layer 1), four warps each.  Every layer-1 accumulator slot has
+// exactly one producer and one consumer -- slot 2 w + (u & 1) belongs to MMA-1 warp w (u = its running tile count)
+// and is drained by epilogue group 2 w + (u & 1) -- so nobody can run two mbarrier phases ahead of a slot (with
+// shared slots a wait on "parity p" is satisfied by the phase before the previous one).
+constexpr int F_EG = 4;
+template <int DG>
+__global__ void __launch_bounds__(32 * (F_DRAIN_WARP0 + 4 * (DG + F_EG)), 1) l01_fused_kernel(const F01Params p) {
+    constexpr int NTHREADS = 32 * (F_DRAIN_WARP0 + 4 * (DG + F_EG));
     constexpr int EPI_WARP0_F = F_DRAIN_WARP0 + 4 * DG;
     extern __shared__ __align__(128) uint8_t smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // The warp index goes through a lane-0 broadcast so that the compiler KNOWS it is warp-uniform: the role branches
+    // below are then uniform control flow, and the MMA issuers' descriptor arithmetic stays on the uniform datapath
+    // (with `tid >> 5` every role body counts as divergent code and each tcgen05.mma gets an elect / R2UR sequence).
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     uint8_t *b0_sm = smem;
     uint8_t *w1_sm = smem + p.off_w1;
     float *bias1_sm = reinterpret_cast<float *>(w1_sm + F_W1BYTES);
@@ -145,11 +227,11 @@ __global__ void __launch_bounds__(32 * (F_DRAIN_WARP0 + 4 * (DG + EG)), 1) l01_f
     uint64_t *a_free = bars + 4;          // [F_CW]  MMA 0 done reading the A buffer
     uint64_t *acc0_full = bars + 8;       // [2]
     uint64_t *acc0_empty = bars + 10;     // [2]
-    uint64_t *mid_free = bars + 12;       // [F_RB]  MMA 1 done reading the ring block
-    uint64_t *acc1_full = bars + 15;      // [4]
-    uint64_t *acc1_empty = bars + 19;     // [4]
-    uint32_t *mid_cnt = reinterpret_cast<uint32_t *>(bars + 23);   // [F_RB] finished (position, row) units, monotonic
-    uint32_t *tmem_ptr = mid_cnt + 4;
+    uint64_t *mid_free = bars + 12;       // [F_RB <= 6]  MMA 1 done reading the ring block
+    uint64_t *acc1_full = bars + 18;      // [4]
+    uint64_t *acc1_empty = bars + 22;     // [4]
+    uint32_t *mid_cnt = reinterpret_cast<uint32_t *>(bars + 26);   // [F_RB] finished (position, row) units, monotonic
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 29);
 
     constexpr int B0BYTES = 3 * 2 * 2 * F_NPAD0 * 16;
     for (int i = tid; i < B0BYTES / 16; i += NTHREADS)
@@ -182,94 +264,47 @@ __global__ void __launch_bounds__(32 * (F_DRAIN_WARP0 + 4 * (DG + EG)), 1) l01_f
         for (int k = warp; k < total0; k += F_CW) {
             const int it = k / p.T0, t = k - it * p.T0;
             const long long n = (long long)blockIdx.x + (long long)it * gridDim.x;
-            mbar_wait(&a_free[warp], (uint32_t)((((k / F_CW) & 1)) ^ 1));
-            if (p.int_pixels) f01_convert_tile<true>(p, a_buf, lut_sm, n * p.H * p.W, t);
+            mbar_wait_tag(&a_free[warp], (uint32_t)((((k / F_CW) & 1)) ^ 1), 1000000 + k);
+            if (p.dbg & 16) {
+            } else if (p.int_pixels) f01_convert_tile<true>(p, a_buf, lut_sm, n * p.H * p.W, t);
             else f01_convert_tile<false>(p, a_buf, lut_sm, n * p.H * p.W, t);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_ready[warp]);
         }
     } else if (warp == F_MMA0_WARP) {
-        // ================= MMA 0: per dx (A_hi, B_hi) [, (A_lo, B_hi)], (A_hi, B_lo) =================
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(F_NPAD0);
-            const uint32_t b0 = smem_u32(b0_sm), b_part = 2 * F_NPAD0 * 16;
-            for (int k = 0; k < total0; ++k) {
-                const int buf = k & (F_CW - 1), slot = k & 1;
-                mbar_wait(&a_ready[buf], (uint32_t)((k / F_CW) & 1));
-                mbar_wait(&acc0_empty[slot], (uint32_t)(((k >> 1) & 1) ^ 1));
-                tc_fence_after();
-                const uint32_t a0 = smem_u32(a_sm + buf * p.abuf);
-                const uint32_t d = tmem_base + (uint32_t)slot * F_SLOT0;
+        // ================= MMA 0: per dx (A_hi, B_hi) [, (A_lo, B_hi)], (A_hi, B_lo); whole warp, one elected lane issues =================
+        if (tmem_base != 0u) __trap();
+        const uint32_t idesc = umma_idesc_bf16(F_NPAD0);
+        const uint32_t b_part = (2 * F_NPAD0 * 16) >> 4;                                    // 16-byte units
+        const uint32_t b_lo0 = ((smem_u32(smem) & 0x3FFFFu) >> 4) | ((uint32_t)F_NPAD0 << 16);     // LBO = 96 * 16 B
+        const uint32_t a_base = ((smem_u32(smem + p.off_a) & 0x3FFFFu) >> 4) | ((uint32_t)F_AROWS << 16);   // LBO = 136 * 16 B
+        const uint32_t abuf16 = (uint32_t)p.abuf >> 4;
+        const bool two_parts = !p.int_pixels, no_mma0 = (p.dbg & 8) != 0;
+        for (int k = 0; k < total0; ++k) {
+            const int buf = k & (F_CW - 1), slot = k & 1;
+            mbar_wait_tag(&a_ready[buf], (uint32_t)((k / F_CW) & 1), 2000000 + k);
+            mbar_wait_tag(&acc0_empty[slot], (uint32_t)(((k >> 1) & 1) ^ 1), 3000000 + k);
+            tc_fence_after();
+            const uint32_t a0 = a_base + (uint32_t)buf * abuf16;
+            const uint32_t d = (uint32_t)slot * F_SLOT0;
+            if (!no_mma0) {
 #pragma unroll
                 for (int dx = 0; dx < 3; ++dx) {
-                    const uint64_t ah = umma_desc(a0 + dx * 16, F_AROWS * 16, 128);
-                    const uint64_t al = umma_desc(a0 + 2 * F_AROWS * 16 + dx * 16, F_AROWS * 16, 128);
-                    const uint64_t bh = umma_desc(b0 + (dx * 2) * b_part, F_NPAD0 * 16, 128);
-                    const uint64_t bl = umma_desc(b0 + (dx * 2 + 1) * b_part, F_NPAD0 * 16, 128);
-                    tc_mma_bf16(d, ah, bh, idesc, dx > 0 ? 1u : 0u);
-                    if (!p.int_pixels) tc_mma_bf16(d, al, bh, idesc, 1u);
-                    tc_mma_bf16(d, ah, bl, idesc, 1u);
+                    const uint32_t ah = a0 + (uint32_t)dx, al = a0 + 2 * F_AROWS + (uint32_t)dx;
+                    const uint32_t bh = b_lo0 + (uint32_t)(dx * 2) * b_part, bl = b_lo0 + (uint32_t)(dx * 2 + 1) * b_part;
+                    tc_mma_bf16_elect(d, ah, bh, UMMA_DESC_HI, idesc, dx > 0 ? 1u : 0u);
+                    if (two_parts) tc_mma_bf16_elect(d, al, bh, UMMA_DESC_HI, idesc, 1u);
+                    tc_mma_bf16_elect(d, ah, bl, UMMA_DESC_HI, idesc, 1u);
                 }
-                tc_commit(&acc0_full[slot]);
-                tc_commit(&a_free[buf]);
             }
+            tc_commit_elect(&acc0_full[slot]);
+            tc_commit_elect(&a_free[buf]);
         }
-    } else if (warp < F_MMA1_WARP0 + 2) {
-        // ================= MMA 1: row groups of this warp's parity, both 128-pixel tiles of a group =================
-        const int w = warp - F_MMA1_WARP0;
-        const uint32_t leader = elect_one() ? 1u : 0u;
-        uint32_t idesc[RS_R + 1];
-#pragma unroll
-        for (int k = 1; k <= RS_R; ++k) idesc[k] = umma_idesc_bf16(F_NP1 * k);
-        const uint32_t a_lbo = ((uint32_t)p.ring_plane >> 4) << 16;
-        const uint32_t w_lo = ((smem_u32(w1_sm) & 0x3FFFFu) >> 4) | ((uint32_t)(RS_R * F_NP1) << 16);   // LBO = 4 * 16 * 16 B
-        const uint32_t ring_lo = ((smem_u32(ring) & 0x3FFFFu) >> 4) | a_lbo;
-        for (int it = 0; it < n_it; ++it) {
-            const int B0 = it * p.NB;
-            for (int rg = w; rg < p.NG; rg += 2) {
-                const int j_lo = rg ? (4 * rg - 1) >> 3 : 0;
-                const int j_hi = min(p.NB - 1, (4 * rg + 4) >> 3);
-                f01_wait_count(&mid_cnt[(B0 + j_lo) % F_RB], (uint32_t)((B0 + j_lo) / F_RB + 1) * block_units);
-                f01_wait_count(&mid_cnt[(B0 + j_hi) % F_RB], (uint32_t)((B0 + j_hi) / F_RB + 1) * block_units);
-                fence_proxy_async();
-                uint32_t vrow[RS_R + 2];                    // ring position (16-byte units) of input row 4 rg - 1 + v, column 0
-#pragma unroll
-                for (int v = 0; v < RS_R + 2; ++v) {
-                    const int m = 4 * rg - 1 + v;
-                    const int rr = (m < 0 || m >= p.H) ? F_ZROW : ((B0 + (m >> 3)) % F_RB) * F_R0 + (m & 7);
-                    vrow[v] = (uint32_t)(rr * p.Wp);
-                }
-                for (int j = 0; j < p.JT; ++j) {
-                    const uint32_t tc1 = (uint32_t)((it * p.NG + rg) * p.JT + j);
-                    const uint32_t slot = tc1 & 3u, sph = (tc1 >> 2) & 1u;
-                    mbar_wait(&acc1_empty[slot], sph ^ 1u);
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + 2 * F_SLOT0 + slot * F_SLOT1;
-                    const uint32_t tile_lo = ring_lo + 128u * (uint32_t)j;
-#pragma unroll
-                    for (int i = 0; i < RS_R + 2; ++i) {
-                        constexpr int order[6] = {2, 0, 1, 3, 4, 5};
-                        const int v = order[i];
-                        const int zs = v < 2 ? 2 - v : 0;
-                        const int db = v > 2 ? v - 2 : 0;
-                        const int nb = v < 2 ? v + 1 : (v > 3 ? 6 - v : 3);
-#pragma unroll
-                        for (int dx = 0; dx < 3; ++dx) {
-                            const bool first = (i == 0 && dx == 0);
-                            const uint32_t a_lo = tile_lo + vrow[v] + (uint32_t)dx;
-                            const uint32_t b_lo = w_lo + (uint32_t)(dx * 2) * (RS_R * F_NP1) + (uint32_t)zs * F_NP1;
-                            tc_mma_bf16_pred(d_tmem + (uint32_t)db * F_NP1, a_lo, b_lo, UMMA_DESC_HI, idesc[first ? RS_R : nb],
-                                             first ? 0u : 1u, leader);
-                        }
-                    }
-                    tc_commit_pred(&acc1_full[slot], leader);
-                }
-                // free the ring blocks for which this was the last row group of this warp's parity
-                for (int jb = j_lo; jb <= j_hi; ++jb)
-                    if (rg + 2 >= p.NG || rg > 2 * jb) tc_commit_pred(&mid_free[(B0 + jb) % F_RB], leader);
-            }
-        }
+    } else if (warp == F_MMA1_WARP0) {
+        f01_mma1<0>(p, smem, n_it, block_units, mid_cnt, acc1_full, acc1_empty, mid_free, tmem_base);
+    } else if (warp == F_MMA1_WARP0 + 1) {
+        f01_mma1<1>(p, smem, n_it, block_units, mid_cnt, acc1_full, acc1_empty, mid_free, tmem_base);
     } else if (warp >= F_DRAIN_WARP0 && warp < EPI_WARP0_F) {
         // ================= drain: TMEM -> ELU -> bf16 -> ring (lane = raster position, group g: rows g, g + DG, ..) =================
         const int q = warp & 3, grp = (warp - F_DRAIN_WARP0) >> 2;
@@ -282,16 +317,16 @@ __global__ void __launch_bounds__(32 * (F_DRAIN_WARP0 + 4 * (DG + EG)), 1) l01_f
             const unsigned g = gw0 + (unsigned)lane;
             const int rbl = (int)__umulhi(g, p.wp_magic);
             const int xp = (int)(g - (unsigned)rbl * (unsigned)p.Wp);
-            if (rb_first < p.NB) mbar_wait(&mid_free[(B0 + rb_first) % F_RB], (uint32_t)((((B0 + rb_first) / F_RB) & 1) ^ 1));
+            if (rb_first < p.NB) mbar_wait_tag(&mid_free[(B0 + rb_first) % F_RB], (uint32_t)((((B0 + rb_first) / F_RB) & 1) ^ 1), 5000000 + k);
             if (rb_last != rb_first && rb_last < p.NB)
-                mbar_wait(&mid_free[(B0 + rb_last) % F_RB], (uint32_t)((((B0 + rb_last) / F_RB) & 1) ^ 1));
-            mbar_wait(&acc0_full[slot], (uint32_t)((k >> 1) & 1));
+                mbar_wait_tag(&mid_free[(B0 + rb_last) % F_RB], (uint32_t)((((B0 + rb_last) / F_RB) & 1) ^ 1), 6000000 + k);
+            mbar_wait_tag(&acc0_full[slot], (uint32_t)((k >> 1) & 1), 7000000 + k);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)slot * F_SLOT0 + ((uint32_t)(q * 32) << 16);
             const bool col_real = xp >= 1 && xp <= p.W;
             uint8_t *dst = ring + ((size_t)(((B0 + rbl) % F_RB) * F_R0) * p.Wp + xp) * 16;
 #pragma unroll 1
-            for (int r = grp; r < F_R0; r += DG) {
+            for (int r = grp; r < ((p.dbg & 4) ? 0 : F_R0); r += DG) {
                 float v[12];
                 tmem_ld12(taddr + (uint32_t)(r * F_C0), v);
                 uint32_t pk[6];
@@ -322,15 +357,18 @@ __global__ void __launch_bounds__(32 * (F_DRAIN_WARP0 + 4 * (DG + EG)), 1) l01_f
         // ================= epilogue: TMEM -> 2x2 max -> bias + ELU -> bf16 -> global =================
         const int q = warp & 3, grp = (warp - EPI_WARP0_F) >> 2;
         const int odd = lane & 1;
-        const int total1 = n_it * p.NG * p.JT;
+        const int w = grp >> 1;                                   // the MMA-1 warp whose tiles this group drains
+        const int ngw = (p.NG - w + 1) / 2;                       // row groups per sample of that warp
+        const int total1 = n_it * ngw * p.JT;                     // its tiles
         const int n_groups16 = (p.cout1 + 3) >> 2;
         const int nchr = (p.cout1 + 7) >> 3;
-        for (int tc1 = grp; tc1 < total1; tc1 += EG) {
-            const uint32_t slot = (uint32_t)tc1 & 3u, sph = ((uint32_t)tc1 >> 2) & 1u;
-            const int G = tc1 / p.JT, j = tc1 - G * p.JT;
-            const int it = G / p.NG, rg = G - it * p.NG;
+        const uint32_t slot = (uint32_t)grp;
+        for (int u = grp & 1; u < total1; u += 2) {
+            const uint32_t sph = ((uint32_t)u >> 1) & 1u;
+            const int G = u / p.JT, j = u - G * p.JT;
+            const int it = G / ngw, rg = w + 2 * (G - it * ngw);
             const long long n = (long long)blockIdx.x + (long long)it * gridDim.x;
-            mbar_wait(&acc1_full[slot], sph);
+            mbar_wait_tag(&acc1_full[slot], sph, 8000000 + u);
             tc_fence_after();
             const int c = 1 + 128 * j + q * 32 + lane;            // padded column of this lane
             const bool valid = c <= p.W;
@@ -340,7 +378,7 @@ __global__ void __launch_bounds__(32 * (F_DRAIN_WARP0 + 4 * (DG + EG)), 1) l01_f
             // the even lane finishes pooled row 0, the odd lane pooled row 1
             const int yo = 2 * rg + odd;
             const long long opos = ((long long)(yo + 1) * p.Wpo + ((c - 1) >> 1) + 1) * 16;
-            for (int h = 0; h < nchr; ++h) {
+            for (int h = 0; h < ((p.dbg & 1) ? 0 : nchr); ++h) {
                 float v[32];
                 tmem_ld8x4(taddr + (uint32_t)(h * 8), (uint32_t)F_NP1, v);
                 float m[8];

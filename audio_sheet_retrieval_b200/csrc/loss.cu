@@ -122,10 +122,11 @@ int asr_contrastive_loss(const float *lv1_dev, const float *lv2_dev, int64_t n, 
     ASR_CHECK_ARG(n >= 2 && n <= 8192, "batch size must be in [2, 8192]");
     const double denom = (double)n * (double)(n - 1);
     const size_t smem = (size_t)5 * n * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[ASR_MAX_DEVICES] = {false};     // cudaFuncSetAttribute is per device
+    const int attr_dev = std::max(0, std::min(current_device(), ASR_MAX_DEVICES - 1));
+    if (!attr_done[attr_dev]) {
         ASR_CUDA(cudaFuncSetAttribute(contrastive_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * 8192 * 4));
-        attr_done = true;
+        attr_done[attr_dev] = true;
     }
     contrastive_rows_kernel<<<(unsigned)n, LOSS_THREADS, smem, (cudaStream_t)stream>>>(
         lv1_dev, lv2_dev, (int)n, gamma, symmetric ? 1 : 0, (float)((double)weight / denom), scratch_dev, grad1_dev, grad2_dev);

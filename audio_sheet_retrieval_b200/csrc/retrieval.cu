@@ -305,7 +305,11 @@ topk_stream_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int t
 template <int MG_WARPS>
 __global__ void __launch_bounds__(MG_WARPS * 32)
 topk_merge_kernel(const float *__restrict__ in_s, const uint32_t *__restrict__ in_i32, const int64_t *__restrict__ in_i64,
-                  int64_t idx_base, int n_lists, int k, float *__restrict__ out_s, int64_t *__restrict__ out_i) {
+                  int64_t idx_base, int n_lists, int k, float *__restrict__ out_s, int64_t *__restrict__ out_i,
+                  int64_t q_stride, int64_t list_stride_s, int64_t list_stride_i) {
+    // element (query qi, list l, position pos) sits at qi * q_stride + l * list_stride + pos: (nq, n_lists, k) arrays
+    // have q_stride = n_lists * k, list_stride = k; the rank-major result of an all-gather has q_stride = k and
+    // list_stride = one rank's chunk (scores and indices may have different chunk strides)
     extern __shared__ __align__(16) uint8_t mg_raw[];
     // [warp][2][k] int64 indices, then [warp][2][k] float scores
     int64_t *li_base = reinterpret_cast<int64_t *>(mg_raw);
@@ -315,7 +319,7 @@ topk_merge_kernel(const float *__restrict__ in_s, const uint32_t *__restrict__ i
     __shared__ int wlen[MG_WARPS], wcur[MG_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t qi = blockIdx.x;
-    const size_t base = (size_t)qi * n_lists * k;
+    const size_t base = (size_t)qi * q_stride;
     int len = 0, cur = 0;
     float thr_s = -CUDART_INF_F;
     int64_t thr_i = INT64_MAX;
@@ -341,14 +345,13 @@ topk_merge_kernel(const float *__restrict__ in_s, const uint32_t *__restrict__ i
         int64_t ci = INT64_MAX;
         if (alive) {
             int pos = c / my_lists, l = warp + (c % my_lists) * MG_WARPS;
-            size_t o = base + (size_t)l * k + pos;
-            cs = in_s[o];
+            cs = in_s[base + (size_t)l * list_stride_s + pos];
             if (in_i32) {
-                uint32_t r = in_i32[o];
+                uint32_t r = in_i32[base + (size_t)l * list_stride_i + pos];
                 alive = r != 0xffffffffu;
                 ci = (int64_t)r + idx_base;
             } else {
-                ci = in_i64[o];
+                ci = in_i64[base + (size_t)l * list_stride_i + pos];
                 alive = ci >= 0;
             }
             if (!alive) ci = INT64_MAX;
@@ -493,8 +496,29 @@ static void launch_merge(const float *in_s, const uint32_t *in_i32, const int64_
         topk_merge_select_kernel<<<(unsigned)nq, MS_THREADS, 0, st>>>(in_s, in_i32, idx_base, n_lists * k, k, out_s, out_i);
     } else {
         const size_t smem = (size_t)4 * 2 * k * (sizeof(int64_t) + sizeof(float));
-        topk_merge_kernel<4><<<(unsigned)nq, 4 * 32, smem, st>>>(in_s, in_i32, in_i64, idx_base, n_lists, k, out_s, out_i);
+        topk_merge_kernel<4><<<(unsigned)nq, 4 * 32, smem, st>>>(in_s, in_i32, in_i64, idx_base, n_lists, k, out_s, out_i,
+                                                                 (int64_t)n_lists * k, k, k);
     }
+}
+
+// best correct item over the shards of an eval_retrieval query set: max score, ties to the smaller global index
+// (the torch.stack / max / where of a host-side merge, as one kernel).  ts_all / ti_all: list l of query i at
+// l * stride + i.
+__global__ void rank_target_merge_kernel(const float *__restrict__ ts_all, const int64_t *__restrict__ ti_all, int n_lists,
+                                         int64_t nq, int64_t stride_s, int64_t stride_i, float *__restrict__ ts,
+                                         int64_t *__restrict__ ti) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    float best = -CUDART_INF_F;
+    int64_t bi = -1;
+    for (int l = 0; l < n_lists; ++l) {
+        const float sc = ts_all[(size_t)l * stride_s + i];
+        const int64_t ix = ti_all[(size_t)l * stride_i + i];
+        if (ix < 0) continue;                          // this shard holds none of the query's correct items
+        if (bi < 0 || sc > best || (sc == best && ix < bi)) { best = sc; bi = ix; }
+    }
+    ts[i] = best;
+    ti[i] = bi;
 }
 
 // ---- rank of target ---------------------------------------------------------------
@@ -1033,13 +1057,18 @@ struct asr_db {
     const float *codes;
     int64_t n;
     int64_t idx_base;
-    CUtensorMap tmap;
-    void *scratch;          // TK_SCRATCH_BYTES: per-slice partial lists
+    int device;             // the handle is bound to the device that was current at create
+    int flags;
+    CUtensorMap tmap;       // over the caller's rows as they are
+    void *scratch;          // TK_SCRATCH_BYTES: per-slice partial lists + the work counter of the pre-filter
     int sms;
-    // tensor-core pre-filter: pinned-normalised copy of the DB (made lazily on first use) + its tensor map
+    // cosine queries stream rows normalised with the pinned definition: an owned copy (default), the caller's own
+    // rows normalised in place (ASR_DB_NORMALISE_IN_PLACE), or nothing (ASR_DB_NO_COSINE_COPY: rows are normalised
+    // in-kernel by the exact path).  Built at create; published only when complete.
+    const float *rows_n = nullptr;
     float *codes_n = nullptr;
     CUtensorMap tmap_n;
-    float *qn = nullptr;    // normalised queries of the current call
+    float *qn = nullptr;    // normalised queries of the current call (pre-filter path), qn_cap rows, sized at create
     int64_t qn_cap = 0;
 };
 
@@ -1047,53 +1076,103 @@ using namespace asr;
 
 extern "C" {
 
-int asr_db_create(asr_db_t **out, const float *codes_dev, int64_t n, int64_t idx_base) {
+static int encode_rows_map(CUtensorMap *tm, const float *rows, int64_t n, int box_rows) {
+    cuuint64_t gdim[2] = {32, (cuuint64_t)n};
+    cuuint64_t gstr[1] = {128};
+    cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = get_encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(rows), gdim, gstr, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+        return ASR_ERR_CUDA;
+    }
+    return ASR_OK;
+}
+
+int asr_db_create_ex(asr_db_t **out, const float *codes_dev, int64_t n, int64_t idx_base, int flags, int64_t max_queries) {
     ASR_CHECK_ARG(out != nullptr, "out is NULL");
     int rc = ensure_device();
     if (rc) return rc;
     ASR_CHECK_ARG(codes_dev != nullptr && n > 0, "empty database");
     ASR_CHECK_ARG((reinterpret_cast<uintptr_t>(codes_dev) & 127) == 0, "codes_dev must be 128-byte aligned");
     ASR_CHECK_ARG(n < ((int64_t)1 << 31), "at most 2^31-1 rows per shard");
-    PFN_encodeTiled enc = get_encode_fn();
-    if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return ASR_ERR_CUDA; }
+    ASR_CHECK_ARG(!((flags & ASR_DB_NORMALISE_IN_PLACE) && (flags & ASR_DB_NO_COSINE_COPY)), "contradictory flags");
+    ASR_CHECK_ARG(max_queries >= 0, "max_queries < 0");
+    if (!get_encode_fn()) { set_error("cuTensorMapEncodeTiled not available from the driver"); return ASR_ERR_CUDA; }
+    static_assert(TK_ROWS == TC_ROWS, "one tensor-map box for both kernels");
     asr_db *db = new asr_db();
     db->codes = codes_dev;
     db->n = n;
     db->idx_base = idx_base;
     db->sms = sm_count();
-    cuuint64_t gdim[2] = {32, (cuuint64_t)n};
-    cuuint64_t gstr[1] = {128};
-    cuuint32_t box[2] = {32, (cuuint32_t)TK_ROWS};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&db->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(codes_dev), gdim, gstr, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        delete db;
-        set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
-        return ASR_ERR_CUDA;
-    }
+    db->device = current_device();
+    db->flags = flags;
+    db->scratch = nullptr;
+#define DB_FAIL(code)                 \
+    do {                              \
+        asr_db_destroy(db);           \
+        return (code);                \
+    } while (0)
+    if ((rc = encode_rows_map(&db->tmap, codes_dev, n, TK_ROWS))) DB_FAIL(rc);
     if (cudaMalloc(&db->scratch, TK_SCRATCH_BYTES) != cudaSuccess) {
-        delete db;
         set_error("cudaMalloc of the top-k scratch failed");
-        return ASR_ERR_CUDA;
+        DB_FAIL(ASR_ERR_CUDA);
     }
-    static bool attr_done = false;
-    if (!attr_done) {
-        ASR_CUDA(cudaFuncSetAttribute(topk_stream_kernel<1, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)sizeof(TkSmem<1, 2>) + 1024));
-        ASR_CUDA(cudaFuncSetAttribute(topk_stream_kernel<4, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)sizeof(TkSmem<4, 2>) + 1024));
-        ASR_CUDA(cudaFuncSetAttribute(topk_stream_kernel<16, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)sizeof(TkSmem<16, 3>) + 1024));
-        ASR_CUDA(cudaFuncSetAttribute(rank_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)sizeof(RkSmem) + 1024));
-        ASR_CUDA(cudaFuncSetAttribute(topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcSmem)));
-
-        attr_done = true;
+    static bool attr_done[ASR_MAX_DEVICES] = {false};     // cudaFuncSetAttribute is per device
+    const int attr_dev = std::max(0, std::min(db->device, ASR_MAX_DEVICES - 1));
+    if (!attr_done[attr_dev]) {
+        cudaError_t e1 = cudaFuncSetAttribute(topk_stream_kernel<1, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)sizeof(TkSmem<1, 2>) + 1024);
+        cudaError_t e2 = cudaFuncSetAttribute(topk_stream_kernel<4, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)sizeof(TkSmem<4, 2>) + 1024);
+        cudaError_t e3 = cudaFuncSetAttribute(topk_stream_kernel<16, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)sizeof(TkSmem<16, 3>) + 1024);
+        cudaError_t e4 = cudaFuncSetAttribute(rank_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)sizeof(RkSmem) + 1024);
+        cudaError_t e5 = cudaFuncSetAttribute(topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcSmem));
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess) {
+            set_error("asr_db_create: cudaFuncSetAttribute failed");
+            DB_FAIL(ASR_ERR_CUDA);
+        }
+        attr_done[attr_dev] = true;
     }
+    // rows normalised with the pinned definition (the same function the kernels apply per row, so results are
+    // bit-identical to normalising in-kernel): built here, synchronously, and published only when complete
+    if (!(flags & ASR_DB_NO_COSINE_COPY)) {
+        float *dst = nullptr;
+        if (flags & ASR_DB_NORMALISE_IN_PLACE) {
+            dst = const_cast<float *>(codes_dev);
+        } else if (cudaMalloc(&db->codes_n, (size_t)n * 128) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("asr_db_create: cudaMalloc of the normalised copy (" + std::to_string((size_t)n * 128) +
+                      " bytes) failed; ASR_DB_NORMALISE_IN_PLACE avoids the copy");
+            DB_FAIL(ASR_ERR_CUDA);
+        } else {
+            dst = db->codes_n;
+        }
+        normalise_rows_kernel<<<(unsigned)((n + 255) / 256), 256>>>(codes_dev, n, dst);
+        count_launch();
+        if (cudaGetLastError() != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+            set_error("asr_db_create: normalising the rows failed");
+            DB_FAIL(ASR_ERR_CUDA);
+        }
+        if ((rc = encode_rows_map(&db->tmap_n, dst, n, TC_ROWS))) DB_FAIL(rc);
+        db->rows_n = dst;
+    }
+    db->qn_cap = std::max<int64_t>(max_queries, TC_QM);
+    if (cudaMalloc(&db->qn, (size_t)db->qn_cap * 128) != cudaSuccess) {
+        set_error("asr_db_create: cudaMalloc of the query workspace failed");
+        DB_FAIL(ASR_ERR_CUDA);
+    }
+#undef DB_FAIL
     *out = db;
     return ASR_OK;
+}
+
+int asr_db_create(asr_db_t **out, const float *codes_dev, int64_t n, int64_t idx_base) {
+    return asr_db_create_ex(out, codes_dev, n, idx_base, 0, 16384);
 }
 
 int asr_db_destroy(asr_db_t *db) {
@@ -1127,35 +1206,15 @@ static void plan_grid(const asr_db *db, int64_t nq, int qt, int ctas_per_sm, int
 
 static float *g_tc_dbg = nullptr;   // set by asr_debug_tc_scores
 
-// First cosine query of a DB: a copy of its rows normalised with the pinned definition (the same function
-// the kernels apply per row, so every later result is bit-identical) + its tensor map.  Halves the dependent
-// add chain per row of the streaming kernel and is the B operand of the tensor-core pre-filter.  The DB
-// contents must not change after asr_db_create.
-static int ensure_normalised_copy(asr_db *db, cudaStream_t st) {
-    if (db->codes_n) return ASR_OK;
-    ASR_CUDA(cudaMalloc(&db->codes_n, (size_t)db->n * 128));
-    normalise_rows_kernel<<<(unsigned)((db->n + 255) / 256), 256, 0, st>>>(db->codes, db->n, db->codes_n);
-    ASR_LAUNCH_CHECK();
-    cuuint64_t gdim[2] = {32, (cuuint64_t)db->n};
-    cuuint64_t gstr[1] = {128};
-    cuuint32_t box[2] = {32, (cuuint32_t)TC_ROWS};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = get_encode_fn()(&db->tmap_n, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, db->codes_n, gdim, gstr, box, estr,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (normalised copy) failed"); return ASR_ERR_CUDA; }
-    return ASR_OK;
-}
-
 static int topk_tc(asr_db *db, const float *q_dev, int64_t nq, int k, float *out_score_dev, int64_t *out_idx_dev,
                    cudaStream_t st) {
-    int rcn = ensure_normalised_copy(db, st);
-    if (rcn) return rcn;
-    if (db->qn_cap < nq) {
-        cudaFree(db->qn);
-        db->qn = nullptr;
-        ASR_CUDA(cudaMalloc(&db->qn, (size_t)nq * 128));
-        db->qn_cap = nq;
+    if (nq > db->qn_cap) {      // more queries than the workspace sized at create: pass over them in chunks (no allocation here)
+        for (int64_t q0 = 0; q0 < nq; q0 += db->qn_cap) {
+            const int64_t nqc = std::min<int64_t>(db->qn_cap, nq - q0);
+            int rcc = topk_tc(db, q_dev + q0 * 32, nqc, k, out_score_dev + q0 * k, out_idx_dev + q0 * k, st);
+            if (rcc) return rcc;
+        }
+        return ASR_OK;
     }
     normalise_rows_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(q_dev, nq, db->qn);
     ASR_LAUNCH_CHECK();
@@ -1206,15 +1265,16 @@ int asr_topk(asr_db_t *db, const float *q_dev, int64_t nq, int k, int normalise,
     // measured crossovers (k = 25): the exact QT=16 kernel wins up to ~24 queries, and for small problems
     // whatever the query count: exact ~ 0.05 ms + 7.3 ms per 1e9 scores, pre-filter ~ 1.15 ms + 0.55 ms per 1e9
     // (profiles/r1_configs_3_5.json: its work items are at least 128 tiles long) -> equal at 1.6e8 scores
+    ASR_CHECK_ARG(current_device() == db->device, "the handle belongs to another device (one handle per device)");
+    ASR_CHECK_ARG(normalise || !(db->flags & ASR_DB_NORMALISE_IN_PLACE),
+                  "the raw rows are gone: this DB was created with ASR_DB_NORMALISE_IN_PLACE");
     const bool want_tc = force ? (strcmp(force, "tc") == 0) : (nq > 24 && (double)nq * (double)db->n >= 1.6e8);
-    if (want_tc && normalise && k <= TC_KMAX) return topk_tc(db, q_dev, nq, k, out_score_dev, out_idx_dev, st);
-    // cosine queries stream the pinned-normalised copy (kernel flag bit 0: normalise queries, bit 1: normalise rows)
-    if (normalise) {
-        int rcn = ensure_normalised_copy(db, st);
-        if (rcn) return rcn;
-    }
-    const CUtensorMap &tm = normalise ? db->tmap_n : db->tmap;
-    const int nflag = normalise ? 1 : 0;
+    if (want_tc && normalise && k <= TC_KMAX && db->rows_n) return topk_tc(db, q_dev, nq, k, out_score_dev, out_idx_dev, st);
+    // cosine queries stream the pinned-normalised rows (kernel flag bit 0: normalise queries, bit 1: normalise rows
+    // in-kernel -- only for handles created without them)
+    const bool pre = normalise && db->rows_n;
+    const CUtensorMap &tm = pre ? db->tmap_n : db->tmap;
+    const int nflag = normalise ? (pre ? 1 : 3) : 0;
     const int qt = nq <= 2 ? 1 : (nq <= 8 ? 4 : 16);
     const int occ = qt == 1 ? 3 : (qt == 4 ? 2 : 1);
     int n_slices, tps, qg0;
@@ -1275,6 +1335,43 @@ int asr_topk_merge(const float *score_dev, const int64_t *idx_dev, int64_t nq, i
     return ASR_OK;
 }
 
+int asr_topk_merge_gathered(const void *gathered_dev, int64_t chunk_bytes, int64_t idx_offset_bytes, int64_t nq, int n_lists,
+                            int k, float *out_score_dev, int64_t *out_idx_dev, void *stream) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    ASR_CHECK_ARG(k >= 1 && k <= ASR_MAX_K && n_lists >= 1, "bad k / n_lists");
+    if (nq == 0) return ASR_OK;
+    ASR_CHECK_ARG(gathered_dev && out_score_dev && out_idx_dev, "NULL buffer");
+    ASR_CHECK_ARG(chunk_bytes % 8 == 0 && idx_offset_bytes % 8 == 0 && idx_offset_bytes >= nq * k * 4 &&
+                      chunk_bytes >= idx_offset_bytes + nq * k * 8,
+                  "chunk layout: [scores (nq,k) f32 | pad to 8 | indices (nq,k) i64], chunk_bytes % 8 == 0");
+    const uint8_t *g = reinterpret_cast<const uint8_t *>(gathered_dev);
+    const size_t smem = (size_t)4 * 2 * k * (sizeof(int64_t) + sizeof(float));
+    topk_merge_kernel<4><<<(unsigned)nq, 4 * 32, smem, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float *>(g), nullptr, reinterpret_cast<const int64_t *>(g + idx_offset_bytes), 0, n_lists, k,
+        out_score_dev, out_idx_dev, (int64_t)k, chunk_bytes / 4, chunk_bytes / 8);
+    ASR_LAUNCH_CHECK();
+    return ASR_OK;
+}
+
+int asr_rank_target_merge(const void *gathered_dev, int64_t chunk_bytes, int64_t idx_offset_bytes, int n_lists, int64_t nq,
+                          float *tscore_dev, int64_t *tidx_dev, void *stream) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    ASR_CHECK_ARG(n_lists >= 1, "n_lists < 1");
+    if (nq == 0) return ASR_OK;
+    ASR_CHECK_ARG(gathered_dev && tscore_dev && tidx_dev, "NULL buffer");
+    ASR_CHECK_ARG(chunk_bytes % 8 == 0 && idx_offset_bytes % 8 == 0 && idx_offset_bytes >= nq * 4 &&
+                      chunk_bytes >= idx_offset_bytes + nq * 8,
+                  "chunk layout: [scores (nq) f32 | pad to 8 | indices (nq) i64], chunk_bytes % 8 == 0");
+    const uint8_t *g = reinterpret_cast<const uint8_t *>(gathered_dev);
+    rank_target_merge_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float *>(g), reinterpret_cast<const int64_t *>(g + idx_offset_bytes), n_lists, nq,
+        chunk_bytes / 4, chunk_bytes / 8, tscore_dev, tidx_dev);
+    ASR_LAUNCH_CHECK();
+    return ASR_OK;
+}
+
 int asr_rank_of_target(asr_db_t *db, const float *q_dev, int64_t nq, int64_t q_base, int64_t kg, int64_t hg,
                        int normalise, int phase, float *tscore_dev, int64_t *tidx_dev, int64_t *better_dev,
                        void *stream) {
@@ -1282,6 +1379,8 @@ int asr_rank_of_target(asr_db_t *db, const float *q_dev, int64_t nq, int64_t q_b
     if (rc) return rc;
     ASR_CHECK_ARG(db != nullptr && q_dev && tscore_dev && tidx_dev, "NULL argument");
     ASR_CHECK_ARG(kg >= 1 && hg >= 1, "kg, hg must be >= 1");
+    ASR_CHECK_ARG(!(db->flags & ASR_DB_NORMALISE_IN_PLACE), "not available for ASR_DB_NORMALISE_IN_PLACE handles");
+    ASR_CHECK_ARG(current_device() == db->device, "the handle belongs to another device (one handle per device)");
     if (nq == 0) return ASR_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if (phase == 0) {
@@ -1311,10 +1410,11 @@ int asr_vote(const int64_t *cand_idx_dev, const int32_t *row_ids_dev, int64_t n_
     if (n_rec == 0) return ASR_OK;
     int p2 = 32;
     while (p2 < m) p2 <<= 1;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[ASR_MAX_DEVICES] = {false};     // cudaFuncSetAttribute is per device
+    const int attr_dev = std::max(0, std::min(current_device(), ASR_MAX_DEVICES - 1));
+    if (!attr_done[attr_dev]) {
         ASR_CUDA(cudaFuncSetAttribute(vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VOTE_MAX * 8));
-        attr_done = true;
+        attr_done[attr_dev] = true;
     }
     vote_kernel<<<n_rec, VOTE_THREADS, p2 * 8, (cudaStream_t)stream>>>(cand_idx_dev, row_ids_dev, n_rows, m, p2, top_k,
                                                                        out_ids_dev, out_counts_dev);

@@ -13,8 +13,12 @@
  *     cudaStream_t passed as void* (NULL = legacy default stream).  No call
  *     synchronises the host unless its name ends in `_host`.
  *   - opaque handles own only what they allocate at create time (weights,
- *     activation arena, per-CTA scratch) or on first use (the DB's normalised
- *     copy, host-entry staging buffers); nothing is allocated in steady state.
+ *     activation arena, scratch, the DB's normalised rows and query workspace);
+ *     the only first-use allocations are the staging buffers of the `_host`
+ *     entry and the layer-0 buffer of an encoder whose fusion is switched off.
+ *     Nothing is allocated in steady state.
+ *   - handles are bound to the device that was current at create and are not
+ *     thread-safe: one stream at a time per handle.
  *   - sm_100a only.  There is no CPU fallback: without a CUDA device every compute
  *     entry point fails with ASR_ERR_CUDA.
  */
@@ -129,9 +133,23 @@ double asr_encoder_flops_per_sample(const asr_encoder_t *enc);
 typedef struct asr_db asr_db_t;
 
 /* codes_dev: (n, 32) float32 row-major, 128-byte aligned, caller-owned, kept alive and NOT modified while the
- * handle exists: the first cosine query makes a device copy of the rows normalised with the pinned definition
- * (n * 128 bytes, owned by the handle) and every later query streams that copy.
- * idx_base: global index of row 0 (this shard's offset in a sharded DB). */
+ * handle exists.  idx_base: global index of row 0 (this shard's offset in a sharded DB).
+ * Everything the handle ever needs is allocated HERE (asr_topk / asr_rank_of_target never allocate):
+ *   - 64 MB of scratch for per-slice partial lists,
+ *   - a query workspace of max_queries rows (more queries per call are processed in chunks of that size),
+ *   - the rows normalised with the pinned definition, which cosine queries stream:
+ *       flags = 0                        an owned copy, n * 128 bytes (a 1e8-row DB: 12.8 GB + 12.8 GB)
+ *       ASR_DB_NORMALISE_IN_PLACE        the caller donates its buffer: rows are overwritten with their normalised
+ *                                        form, no second copy; only cosine (normalise != 0) queries afterwards
+ *       ASR_DB_NO_COSINE_COPY            nothing: cosine queries normalise rows in-kernel (exact kernel only,
+ *                                        the tensor-core pre-filter needs the normalised rows)
+ * The create call runs one kernel on the default stream and synchronises; the handle is bound to the current
+ * device.  One stream at a time per handle: its scratch is shared by consecutive calls (calls on the SAME stream
+ * serialise naturally; concurrent use from two streams needs two handles). */
+#define ASR_DB_NORMALISE_IN_PLACE 1
+#define ASR_DB_NO_COSINE_COPY 2
+int asr_db_create_ex(asr_db_t **out, const float *codes_dev, int64_t n, int64_t idx_base, int flags, int64_t max_queries);
+/* = asr_db_create_ex(out, codes_dev, n, idx_base, 0, 16384) */
 int asr_db_create(asr_db_t **out, const float *codes_dev, int64_t n, int64_t idx_base);
 int asr_db_destroy(asr_db_t *db);
 
@@ -146,6 +164,16 @@ int asr_debug_tc_scores(asr_db_t *db, const float *q_dev, int64_t nq, float *out
  * all-gather of per-GPU top-k. */
 int asr_topk_merge(const float *score_dev, const int64_t *idx_dev, int64_t nq, int n_lists, int k,
                    float *out_score_dev, int64_t *out_idx_dev, void *stream);
+/* The same merge reading the result of ONE all-gather directly.  Every rank lays its local result out as one chunk
+ * of chunk_bytes: [scores (nq,k) f32 | pad to 8 bytes | indices (nq,k) i64 at idx_offset_bytes] (asr_topk can write
+ * straight into such a chunk); gathered_dev holds n_lists chunks back to back (rank-major), no transpose needed. */
+int asr_topk_merge_gathered(const void *gathered_dev, int64_t chunk_bytes, int64_t idx_offset_bytes, int64_t nq,
+                            int n_lists, int k, float *out_score_dev, int64_t *out_idx_dev, void *stream);
+/* eval_retrieval over a sharded DB: after phase 0 of asr_rank_of_target every rank holds (tscore, tidx) of its
+ * shard's best correct item (-inf / -1 if it owns none); all-gather chunks [tscore (nq) f32 | pad | tidx (nq) i64]
+ * and this picks, per query, the best score (ties: smaller global index) -- the value every rank needs for phase 1. */
+int asr_rank_target_merge(const void *gathered_dev, int64_t chunk_bytes, int64_t idx_offset_bytes, int n_lists,
+                          int64_t nq, float *tscore_dev, int64_t *tidx_dev, void *stream);
 /* eval_retrieval ranking: query i's correct items are DB rows j with j/kg == (q_base+i)/hg
  * (global j).  tscore_dev (nq) in/out: pass 1 (phase=0) computes the best correct score/index
  * on the shard that owns them (others leave -inf); after a max-allreduce, phase=1 adds to
@@ -169,8 +197,18 @@ int asr_vote(const int64_t *cand_idx_dev, const int32_t *row_ids_dev, int64_t n_
  * shift1/shift2 (32, fp32, device, may be NULL) are subtracted from every row first. */
 int asr_cca_accumulate(const float *h1_dev, const float *h2_dev, int64_t n, const float *shift1_dev,
                        const float *shift2_dev, double *sums_dev, void *stream);
+/* Counted layout for row-sharded fits: sums_dev has ASR_CCA_NSUMS + 1 entries and the call also adds n to the
+ * last one, so ONE all-reduce of the buffer carries everything (asr/refine_cca.py:94-101 sharded over ranks);
+ * asr_cca_solve then reads the total row count from the device (n_total = ASR_CCA_COUNT_ON_DEVICE) -- no host
+ * synchronisation between accumulation, all-reduce and solve.  Use the same shift (or NULL) on every rank:
+ * the solve removes it exactly (raw-moment correction in fp64), so no pass over the data for the means is needed. */
+#define ASR_CCA_COUNT_ON_DEVICE (-1)
+int asr_cca_accumulate_counted(const float *h1_dev, const float *h2_dev, int64_t n, const float *shift1_dev,
+                               const float *shift2_dev, double *sums_dev, void *stream);
 /* 'svd' fit from (all-reduced) sums.  mode 0 = CCA.fit('svd') (sigma descending);
- * mode 1 = CCALayer train forward (eigh of TT'+rT, ascending, sign fix).
+ * mode 1 = CCALayer train forward (eigh of TT'+rT, ascending, sign fix) from BATCH statistics only, i.e. the
+ * reference layer with ALPHA = 1.0 (asr/models/mutopia_ccal_cont.py:48; layers/cca.py:96-141 blends batch and
+ * running statistics with alpha -- other alphas are not provided).
  * Outputs (device): m1,m2 (32) U,V (32x32 row-major) as fp64, sigma (32) fp64. */
 int asr_cca_solve(const double *sums_dev, int64_t n_total, const float *shift1_dev, const float *shift2_dev,
                   double r1, double r2, double rT, int mode, double *m1_dev, double *m2_dev,
