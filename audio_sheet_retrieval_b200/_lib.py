@@ -19,6 +19,8 @@ IN_F32, IN_U8 = 0, 1
 PREP_NONE, PREP_SCALE, PREP_SCALE_HALF = 0, 1, 2
 PATH_TCGEN05, PATH_FP32 = 0, 1
 CCA_NSUMS = 3136
+CCA_COUNT_ON_DEVICE = -1
+DB_NORMALISE_IN_PLACE, DB_NO_COSINE_COPY = 1, 2
 
 
 class AsrError(RuntimeError):
@@ -79,7 +81,11 @@ def _load():
     lib.asr_encoder_flops_per_sample.argtypes = [c_void_p]
     lib.asr_encoder_flops_per_sample.restype = c_double
     lib.asr_db_create.argtypes = [POINTER(c_void_p), c_void_p, c_int64, c_int64]
+    lib.asr_db_create_ex.argtypes = [POINTER(c_void_p), c_void_p, c_int64, c_int64, c_int, c_int64]
     lib.asr_db_destroy.argtypes = [c_void_p]
+    lib.asr_topk_merge_gathered.argtypes = [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]
+    lib.asr_rank_target_merge.argtypes = [c_void_p, c_int64, c_int64, c_int, c_int64, c_void_p, c_void_p, c_void_p]
+    lib.asr_cca_accumulate_counted.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.asr_topk.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]
     lib.asr_debug_tc_scores.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
     lib.asr_debug_tc_scores.restype = c_int
@@ -97,7 +103,8 @@ def _load():
                  "asr_encoder_embed_host", "asr_encoder_debug_activation", "asr_encoder_set_timing",
                  "asr_encoder_get_timing", "asr_db_create", "asr_db_destroy",
                  "asr_topk", "asr_topk_merge", "asr_rank_of_target", "asr_vote", "asr_cca_accumulate",
-                 "asr_cca_solve"):
+                 "asr_cca_solve", "asr_db_create_ex", "asr_topk_merge_gathered", "asr_rank_target_merge",
+                 "asr_cca_accumulate_counted"):
         getattr(lib, name).restype = c_int
     return lib
 

@@ -23,14 +23,35 @@ def _as_codes(x, device):
         raise ValueError("codes must be (n, d) with 1 <= d <= 32, got %s" % (tuple(t.shape),))
     t = t.to(device, non_blocking=True)
     if t.shape[1] < _lib.DIM:
-        t = torch.nn.functional.pad(t, (0, _lib.DIM - t.shape[1]))
+        full = torch.zeros((t.shape[0], _lib.DIM), dtype=torch.float32, device=device)
+        full[:, :t.shape[1]].copy_(t)
+        t = full
     return t.contiguous()
+
+
+def chunk_layout(nq, k):
+    """Byte layout of one rank's result in an all-gather: [scores (nq,k) f32 | pad to 8 | indices (nq,k) i64].
+    -> (chunk_bytes, idx_offset_bytes); the layout asr_topk_merge_gathered / asr_rank_target_merge read."""
+    idx_off = (nq * k * 4 + 7) // 8 * 8
+    return idx_off + nq * k * 8, idx_off
+
+
+def chunk_views(buf, nq, k, rank=0):
+    """(scores (nq,k) f32, indices (nq,k) i64) views of chunk `rank` of a uint8 buffer laid out by chunk_layout."""
+    chunk, idx_off = chunk_layout(nq, k)
+    c = buf[rank * chunk:(rank + 1) * chunk]
+    return c[:nq * k * 4].view(torch.float32).view(nq, k), c[idx_off:idx_off + nq * k * 8].view(torch.int64).view(nq, k)
 
 
 class EmbeddingDB(object):
     """One shard of an embedding DB resident in HBM: rows [idx_base, idx_base + n)."""
 
-    def __init__(self, codes, ids=None, idx_base=0, device=None):
+    def __init__(self, codes, ids=None, idx_base=0, device=None, normalise_in_place=False, cosine_copy=True,
+                 max_queries=16384):
+        """normalise_in_place: donate `codes` (a CUDA tensor) -- its rows are overwritten with their pinned-normalised
+        form and streamed from there, no second copy (a 1e8-row DB stays at 12.8 GB); cosine queries only.
+        cosine_copy=False: no normalised rows at all (cosine queries normalise in-kernel, exact kernel only).
+        max_queries: size of the query workspace (larger calls are processed in chunks)."""
         if not torch.cuda.is_available():
             raise _lib.AsrError("no CUDA device: the retrieval path has no CPU fallback")
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
@@ -49,8 +70,10 @@ class EmbeddingDB(object):
             self.ids = torch.as_tensor(np.asarray(ids)).to(torch.int32).to(self.device).contiguous()
             if self.ids.numel() != self.n:
                 raise ValueError("ids must have one entry per DB row")
+        flags = (_lib.DB_NORMALISE_IN_PLACE if normalise_in_place else 0) | (0 if cosine_copy else _lib.DB_NO_COSINE_COPY)
         h = ctypes.c_void_p()
-        _lib.check(_lib.lib.asr_db_create(ctypes.byref(h), _lib.dptr(self.codes), self.n, self.idx_base))
+        _lib.check(_lib.lib.asr_db_create_ex(ctypes.byref(h), _lib.dptr(self.codes), self.n, self.idx_base, flags,
+                                             int(max_queries)))
         self.handle = h
 
     def close(self):
@@ -86,8 +109,8 @@ class EmbeddingDB(object):
 
     # -- eval_retrieval ranks ----------------------------------------------------------------
     def ranks_device(self, q, kg=1, hg=1, q_base=0, normalise=True, group=None):
-        """Rank (1-based) of the best correct item per query + its score.  With a process group
-        the DB is sharded over the ranks (queries replicated)."""
+        """Per query: how many DB rows rank BEFORE its best correct item (rank = count + 1) and that item's
+        score.  With a process group the DB is sharded over the ranks (queries replicated)."""
         nq = int(q.shape[0])
         ts = torch.empty(nq, dtype=torch.float32, device=self.device)
         ti = torch.empty(nq, dtype=torch.int64, device=self.device)
@@ -96,23 +119,22 @@ class EmbeddingDB(object):
         args = (self.handle, _lib.dptr(q), nq, int(q_base), int(kg), int(hg), int(bool(normalise)))
         _lib.check(_lib.lib.asr_rank_of_target(*args, 0, _lib.dptr(ts), _lib.dptr(ti), _lib.dptr(better), st))
         if group is not None:
+            # one all-gather of [tscore | tidx] chunks, then one kernel picks the best correct item over the shards
             import torch.distributed as dist
             ws = dist.get_world_size(group)
-            all_s = [torch.empty_like(ts) for _ in range(ws)]
-            all_i = [torch.empty_like(ti) for _ in range(ws)]
-            dist.all_gather(all_s, ts, group=group)
-            dist.all_gather(all_i, ti, group=group)
-            S, I = torch.stack(all_s), torch.stack(all_i)
-            I = torch.where(I < 0, torch.full_like(I, 2 ** 62), I)
-            best = S.max(dim=0).values
-            cand = torch.where(S == best, I, torch.full_like(I, 2 ** 62))
-            ti = cand.min(dim=0).values.contiguous()
-            ts = best.contiguous()
+            chunk, idx_off = chunk_layout(nq, 1)
+            mine = torch.empty(chunk, dtype=torch.uint8, device=self.device)
+            cs, ci = chunk_views(mine, nq, 1)
+            cs.view(-1).copy_(ts); ci.view(-1).copy_(ti)
+            gathered = torch.empty(ws * chunk, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(gathered, mine, group=group)
+            _lib.check(_lib.lib.asr_rank_target_merge(_lib.dptr(gathered), chunk, idx_off, ws, nq, _lib.dptr(ts),
+                                                      _lib.dptr(ti), st))
         _lib.check(_lib.lib.asr_rank_of_target(*args, 1, _lib.dptr(ts), _lib.dptr(ti), _lib.dptr(better), st))
         if group is not None:
             import torch.distributed as dist
             dist.all_reduce(better, group=group)
-        return better + 1, ts
+        return better, ts
 
     # -- vote -------------------------------------------------------------------------------
     def vote_device(self, cand_idx, top_k):
@@ -134,6 +156,17 @@ def merge_topk_device(scores, idx, n_lists, k):
     out_i = torch.empty((nq, k), dtype=torch.int64, device=scores.device)
     _lib.check(_lib.lib.asr_topk_merge(_lib.dptr(scores.contiguous()), _lib.dptr(idx.contiguous()), nq, int(n_lists),
                                        int(k), _lib.dptr(out_s), _lib.dptr(out_i), _lib.stream_ptr()))
+    return out_s, out_i
+
+
+def merge_gathered_topk_device(gathered, nq, n_lists, k):
+    """The result of ONE all-gather of chunk_layout chunks (rank-major, as all_gather_into_tensor leaves it)
+    -> merged (nq,k) lists; the kernel reads the chunks where they are (no transpose copies)."""
+    chunk, idx_off = chunk_layout(nq, k)
+    out_s = torch.empty((nq, k), dtype=torch.float32, device=gathered.device)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=gathered.device)
+    _lib.check(_lib.lib.asr_topk_merge_gathered(_lib.dptr(gathered), chunk, idx_off, nq, int(n_lists), int(k),
+                                                _lib.dptr(out_s), _lib.dptr(out_i), _lib.stream_ptr()))
     return out_s, out_i
 
 

@@ -1,9 +1,10 @@
 """CCA(method='svd') with the reference's interface (audio_sheet_retrieval/utils/cca.py:6-53,
 199-211, 432-444): fit -> canonical correlations; attributes m1, m2, U, V; transform_V1/V2.
 
-fit runs on the device: a fused Gram kernel accumulates the sufficient statistics in fp64 (the
-reference uses an fp32 sgemm on centred data), optionally all-reduced over a process group for
-row-sharded inputs, then a single-CTA Jacobi kernel computes S11^-1/2, S22^-1/2, T and its SVD.
+fit runs on the device: a fused Gram kernel accumulates the sufficient statistics (column sums, second
+moments, row count) in fp64 in one pass (the reference centres, then uses an fp32 sgemm), all-reduced as
+ONE buffer over a process group for row-sharded inputs, then a single-CTA Jacobi kernel centres the
+moments and computes S11^-1/2, S22^-1/2, T and its SVD.  torch only holds the buffers.
 Only method 'svd' is supported: it is the only one the reference ever selects
 (refine_cca.py:100, utils/train_dcca_pool.py:250).
 """
@@ -54,23 +55,16 @@ class CCA(object):
         H2 = torch.as_tensor(H2).to(dev, torch.float32).contiguous()
         if H1.shape[1] != 32 or H2.shape[1] != 32 or H1.shape[0] != H2.shape[0]:
             raise ValueError("expected two (m,32) arrays")
-        n = torch.tensor([H1.shape[0]], dtype=torch.float64, device=dev)
-        # pass 1: means (as the reference, which centres before its sgemm)
-        s0 = torch.zeros(64, dtype=torch.float64, device=dev)
-        s0[:32] = H1.sum(dim=0, dtype=torch.float64)
-        s0[32:] = H2.sum(dim=0, dtype=torch.float64)
+        # One pass, one collective: Gram + column sums + row count of this rank's rows in fp64 (products of fp32 values
+        # are exact in fp64), all-reduced as ONE buffer; the solve centres the moments exactly (raw-moment correction
+        # in fp64) and reads the total row count from the device -- no pass for the means, no host synchronisation.
+        sums = torch.zeros(_lib.CCA_NSUMS + 1, dtype=torch.float64, device=dev)
+        _lib.check(_lib.lib.asr_cca_accumulate_counted(_lib.dptr(H1), _lib.dptr(H2), int(H1.shape[0]), None, None,
+                                                       _lib.dptr(sums), _lib.stream_ptr()))
         if group is not None:
             import torch.distributed as dist
-            dist.all_reduce(n, group=group)
-            dist.all_reduce(s0, group=group)
-        n_total = int(n.item())
-        shift = (s0 / n_total).to(torch.float32)
-        sh1, sh2 = shift[:32].contiguous(), shift[32:].contiguous()
-        # pass 2: centred second moments (fp64 accumulation)
-        sums = cca_sums_device(H1, H2, sh1, sh2)
-        if group is not None:
             dist.all_reduce(sums, group=group)
-        m1, m2, U, V, sig = cca_solve_device(sums, n_total, sh1, sh2, self.r1, self.r2, self.rT, mode=0)
+        m1, m2, U, V, sig = cca_solve_device(sums, _lib.CCA_COUNT_ON_DEVICE, None, None, self.r1, self.r2, self.rT, mode=0)
         self.m1, self.m2 = m1.cpu().numpy(), m2.cpu().numpy()
         self.U, self.V = U.cpu().numpy(), V.cpu().numpy()
         coeffs = sig.cpu().numpy()

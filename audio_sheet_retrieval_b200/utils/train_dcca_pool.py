@@ -14,22 +14,31 @@ from ..retrieval import EmbeddingDB, _as_codes
 
 
 def retrieval_ranks(lv1_cca, lv2_cca, group=None):
-    """-> (ranks (n_v1,) int64, target cosine scores (n_v1,) float32) as NumPy arrays."""
+    """-> (ranks (n_v1,) int64, target cosine scores (n_v1,) float32) as NumPy arrays.
+
+    With a process group every rank passes the same arrays and searches only its contiguous shard of the
+    view-2 rows: the best correct item is agreed on with one all-gather + asr_rank_target_merge, the
+    per-shard "ranked before it" counts are summed with one all-reduce."""
     n_v1, n_v2 = lv1_cca.shape[0], lv2_cca.shape[0]
     k = n_v2 // n_v1 if n_v2 > n_v1 else 1      # :35-36 (Python-2 integer division)
     h = n_v1 // n_v2 if n_v1 > n_v2 else 1
-    db = EmbeddingDB(lv2_cca)
+    lo, hi = 0, n_v2
+    if group is not None:
+        import torch.distributed as dist
+        from ..dist import shard_bounds
+        lo, hi = shard_bounds(n_v2, dist.get_rank(group), dist.get_world_size(group))
+    db = EmbeddingDB(lv2_cca[lo:hi], idx_base=lo)
     try:
         q = _as_codes(lv1_cca, db.device)
-        ranks, ts = db.ranks_device(q, kg=k, hg=h, normalise=True, group=group)
-        return ranks.cpu().numpy(), ts.cpu().numpy()
+        before, ts = db.ranks_device(q, kg=k, hg=h, normalise=True, group=group)
+        return before.cpu().numpy() + 1, ts.cpu().numpy()
     finally:
         db.close()
 
 
-def eval_retrieval(lv1_cca, lv2_cca):
+def eval_retrieval(lv1_cca, lv2_cca, group=None):
     """Compute retrieval eval measures -> (mean_rank, median_rank, mean_dist, hit_rates, map)."""
-    ranks, ts = retrieval_ranks(np.asarray(lv1_cca), np.asarray(lv2_cca))
+    ranks, ts = retrieval_ranks(np.asarray(lv1_cca), np.asarray(lv2_cca), group=group)
     hit_rates = {1: 0, 5: 0, 10: 0, 25: 0}
     for key in hit_rates:
         hit_rates[key] = int((ranks <= key).sum())

@@ -87,3 +87,27 @@ def test_layer_train_forward_mode():
         s = np.sign((out[:, j] * ref["out"][:, j]).sum())
         np.testing.assert_allclose(out[:, j] * s, ref["out"][:, j], atol=1e-5)
         np.testing.assert_allclose(out[:, 32 + j] * s, ref["out"][:, 32 + j], atol=1e-5)
+
+
+def test_counted_layout_sharded_equals_fit():
+    """The one-buffer layout of a row-sharded fit: four shards accumulate [sums | row count] into 3137 doubles (what
+    the single all-reduce carries), the solve reads the count from the device -- equal to CCA.fit on all rows."""
+    import torch
+    from audio_sheet_retrieval_b200 import _lib
+    from audio_sheet_retrieval_b200.utils.cca import CCA, cca_solve_device
+    H1, H2 = occa.synth_latents(5003, seed=6)
+    h1, h2 = torch.as_tensor(H1).cuda(), torch.as_tensor(H2).cuda()
+    total = torch.zeros(_lib.CCA_NSUMS + 1, dtype=torch.float64, device="cuda")
+    for r in range(4):
+        lo, hi = 5003 * r // 4, 5003 * (r + 1) // 4
+        part = torch.zeros_like(total)
+        _lib.check(_lib.lib.asr_cca_accumulate_counted(_lib.dptr(h1[lo:hi].contiguous()), _lib.dptr(h2[lo:hi].contiguous()),
+                                                       hi - lo, None, None, _lib.dptr(part), _lib.stream_ptr()))
+        assert part[-1].item() == hi - lo
+        total += part                                          # stands for the all-reduce
+    m1, m2, U, V, sig = cca_solve_device(total, _lib.CCA_COUNT_ON_DEVICE)
+    c = CCA()
+    sig_ref = c.fit(H1, H2)
+    np.testing.assert_allclose(sig.cpu().numpy(), sig_ref, atol=1e-12)
+    np.testing.assert_allclose(U.cpu().numpy(), c.U, atol=1e-9 * np.abs(c.U).max())
+    np.testing.assert_allclose(m1.cpu().numpy(), H1.astype(np.float64).mean(0), atol=1e-12)

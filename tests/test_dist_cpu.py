@@ -1,5 +1,6 @@
-"""world_size-2 gloo tests of the multi-GPU host logic (sharding, gather layout, merge order).
-The per-shard kernels are replaced by the oracle here; the GPU versions are in test_retrieval_gpu."""
+"""world_size-2 gloo tests of the multi-GPU host logic (sharding, the single-buffer chunk layout of the
+all-gathers, merge order, the counted CCA all-reduce).  The per-shard kernels are replaced by the oracle here;
+the same code paths run on NCCL with the real kernels in tests/test_multigpu_gpu.py."""
 import os
 import socket
 
@@ -24,6 +25,7 @@ def _worker(rank, world, port, q):
                       LOCAL_RANK=str(rank))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from audio_sheet_retrieval_b200.dist import gather_topk, shard_bounds
+    from audio_sheet_retrieval_b200.retrieval import chunk_layout, chunk_views
     rng = np.random.RandomState(0)
     D = rng.normal(size=(1001, 32)).astype(np.float32)
     D[900] = D[3]                                           # tie across shards -> lower global index wins
@@ -31,18 +33,38 @@ def _worker(rank, world, port, q):
     k = 5
     lo, hi = shard_bounds(len(D), rank, world)
     s, i = search.pinned_topk(Q, D[lo:hi], k, idx_base=lo)
-    gs, gi = gather_topk(torch.as_tensor(s), torch.as_tensor(i))
-    assert gs.shape == (7, world * k)
-    ms, mi = search.merge_topk([gs.numpy()], [gi.numpy()], k)
+    gathered = gather_topk(torch.as_tensor(s), torch.as_tensor(i))
+    chunk, idx_off = chunk_layout(7, k)
+    ok = gathered.dtype == torch.uint8 and gathered.numel() == world * chunk and chunk % 8 == 0 and idx_off % 8 == 0
+    lists = [chunk_views(gathered, 7, k, r) for r in range(world)]
+    ok = ok and bool((lists[rank][0].numpy() == s).all() and (lists[rank][1].numpy() == i).all())
+    gs = np.concatenate([l[0].numpy() for l in lists], axis=1)
+    gi = np.concatenate([l[1].numpy() for l in lists], axis=1)
+    ms, mi = search.merge_topk([gs], [gi], k)
     s_ref, i_ref = search.pinned_topk(Q, D, k)
-    ok = bool((mi == i_ref).all() and (ms == s_ref).all())
-    # CCA sums all-reduce: sum of per-shard second moments == global
+    ok = ok and bool((mi == i_ref).all() and (ms == s_ref).all())
+    # rank-of-target exchange: chunks [tscore (nq) | pad | tidx (nq)] with k = 1; odd nq exercises the padding
+    nq = 7
+    ts = np.full(nq, -np.inf, np.float32)
+    ti = np.full(nq, -1, np.int64)
+    for j in range(nq):
+        if (j % world) == rank:                             # this shard owns query j's correct item
+            ts[j], ti[j] = 0.25 * j, 100 * rank + j
+    mine = torch.empty(chunk_layout(nq, 1)[0], dtype=torch.uint8)
+    cs, ci = chunk_views(mine, nq, 1)
+    cs.view(-1).copy_(torch.as_tensor(ts)); ci.view(-1).copy_(torch.as_tensor(ti))
+    g2 = torch.empty(world * mine.numel(), dtype=torch.uint8)
+    dist.all_gather_into_tensor(g2, mine)
+    best = [max(((chunk_views(g2, nq, 1, r)[0][j, 0].item(), -chunk_views(g2, nq, 1, r)[1][j, 0].item())
+                 for r in range(world) if chunk_views(g2, nq, 1, r)[1][j, 0].item() >= 0)) for j in range(nq)]
+    ok = ok and all(best[j] == (0.25 * j, -(100 * (j % world) + j)) for j in range(nq))
+    # counted CCA sums: [second moments | row count] all-reduced as one buffer == global
     H = rng.normal(size=(501, 4))
     lo2, hi2 = shard_bounds(len(H), rank, world)
-    part = torch.as_tensor(H[lo2:hi2].T @ H[lo2:hi2])
+    part = torch.cat([torch.as_tensor(H[lo2:hi2].T @ H[lo2:hi2]).view(-1), torch.tensor([float(hi2 - lo2)], dtype=torch.float64)])
     dist.all_reduce(part)
-    ok = ok and bool(np.allclose(part.numpy(), H.T @ H))
-    q.put((rank, ok))
+    ok = ok and bool(np.allclose(part[:-1].numpy().reshape(4, 4), H.T @ H)) and part[-1].item() == 501.0
+    q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
 
@@ -57,6 +79,18 @@ def test_sharded_topk_gather_merge_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_chunk_layout_alignment():
+    from audio_sheet_retrieval_b200.retrieval import chunk_layout, chunk_views
+    for nq, k in ((1, 1), (7, 5), (10000, 25), (3, 128)):
+        chunk, off = chunk_layout(nq, k)
+        assert chunk % 8 == 0 and off % 8 == 0 and off >= nq * k * 4 and chunk == off + nq * k * 8
+        buf = torch.zeros(3 * chunk, dtype=torch.uint8)
+        s, i = chunk_views(buf, nq, k, rank=2)
+        assert s.shape == (nq, k) and i.shape == (nq, k) and s.dtype == torch.float32 and i.dtype == torch.int64
+        i.fill_(-1)
+        assert buf[:2 * chunk].sum() == 0                   # views alias exactly the third chunk
 
 
 def test_shard_bounds_cover_everything():

@@ -209,3 +209,47 @@ def test_many_slices_select_merge_ties_and_degenerate_rows(nq, k):
     E = np.tile(_db(1, 33), (n, 1))
     s2, i2 = EmbeddingDB(E).topk(Q[:1], k)
     assert list(i2[0]) == list(range(k)) and (s2[0] == s2[0, 0]).all()
+
+
+def test_config4_full_size_default_dispatch_bit_exact():
+    """BASELINE config 4 at its full size through the path asr_topk picks BY ITSELF (nothing forced): 10 000 queries x
+    10^6 rows, k = 25 -> the tf32 pre-filter with many query tiles x several DB slices + the slice merge.  A 64-query
+    sample of the result (indices and scores) must equal the pinned-order C oracle, and the piece vote on the full
+    result must find every recording's piece."""
+    import torch
+    from audio_sheet_retrieval_b200.retrieval import EmbeddingDB, vote_device
+    n_db, n_rec, win, k = 1000000, 100, 100, 25
+    g = torch.Generator(device="cuda").manual_seed(1)
+    D = torch.randn((n_db, 32), generator=g, device="cuda")
+    D = D / D.norm(dim=1, keepdim=True)
+    ids = (torch.arange(n_db, device="cuda") // 100).to(torch.int32)
+    g2 = torch.Generator(device="cuda").manual_seed(2)
+    true_piece = torch.randint(0, n_db // 100, (n_rec,), generator=g2, device="cuda")
+    rows = (true_piece[:, None] * 100 + torch.randint(0, 100, (n_rec, win), generator=g2, device="cuda")).view(-1)
+    Q = (D[rows] + 0.12 * torch.randn((n_rec * win, 32), generator=g2, device="cuda")).contiguous()
+    assert Q.shape[0] * n_db >= 1.6e8 and Q.shape[0] > 24          # the dispatch rule sends this to the pre-filter
+    db = EmbeddingDB(D)
+    s, i = db.topk_device(Q, k)
+    sample = np.linspace(0, Q.shape[0] - 1, 64).astype(int)
+    s_ref, i_ref = clib.topk(Q[sample].cpu().numpy(), D.cpu().numpy(), k)
+    assert (i[sample].cpu().numpy() == i_ref).all() and (s[sample].cpu().numpy() == s_ref).all()
+    pid, cnt = vote_device(i.view(n_rec, -1), ids, 5)
+    assert (pid[:, 0].long() == true_piece).all()
+    # the same DB donated (rows normalised in place, no second copy) and with a small query workspace (chunked calls)
+    db2 = EmbeddingDB(D.clone(), normalise_in_place=True, max_queries=3000)
+    s2, i2 = db2.topk_device(Q, k)
+    assert torch.equal(i2, i) and torch.equal(s2, s)
+    with pytest.raises(Exception):
+        db2.topk_device(Q[:4], k, normalise=False)                   # the raw rows are gone
+
+
+def test_db_without_cosine_copy_matches():
+    """ASR_DB_NO_COSINE_COPY: no normalised rows are kept, cosine queries normalise in-kernel -- same bits."""
+    from audio_sheet_retrieval_b200.retrieval import EmbeddingDB
+    D, Q = _db(50000, 41, unit=False), _db(19, 42, unit=False)
+    D[4000] = D[17]
+    s_ref, i_ref = clib.topk(Q, D, 25)
+    s, i = EmbeddingDB(D, cosine_copy=False).topk(Q, 25)
+    assert (i == i_ref).all() and (s == s_ref).all()
+    s, i = EmbeddingDB(D, cosine_copy=False).topk(Q[:1], 25)
+    assert (i == i_ref[:1]).all() and (s == s_ref[:1]).all()
