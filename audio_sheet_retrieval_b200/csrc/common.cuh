@@ -52,6 +52,22 @@ inline int current_device() {
     int d = 0;
     return cudaGetDevice(&d) == cudaSuccess ? d : -1;
 }
+// Handles are bound to the device that was current at create.  The CUDA runtime's current device is per host thread
+// (a new thread starts on device 0), so every entry point that takes a handle switches to the handle's device for the
+// duration of the call and restores the caller's device afterwards.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        int cur = current_device();
+        if (dev >= 0 && cur != dev) {
+            prev = cur;
+            cudaSetDevice(dev);
+        }
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
 
 // ------------------------------------------------------------------------------------
 // device-side PTX wrappers

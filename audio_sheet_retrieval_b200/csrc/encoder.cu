@@ -1287,6 +1287,7 @@ using namespace asr;
 struct asr_encoder {
     asr_encoder_desc d;
     int max_batch;
+    int device = -1;                // the handle is bound to the device that was current at create
     int H0, W0;                     // prepared input size
     LayerGeom g[8];
     int head_c, head_h, head_w;
@@ -1509,6 +1510,7 @@ int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *d, int max_b
     asr_encoder *e = new asr_encoder();
     e->d = *d;
     e->max_batch = max_batch;
+    e->device = current_device();
     e->H0 = d->prepare == ASR_PREP_SCALE_HALF ? d->in_h / 2 : d->in_h;
     e->W0 = d->prepare == ASR_PREP_SCALE_HALF ? d->in_w / 2 : d->in_w;
     int H = e->H0, W = e->W0, cin = 1;
@@ -1787,6 +1789,7 @@ int asr_encoder_embed(asr_encoder_t *e, const void *x_dev, int x_dtype, int64_t 
     int rc = ensure_device();
     if (rc) return rc;
     ASR_CHECK_ARG(e && x_dev, "NULL argument");
+    DeviceGuard guard(e->device);
     ASR_CHECK_ARG(n >= 0 && n <= e->max_batch, "n exceeds max_batch");
     ASR_CHECK_ARG(x_dtype == ASR_IN_F32 || x_dtype == ASR_IN_U8, "bad x_dtype");
     ASR_CHECK_ARG(path == ASR_PATH_TCGEN05 || path == ASR_PATH_FP32, "bad path");
@@ -2048,6 +2051,7 @@ int asr_encoder_embed_host(asr_encoder_t *e, const void *x_host, int x_dtype, in
     int rc = ensure_device();
     if (rc) return rc;
     ASR_CHECK_ARG(e && x_host, "NULL argument");
+    DeviceGuard guard(e->device);
     ASR_CHECK_ARG(x_dtype == ASR_IN_F32 || x_dtype == ASR_IN_U8, "bad x_dtype");
     if (n == 0) return ASR_OK;
     const size_t esz = x_dtype == ASR_IN_U8 ? 1 : 4;
@@ -2072,6 +2076,9 @@ int asr_encoder_embed_host(asr_encoder_t *e, const void *x_host, int x_dtype, in
     cudaPointerAttributes pa;
     bool pinned = cudaPointerGetAttributes(&pa, x_host) == cudaSuccess && pa.type == cudaMemoryTypeHost;
     cudaGetLastError();
+    if (getenv("ASR_DEBUG_HOST"))
+        fprintf(stderr, "[asr] embed_host: n %lld, input %s (attr type %d), chunk %d\n", (long long)n,
+                pinned ? "pinned" : "PAGEABLE (staged through pinned buffers)", (int)pa.type, e->max_batch);
     if (!pinned && !e->pin_in[0])
         for (int b = 0; b < 2; ++b) ASR_CUDA(cudaMallocHost(&e->pin_in[b], max_bytes));
     // Chunk sizes ramp up (512, 1024, ... max_batch): the first host->device copy is the only one that no

@@ -1265,7 +1265,7 @@ int asr_topk(asr_db_t *db, const float *q_dev, int64_t nq, int k, int normalise,
     // measured crossovers (k = 25): the exact QT=16 kernel wins up to ~24 queries, and for small problems
     // whatever the query count: exact ~ 0.05 ms + 7.3 ms per 1e9 scores, pre-filter ~ 1.15 ms + 0.55 ms per 1e9
     // (profiles/r1_configs_3_5.json: its work items are at least 128 tiles long) -> equal at 1.6e8 scores
-    ASR_CHECK_ARG(current_device() == db->device, "the handle belongs to another device (one handle per device)");
+    DeviceGuard guard(db->device);
     ASR_CHECK_ARG(normalise || !(db->flags & ASR_DB_NORMALISE_IN_PLACE),
                   "the raw rows are gone: this DB was created with ASR_DB_NORMALISE_IN_PLACE");
     const bool want_tc = force ? (strcmp(force, "tc") == 0) : (nq > 24 && (double)nq * (double)db->n >= 1.6e8);
@@ -1380,7 +1380,7 @@ int asr_rank_of_target(asr_db_t *db, const float *q_dev, int64_t nq, int64_t q_b
     ASR_CHECK_ARG(db != nullptr && q_dev && tscore_dev && tidx_dev, "NULL argument");
     ASR_CHECK_ARG(kg >= 1 && hg >= 1, "kg, hg must be >= 1");
     ASR_CHECK_ARG(!(db->flags & ASR_DB_NORMALISE_IN_PLACE), "not available for ASR_DB_NORMALISE_IN_PLACE handles");
-    ASR_CHECK_ARG(current_device() == db->device, "the handle belongs to another device (one handle per device)");
+    DeviceGuard guard(db->device);
     if (nq == 0) return ASR_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if (phase == 0) {

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py - headline benchmark of the retrieval hot path (one JSON line on rank 0).
 
-Workload (BASELINE.json configs[1]): the full-resolution encoder pair `mutopia_ccal_cont`
+Headline workload (BASELINE.json configs[1]): the full-resolution encoder pair `mutopia_ccal_cont`
 (12/24/48/48 filters; synthetic weights in the reference's pickle format, no weights are shipped
 for this model) batch-embedding `--pairs` synthetic snippet pairs (sheet 160x200 uint8 +
 spectrogram 92x42 float32) + CCA projection + length norm on every GPU.  One step = one pass
@@ -10,12 +10,19 @@ over all pairs.  Weak scaling: every rank embeds its own `--pairs` pairs, no dat
   value      pairs/s with inputs resident in HBM (asr_encoder_embed, chunks of --max-batch)
   e2e        pairs/s through the host-buffer C-ABI entry RetrievalWrapper uses
              (asr_encoder_embed_host): pinned host inputs, H2D + D2H inside the timed region
-  roofline   tcgen05 conv kernel (layers 1..7, both views): algorithmic TFLOP/s vs measured bf16 peak,
-             kernel time measured with CUDA events on the launching stream inside the timed region
-  retrieval  fused normalise+dot+top-k over a resident DB: HBM GB/s (Q=1, k=25) and queries/s
-  cpu_baseline  the oracle port of the reference's CPU path on a bounded sample
+  roofline   tcgen05 kernels (fused layer 0+1, layers 1..7, both views): algorithmic TFLOP/s vs measured bf16
+             peak, kernel time measured with CUDA events on the launching stream inside the timed region
 
-`--impl reference` times that CPU path alone (rank 0 only).
+The other BASELINE configs ride along as extra keys of the same line (their sizes are BASELINE's):
+  config1_rsz_eval       configs[0]: rsz model + tutorial pickle, 2000 pairs, R@k / MRR / MR with parity vs the oracle
+  config3_refit          configs[2]: CCA refit on 25 000 latent pairs, rows sharded over the ranks, ONE all-reduce
+  piece_identification   configs[3]: 10 000 queries vs a 10^6-row DB sharded over the ranks, k = 25, all-gather +
+                         merge + vote; per-phase times; bit_exact = a 64-query sample equals the pinned-order oracle
+  retrieval_sweep        configs[4]: 10^5 .. 10^8 rows x Q in {1, 16, 100}, DB sharded over the ranks, fraction of the
+                         measured HBM bandwidth per cell
+  cpu_baseline(s)        the oracle port of the reference's CPU path on a bounded sample (rank 0, N = 1 only)
+
+`--impl reference` times the CPU port of the encoder path alone (rank 0 only), same generator and chunking.
 """
 import argparse
 import json
@@ -33,8 +40,10 @@ if ROOT not in sys.path:
 
 MODEL = "mutopia_ccal_cont"
 PKL = os.path.join(ROOT, "tests", "golden", "params_synth_mutopia_ccal_cont.pkl")
+PKL_RSZ = os.path.join(ROOT, "tests", "golden", "params_all_split_mutopia_full_aug.pkl")
 METRIC = "snippet pairs embedded per second (both encoder branches + CCA projection)"
 UNIT = "pairs/s"
+L2_BYTES = 126e6
 
 
 def peaks():
@@ -92,22 +101,36 @@ class ClockSampler(object):
                     reasons=sorted(reasons), samples=len(sm))
 
 
-def cpu_reference_pairs_per_s(n_sample, steps=1, warmup=0):
-    """The reference's CPU path (oracle port: torch-CPU fp32 NCHW conv/BN/ELU/pool, batch 100,
-    CCA projection, length norm; asr/retrieval_wrapper.py + model graph) on all host threads."""
+def make_inputs(torch, n, device, seed):
+    """The synthetic workload of BOTH arms: sheet-like uint8 (mostly white, ~19 % dark pixels) and spectrogram-like
+    float32 (sparse, mean ~0.1)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    X1 = torch.where(torch.rand((n, 1, 160, 200), generator=g, device=device) < 0.19,
+                     torch.randint(0, 120, (n, 1, 160, 200), generator=g, device=device, dtype=torch.uint8),
+                     torch.full((1,), 255, device=device, dtype=torch.uint8))
+    X2 = torch.relu(torch.randn((n, 1, 92, 42), generator=g, device=device) - 1.2) * 0.8
+    return X1, X2
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU side: the oracle port of the reference's CPU path (bounded samples; reported baselines, never the target)
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference_pairs_per_s(n_sample, steps=1, warmup=0, chunk=4096):
+    """The reference's CPU path (oracle port: torch-CPU fp32 NCHW conv/BN/ELU/pool in batches of 100 as
+    retrieval_wrapper.py:60, CCA projection, length norm) on all host threads, over the same generator and the same
+    chunking (chunks of --max-batch pairs) as the GPU arm."""
     import torch
-    from oracle.encoders import OracleNet, load_param_list, synth_inputs
+    from oracle.encoders import OracleNet, load_param_list
     torch.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1; use every host core
     net = OracleNet(MODEL, load_param_list(PKL))
-    X1, X2 = synth_inputs(min(n_sample, 64), seed=3)
-    reps = (n_sample + len(X1) - 1) // len(X1)
-    X1 = np.concatenate([X1] * reps)[:n_sample]
-    X2 = np.concatenate([X2] * reps)[:n_sample]
+    X1, X2 = make_inputs(torch, n_sample, "cpu", 23)
+    X1, X2 = X1.numpy().astype(np.float32), X2.numpy()          # the reference pools hand out float32 holding 0..255
     times = []
     for i in range(warmup + steps):
         t = time.perf_counter()
-        net.compute_view_1(X1)
-        net.compute_view_2(X2)
+        for s in range(0, n_sample, chunk):
+            net.compute_view_1(X1[s:s + chunk])
+            net.compute_view_2(X2[s:s + chunk])
         dt = time.perf_counter() - t
         if i >= warmup:
             times.append(dt)
@@ -118,57 +141,106 @@ def run_reference(args, rank):
     if rank != 0:
         return
     n_sample = args.cpu_sample or 1024
-    v, dt, cores = cpu_reference_pairs_per_s(n_sample, steps=args.steps, warmup=min(args.warmup, 1))
+    v, dt, cores = cpu_reference_pairs_per_s(n_sample, steps=args.steps, warmup=args.warmup, chunk=args.max_batch)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: %s full-res encoders, batch-embed synthetic pairs + CCA projection" % MODEL,
-                   "pairs_per_step": n_sample, "note": "bounded sample of the %d-pair job" % args.pairs},
+        "config": {"workload": "configs[1]: %s full-res encoders (12/24/48/48), synthetic pairs + CCA projection + length norm"
+                               % MODEL,
+                   "pairs_per_step": n_sample, "max_batch": args.max_batch,
+                   "generator": "bench.make_inputs (the generator of the GPU arm)",
+                   "note": "bounded sample of the %d-pair job: a rate, so it compares with the GPU arm's pairs/s" % args.pairs},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d pairs per step, torch-CPU fp32 oracle port (Theano/Lasagne cannot be installed)" % n_sample},
+                         "sample": "%d pairs per step, torch-CPU fp32 oracle port (the reference is Python 2 + Theano/Lasagne: "
+                                   "not installable here)" % n_sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def retrieval_leg(torch, dev, pk, rows, quick=False):
-    """Fused top-k: HBM-regime bandwidth (Q=1) and throughput at larger query counts."""
-    from audio_sheet_retrieval_b200.retrieval import EmbeddingDB
-    g = torch.Generator(device=dev).manual_seed(1)
-    D = torch.randn((rows, 32), generator=g, device=dev)
-    D = D / D.norm(dim=1, keepdim=True)
-    db = EmbeddingDB(D)
-    out = {"db_rows": rows, "k": 25, "db_bytes": rows * 128}
+def cpu_retrieve_loop(db, queries, n_candidates):
+    """The reference's per-query loop (audio_sheet_server.py:230-234 -> :530-551): cdist(DB, q, 'cosine') over the whole
+    DB + a FULL argsort, one query at a time.  Returns (seconds per query, indices (nq, n_candidates))."""
+    from oracle.search import retrieve_ids_ref
+    ids = np.zeros(len(db), np.int64)
+    out = np.empty((len(queries), n_candidates), np.int64)
+    t = time.perf_counter()
+    for i in range(len(queries)):
+        _, out[i] = retrieve_ids_ref(db, ids, queries[i:i + 1], n_candidates)
+    return (time.perf_counter() - t) / len(queries), out
 
-    def timed(q, iters):
-        s = torch.empty((q.shape[0], 25), device=dev)
-        i = torch.empty((q.shape[0], 25), dtype=torch.int64, device=dev)
-        for _ in range(3):
-            db.topk_device(q, 25, out_scores=s, out_idx=i)
-        torch.cuda.synchronize()
+
+# ----------------------------------------------------------------------------------------------------------------
+# GPU legs
+# ----------------------------------------------------------------------------------------------------------------
+def timed_ms(torch, fn, iters, flush=None):
+    """Mean device time of fn() over `iters` calls, each timed by its own event pair; `flush` (a big buffer) is
+    rewritten before every call so that nothing of the previous call is left in L2."""
+    times = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.fill_(1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(iters):
-            db.topk_device(q, 25, out_scores=s, out_idx=i)
+        fn()
         e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / iters
-
-    for nq in ((1, 16, 100) if not quick else (1,)):
-        q = torch.randn((nq, 32), generator=g, device=dev)
-        ms = timed(q, 10 if nq <= 16 else 5)
-        gbs = rows * 128 / (ms * 1e-3) / 1e9
-        out["q%d" % nq] = {"ms": ms, "queries_per_s": nq / (ms * 1e-3), "algorithmic_gbs": gbs,
-                           "hbm_frac": gbs / pk["hbm_gbs"]}
-    db.close()
-    return out
+        times.append(e0.elapsed_time(e1))
+    return float(np.mean(times))
 
 
-def piece_id_leg(torch, dev, rank, world, quick=False):
-    """Config 4: 10k queries (100 recordings x 100 windows) vs a 1M-row DB sharded over the ranks,
-    k=25, all-gather + merge + vote."""
-    import torch.distributed as dist
+def unit_rows(torch, n, dev, seed):
+    """(n,32) fp32 unit-norm Gaussian directions, generated in slabs (a 1e8-row DB is 12.8 GB)."""
+    g = torch.Generator(device=dev).manual_seed(seed)
+    D = torch.empty((n, 32), device=dev)
+    slab = 1 << 24
+    for s in range(0, n, slab):
+        d = torch.randn((min(slab, n - s), 32), generator=g, device=dev)
+        D[s:s + slab] = d / d.norm(dim=1, keepdim=True)
+    return D
+
+
+def retrieval_sweep_leg(torch, dist, dev, pk, rank, world, rows_list, quick=False):
+    """Config 5: rows x Q sweep, the DB sharded over the ranks (contiguous shards, queries replicated), local top-k +
+    ONE all-gather + merge inside the timed region, max over ranks.  hbm_frac = whole-DB bytes / time / (N x peak)."""
+    from audio_sheet_retrieval_b200.dist import ShardedDB, shard_bounds
+    flush = torch.empty(int(2 * L2_BYTES), dtype=torch.uint8, device=dev)
+    cells = []
+    for rows in rows_list:
+        lo, hi = shard_bounds(rows, rank, world)
+        shard = unit_rows(torch, hi - lo, dev, 1000 + rank)
+        sdb = ShardedDB(shard, lo, group=None, normalise_in_place=True)      # donated buffer: no second copy
+        g = torch.Generator(device=dev).manual_seed(7)
+        for nq in (1, 16, 100):
+            q = torch.randn((nq, 32), generator=g, device=dev)
+            for _ in range(3):
+                sdb.topk_device(q, 25)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            ms = timed_ms(torch, lambda: sdb.topk_device(q, 25), 3 if quick else 8, flush)
+            t = torch.tensor([ms], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            gbs = rows * 128 / (ms * 1e-3) / 1e9
+            cells.append({"rows": rows, "q": nq, "ms": ms, "queries_per_s": nq / (ms * 1e-3), "algorithmic_gbs": gbs,
+                          "hbm_frac": gbs / (world * pk["hbm_gbs"]),
+                          "shard_fits_l2": bool((hi - lo) * 128 <= L2_BYTES)})
+        sdb.local.close()
+        del sdb, shard
+        torch.cuda.empty_cache()
+    return {"k": 25, "n_gpus": world, "cells": cells,
+            "timing": "CUDA events per call, L2 flushed (252 MB rewritten) before every call, max over ranks; "
+                      "N > 1: local top-k + one NCCL all-gather + merge kernel inside the timed region",
+            "directions": "audio->sheet and sheet->audio are the same computation (which codes are the DB)",
+            "peak_gbs_per_gpu": pk["hbm_gbs"]}
+
+
+def piece_id_leg(torch, dist, dev, rank, world, with_cpu, quick=False):
+    """Config 4: 10k queries (100 recordings x 100 windows) vs a 1M-row DB sharded over the ranks, k=25, all-gather +
+    merge + vote; per-phase device times; a 64-query sample checked against the pinned-order oracle."""
     from audio_sheet_retrieval_b200.dist import ShardedDB, shard_bounds
     n_db, n_rec, win = 1000000, (100 if not quick else 10), 100
     g = torch.Generator(device=dev).manual_seed(1)
@@ -178,7 +250,7 @@ def piece_id_leg(torch, dev, rank, world, quick=False):
     g2 = torch.Generator(device=dev).manual_seed(2)
     true_piece = torch.randint(0, n_db // 100, (n_rec,), generator=g2, device=dev)
     rows = (true_piece[:, None] * 100 + torch.randint(0, 100, (n_rec, win), generator=g2, device=dev)).view(-1)
-    Q = D[rows] + 0.12 * torch.randn((n_rec * win, 32), generator=g2, device=dev)
+    Q = (D[rows] + 0.12 * torch.randn((n_rec * win, 32), generator=g2, device=dev)).contiguous()
     lo, hi = shard_bounds(n_db, rank, world)
     sdb = ShardedDB(D[lo:hi].contiguous(), lo, row_ids_global=ids, group=None)
     for _ in range(2):
@@ -186,9 +258,9 @@ def piece_id_leg(torch, dev, rank, world, quick=False):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    iters = 3
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    iters = 3
     for _ in range(iters):
         pid, cnt = sdb.identify(Q, n_rec, 5, 25)
     e1.record()
@@ -196,11 +268,178 @@ def piece_id_leg(torch, dev, rank, world, quick=False):
     ms = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    # per-phase breakdown (one more call with events between the phases)
+    ev = []
+    v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    v0.record()
+    pid, cnt = sdb.identify(Q, n_rec, 5, 25, events=ev)
+    v1.record()
+    torch.cuda.synchronize()
+    if ev:
+        ph = torch.tensor([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3]),
+                           ev[3].elapsed_time(v1)], device=dev)
+        dist.all_reduce(ph, op=dist.ReduceOp.MAX)
+        phases = dict(zip(("local_topk_ms", "allgather_ms", "merge_ms", "vote_ms"), [float(x) for x in ph.tolist()]))
+    else:
+        phases = {"local_topk_and_vote_ms": v0.elapsed_time(v1)}
     acc = float((pid[:, 0].long() == true_piece).float().mean().item())
-    return {"db_rows": n_db, "queries": n_rec * win, "k": 25, "ms": float(ms.item()),
-            "queries_per_s": n_rec * win / (float(ms.item()) * 1e-3), "top1_piece_accuracy": acc,
-            "regime": "tcgen05 tf32 pre-filter + exact fp32 re-scoring (bit-exact results); bound by the TMEM read-out of "
-                      "the 128x256 score tiles; DB sharded over %d GPU(s)" % world}
+    out = {"db_rows": n_db, "queries": n_rec * win, "k": 25, "ms": float(ms.item()),
+           "queries_per_s": n_rec * win / (float(ms.item()) * 1e-3), "top1_piece_accuracy": acc, "phases": phases,
+           "regime": "tcgen05 tf32 pre-filter + exact fp32 re-scoring; DB sharded over %d GPU(s); "
+                     "one all-gather of [scores | indices] chunks, merge kernel reads the rank-major chunks" % world}
+    # parity at full size: a 64-query sample of the merged result (indices AND scores) vs the pinned-order C oracle
+    s_all, i_all = sdb.topk_device(Q, 25)
+    if rank == 0:
+        from oracle import clib
+        sample = np.linspace(0, Q.shape[0] - 1, 64).astype(int)
+        Dh = D.cpu().numpy()
+        s_ref, i_ref = clib.topk(Q[sample].cpu().numpy(), Dh, 25)
+        out["bit_exact"] = bool((i_all[sample].cpu().numpy() == i_ref).all() and (s_all[sample].cpu().numpy() == s_ref).all())
+        out["bit_exact_sample"] = "64 of %d queries, indices and scores after the merge, vs oracle/c pinned-order top-k" % Q.shape[0]
+        if with_cpu:
+            nq_cpu = 100 if not quick else 5
+            qs = np.linspace(0, Q.shape[0] - 1, nq_cpu).astype(int)
+            spq, idx_cpu = cpu_retrieve_loop(Dh, Q[qs].cpu().numpy(), 25)
+            same = float((idx_cpu == i_all[qs].cpu().numpy()).mean())
+            out["cpu_baseline"] = {"value": 1.0 / spq, "unit": "queries/s", "cores": 1, "kind": "port",
+                                   "sample": "%d of the %d queries (%.1f s): scipy cdist(DB, q, 'cosine') over the 10^6 rows + "
+                                             "full argsort per query, the loop of audio_sheet_server.py:230-240"
+                                             % (nq_cpu, Q.shape[0], spq * nq_cpu),
+                                   "index_agreement_with_gpu": same}
+    sdb.local.close()
+    return out
+
+
+def config1_leg(torch, dev, with_cpu):
+    """Config 1: rsz model + tutorial pickle, 2000 synthetic pairs through RetrievalWrapper + eval_retrieval;
+    R@k / MRR / median rank next to the oracle's on the same inputs (tolerance of the north star: 0.5 % absolute)."""
+    from audio_sheet_retrieval_b200.models import mutopia_ccal_cont_rsz as model
+    from audio_sheet_retrieval_b200.retrieval_wrapper import RetrievalWrapper
+    from audio_sheet_retrieval_b200.utils.mutopia_data import SyntheticPairPool
+    from audio_sheet_retrieval_b200.utils.train_dcca_pool import eval_retrieval
+    import contextlib
+    import io
+    n = 2000
+    pool = SyntheticPairPool(2000, seed=25)
+    X1, X2 = pool[np.linspace(0, 1999, n).astype(int)]
+    with contextlib.redirect_stdout(io.StringIO()):
+        w = RetrievalWrapper(model, PKL_RSZ, prepare_view_1=model.prepare, prepare_view_2=None)
+    w.compute_view_1(X1[:200]); w.compute_view_2(X2[:200])
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    c1, c2 = w.compute_view_1(X1), w.compute_view_2(X2)
+    t_embed = time.perf_counter() - t
+    eval_retrieval(c1[:100], c2[:100])
+    t = time.perf_counter()
+    mr, med, md, hr, mrr = eval_retrieval(c1, c2)
+    t_eval = time.perf_counter() - t
+    out = {"model": "mutopia_ccal_cont_rsz (tutorial pickle)", "pairs": n, "embed_pairs_per_s": n / t_embed,
+           "embed_ms": t_embed * 1e3, "eval_retrieval_ms": t_eval * 1e3,
+           "api": "RetrievalWrapper.compute_view_1/2 (NumPy in, NumPy out) + eval_retrieval",
+           "metrics": {"mrr": float(mrr), "median_rank": float(med), "mean_rank": float(mr),
+                       "recall_at_k": dict((str(k), 100.0 * hr[k] / n) for k in (1, 5, 10, 25))}}
+    if with_cpu:
+        from oracle import metrics
+        from oracle.encoders import OracleNet, load_param_list
+        torch.set_num_threads(os.cpu_count() or 1)
+        onet = OracleNet("mutopia_ccal_cont_rsz", load_param_list(PKL_RSZ))
+        t = time.perf_counter()
+        r1, r2 = onet.compute_view_1(X1), onet.compute_view_2(X2)
+        t_cpu = time.perf_counter() - t
+        t = time.perf_counter()
+        omr, omed, omd, ohr, omrr = metrics.eval_retrieval_ref(r1, r2)
+        t_cpu_eval = time.perf_counter() - t
+        cos = float(min(((c1 * r1).sum(1)).min(), ((c2 * r2).sum(1)).min()))
+        out["parity"] = {"min_code_cosine_vs_oracle": cos, "mrr_abs_diff": abs(float(mrr) - float(omrr)),
+                         "median_rank_abs_diff": abs(float(med) - float(omed)),
+                         "recall_at_k_abs_diff_pct": dict((str(k), abs(100.0 * (hr[k] - ohr[k]) / n)) for k in (1, 5, 10, 25)),
+                         "within_tolerance": bool(cos >= 0.999 and abs(float(mrr) - float(omrr)) <= 0.005
+                                                  and all(abs(100.0 * (hr[k] - ohr[k]) / n) <= 0.5 for k in (1, 5, 10, 25)))}
+        out["cpu_baseline"] = {"value": n / t_cpu, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": "all 2000 pairs (%.1f s embed, %.2f s cdist + per-row argsort): torch-CPU fp32 "
+                                         "oracle port of run_eval.py:102-174" % (t_cpu, t_cpu_eval),
+                               "eval_retrieval_ms": t_cpu_eval * 1e3}
+    return out
+
+
+def config3_leg(torch, dist, dev, rank, world, with_cpu):
+    """Config 3: CCA('svd') refit on 25 000 latent pairs, rows sharded over the ranks: one fused Gram pass per rank,
+    ONE all-reduce of 3137 doubles, replicated single-CTA Jacobi solve."""
+    from audio_sheet_retrieval_b200 import _lib
+    from audio_sheet_retrieval_b200.dist import shard_bounds
+    from audio_sheet_retrieval_b200.utils.cca import CCA, cca_solve_device
+    n = 25000
+    rng = np.random.RandomState(23)
+    Z = rng.normal(size=(n, 32))
+    H1 = (Z @ rng.normal(size=(32, 32)) * 0.05 + 0.3).astype(np.float32)
+    H2 = (Z @ rng.normal(size=(32, 32)) * 0.05 + 0.02 * rng.normal(size=(n, 32)) - 0.1).astype(np.float32)
+    lo, hi = shard_bounds(n, rank, world)
+    h1, h2 = torch.as_tensor(H1[lo:hi]).to(dev), torch.as_tensor(H2[lo:hi]).to(dev)
+    group = dist.group.WORLD if world > 1 else None
+    c = CCA()
+    for _ in range(3):
+        sig = c.fit(h1, h2, group=group)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    iters = 10
+    t = time.perf_counter()
+    for _ in range(iters):
+        sig = c.fit(h1, h2, group=group)
+    torch.cuda.synchronize()
+    wall = torch.tensor([(time.perf_counter() - t) / iters * 1e3], device=dev, dtype=torch.float64)
+    # device-side breakdown: accumulate / all-reduce / solve
+    sums = torch.zeros(_lib.CCA_NSUMS + 1, dtype=torch.float64, device=dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    if world > 1:
+        dist.barrier()
+    ev[0].record()
+    _lib.check(_lib.lib.asr_cca_accumulate_counted(_lib.dptr(h1), _lib.dptr(h2), int(h1.shape[0]), None, None,
+                                                   _lib.dptr(sums), _lib.stream_ptr()))
+    ev[1].record()
+    if world > 1:
+        dist.all_reduce(sums)
+    ev[2].record()
+    cca_solve_device(sums, _lib.CCA_COUNT_ON_DEVICE)
+    ev[3].record()
+    torch.cuda.synchronize()
+    ph = torch.tensor([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])], device=dev,
+                      dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ph, op=dist.ReduceOp.MAX)
+    out = {"samples": n, "n_gpus": world, "fit_wall_ms": float(wall.item()),
+           "device_ms": {"gram_pass": float(ph[0]), "allreduce_3137_f64": float(ph[1]), "jacobi_solve": float(ph[2])},
+           "regime": "latency-bound: 6.4 MB of latents, a 25 KB all-reduce, one single-CTA fp64 solve; fit_wall_ms is the "
+                     "user-visible CCA.fit (includes the D2H copies of U, V, m, sigma)"}
+    if with_cpu and rank == 0:
+        from oracle import cca as occa
+        o = occa.CCA()
+        o.fit(H1, H2)
+        t = time.perf_counter()
+        for _ in range(5):
+            sig_ref = o.fit(H1, H2)
+        t_cpu = (time.perf_counter() - t) / 5
+        out["cpu_baseline"] = {"value": t_cpu * 1e3, "unit": "ms per fit", "cores": os.cpu_count(), "kind": "port",
+                               "sample": "the full 25 000 x 32 fit: NumPy fp32 sgemm covariances + SciPy sqrtm/inv + LAPACK svd "
+                                         "(oracle/cca.py, pinned against the reference's own CCA.fit)"}
+        out["sigma_abs_diff_vs_port"] = float(np.abs(np.asarray(sig) - sig_ref).max())
+    return out
+
+
+def read_traffic(mb):
+    """Measured DRAM traffic of the tcgen05 kernels (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged
+    over the launches of one chunk pair): written by tools/launch_table.py from the ncu launch list of this command."""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if not os.path.exists(p):
+        return None, "no capture committed"
+    d = json.load(open(p))
+    e = d.get(str(mb))
+    if not e:
+        return None, "no capture for max_batch %d" % mb
+    return e["bytes_per_conv_launch"], "%s (%s)" % (e["source"], d.get("command", ""))
 
 
 def main():
@@ -210,11 +449,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=100000, help="pairs per GPU per step")
-    ap.add_argument("--max-batch", type=int, default=4096, help="samples per launch (activation arena: ~2.7 MB per pair)")
+    ap.add_argument("--max-batch", type=int, default=4096, help="samples per launch (activation arena: ~1.7 MB per pair)")
     ap.add_argument("--cpu-sample", type=int, default=0,
                     help="pairs per CPU step (default: 1024 per step for --impl reference, 4096 for the cpu_baseline leg)")
     ap.add_argument("--db-rows", type=int, default=10000000)
+    ap.add_argument("--sweep-max-rows", type=int, default=100000000)
     ap.add_argument("--skip-extras", action="store_true", help="only the headline leg (used under ncu)")
+    ap.add_argument("--quick", action="store_true", help="small extras (smoke runs)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -246,12 +487,7 @@ def main():
     flops_pair = e1.flops_per_sample + e2.flops_per_sample
 
     n, mb = args.pairs, args.max_batch
-    g = torch.Generator(device=dev).manual_seed(23 + rank)
-    # sheet-like uint8 (mostly white, ~19 % dark) and spectrogram-like float32 (sparse, mean ~0.1)
-    X1 = torch.where(torch.rand((n, 1, 160, 200), generator=g, device=dev) < 0.19,
-                     torch.randint(0, 120, (n, 1, 160, 200), generator=g, device=dev, dtype=torch.uint8),
-                     torch.full((1,), 255, device=dev, dtype=torch.uint8))
-    X2 = torch.relu(torch.randn((n, 1, 92, 42), generator=g, device=dev) - 1.2) * 0.8
+    X1, X2 = make_inputs(torch, n, dev, 23 + rank)
     codes1 = torch.empty((n, 32), device=dev)
     codes2 = torch.empty((n, 32), device=dev)
 
@@ -290,22 +526,28 @@ def main():
     ms_step = float(ms_total.item()) / args.steps
     value = world * n / (ms_step * 1e-3)
 
-    # roofline of the dominant kernel family: the tcgen05 convolutions of layers 1-7 (7 launches per embed call)
-    conv_flops_pair = flops_pair - 2.0 * 9 * 12 * (160 * 200 + 92 * 42) - 2.0 * 48 * 32 * (10 * 12 + 5 * 2)
+    # Roofline of the dominant kernel family: the tcgen05 kernels.  Layer 0 of a branch counts with them when it runs
+    # inside the fused layer-0 + layer-1 kernel (its time cannot be separated any more); an unfused layer 0 and the
+    # fp32 head are reported beside them.
+    f1, f2 = e1.fusion & 1, e2.fusion & 1
+    l0_flops = {1: 2.0 * 9 * 12 * 160 * 200, 2: 2.0 * 9 * 12 * 92 * 42}
+    head_flops = 2.0 * 48 * 32 * (10 * 12 + 5 * 2)
+    conv_flops_pair = flops_pair - head_flops - (0 if f1 else l0_flops[1]) - (0 if f2 else l0_flops[2])
     conv_ms = t1["ms_conv_tc"] + t2["ms_conv_tc"]
-    conv_launches = 7 * (t1["calls"] + t2["calls"])
+    conv_launches = (7 * t1["calls"]) + (7 * t2["calls"])
     achieved = conv_flops_pair * n * args.steps / (conv_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "conv3x3_rows_kernel + conv3x3_tc_kernel (tcgen05 implicit GEMM, layers 1-7 of both branches)",
+    traffic, traffic_src = read_traffic(mb)
+    roofline = {"bound": "tensor",
+                "kernel": "l01_fused_kernel (prepare + layer 0 + layer 1, sheet branch) + conv3x3_rows_kernel + conv3x3_tc_kernel "
+                          "(tcgen05 implicit GEMM, layers 1-7 of both branches)",
                 "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
                 "peak_source": pk["src"] + ", sustained figure (kernel timed inside a long step)",
-                # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the 14 conv launches of one
-                # chunk pair: ncu captures profiles/r1_launches_mb4096.csv (14945 MB / 14) and r1_launches_final.csv
-                # (1024-pair chunks, 3397 MB / 14); other chunk sizes: not captured
-                "traffic": {4096: 1067.5e6, 1024: 242.6e6}.get(mb),
+                "traffic": traffic, "traffic_source": traffic_src,
                 "avg_launch_ms": conv_ms / max(conv_launches, 1), "launches": conv_launches,
                 "algorithmic_flops_per_pair": conv_flops_pair,
+                "fused_layer01": {"sheet_branch": bool(f1), "spectrogram_branch": bool(f2)},
                 "share_of_step": conv_ms / (ms_step * args.steps),
-                "other_ms_per_step": {"layer0_tcgen05_toeplitz": (t1["ms_layer0"] + t2["ms_layer0"]) / args.steps,
+                "other_ms_per_step": {"layer0_unfused_tcgen05_toeplitz": (t1["ms_layer0"] + t2["ms_layer0"]) / args.steps,
                                       "head": (t1["ms_head"] + t2["ms_head"]) / args.steps}}
 
     # ---- e2e: host buffers through the C-ABI entry the wrapper uses ----
@@ -318,28 +560,52 @@ def main():
     barrier()
     k_e2e = max(1, args.steps)
     t0 = time.perf_counter()
+    t_v1 = 0.0
+    # the two branches are independent calls (compute_view_1 / compute_view_2): issue them from two host threads so
+    # that the spectrogram branch's copies overlap the sheet branch's kernels (each handle has its own streams)
+    res, t_br = {}, {}
+
+    def run_branch(name, enc, h):
+        ta = time.perf_counter()
+        res[name] = enc.embed_host(h)
+        t_br[name] = t_br.get(name, 0.0) + time.perf_counter() - ta
+
     for _ in range(k_e2e):
-        c1h = e1.embed_host(h1)
-        c2h = e2.embed_host(h2)
+        th = threading.Thread(target=run_branch, args=("v2", e2, h2))
+        th.start()
+        run_branch("v1", e1, h1)
+        th.join()
     torch.cuda.synchronize()
+    c1h, c2h = res["v1"], res["v2"]
     dt = torch.tensor([(time.perf_counter() - t0) / k_e2e], device=dev, dtype=torch.float64)
+    ms_v1, ms_v2 = t_br["v1"] / k_e2e * 1e3, t_br["v2"] / k_e2e * 1e3
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_value = world * n_e2e / float(dt.item())
     same = bool(np.array_equal(c1h, codes1[:n_e2e].cpu().numpy()) and np.array_equal(c2h, codes2[:n_e2e].cpu().numpy()))
-    # what the host link gives a plain pinned copy of the same bytes (explains e2e vs value)
+    # what the host link gives a plain pinned copy of the same bytes (explains e2e vs value), all ranks copying at once
     hv = h1.view(-1)[:min(h1.numel(), 1 << 30)]
     dv = torch.empty_like(hv, device=dev)
-    dv.copy_(hv, non_blocking=True); torch.cuda.synchronize()
-    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l0.record(); dv.copy_(hv, non_blocking=True); l1.record(); torch.cuda.synchronize()
-    link_gbs = hv.numel() / (l0.elapsed_time(l1) * 1e-3) / 1e9
+    dv.copy_(hv, non_blocking=True)
+    barrier()
+    la, lb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    la.record(); dv.copy_(hv, non_blocking=True); lb.record(); torch.cuda.synchronize()
+    link = torch.tensor([hv.numel() / (la.elapsed_time(lb) * 1e-3) / 1e9], device=dev)
+    if world > 1:
+        dist.all_reduce(link, op=dist.ReduceOp.MIN)
+    link_gbs = float(link.item())
     del dv
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_e2e * (160 * 200 + 92 * 42 * 4),
+    h2d = n_e2e * (160 * 200 + 92 * 42 * 4)
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": n_e2e * 2 * 32 * 4, "steps": k_e2e,
            "api": "asr_encoder_embed_host (what RetrievalWrapper.compute_view_1/2 call)", "codes_equal_device_path": same,
-           "h2d_gbs_used": n_e2e * (160 * 200 + 92 * 42 * 4) / float(dt.item()) / 1e9,
-           "h2d_gbs_plain_pinned_copy": link_gbs}
+           "ms_per_step_sheet_branch": ms_v1, "ms_per_step_spectrogram_branch": ms_v2,
+           "concurrency": "the two branch calls run concurrently from two host threads",
+           "h2d_gbs_used": h2d / float(dt.item()) / 1e9,
+           "h2d_gbs_plain_pinned_copy": link_gbs,
+           "host_link_note": "min over ranks of a plain pinned copy with all %d rank(s) copying at once; e2e needs "
+                             "value x 47.5 KB per pair = %.1f GB/s per GPU, so e2e is bound by this link whenever it is "
+                             "lower (all GPUs of the box share the host's PCIe root complexes)" % (world, value / world * 47456 / 1e9)}
     del h1, h2
 
     line = {
@@ -349,34 +615,50 @@ def main():
         "config": {"workload": "configs[1]: %s full-res encoders (12/24/48/48), %d synthetic pairs per GPU per step "
                                "+ CCA projection + length norm" % (MODEL, n),
                    "pairs_per_gpu": n, "max_batch": mb, "weights": "synthetic, reference pickle format (none shipped for this model)",
+                   "generator": "bench.make_inputs (also the generator of --impl reference)",
                    "l2": "inputs (%.1f GB per GPU) are larger than L2; no flush needed" % ((n * (32000 + 15456)) / 1e9),
                    "algorithmic_mflop_per_pair": flops_pair / 1e6},
         "algorithmic_tflops": flops_pair * value / 1e12,
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
     }
-    del X1, X2
+    del X1, X2, codes1, codes2
+    e1.close(); e2.close()
     torch.cuda.empty_cache()
+    with_cpu = rank == 0 and world == 1
     if not args.skip_extras:
-        try:
-            r = retrieval_leg(torch, dev, pk, args.db_rows)
-            r["peak_gbs"] = pk["hbm_gbs"]
-            line["retrieval"] = r
-            line["roofline_retrieval"] = {"bound": "hbm", "kernel": "topk_stream_kernel (Q=1, k=25, %d-row fp32 DB)" % args.db_rows,
-                                          "achieved": r["q1"]["algorithmic_gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
-                                          "frac": r["q1"]["hbm_frac"],
-                                          # ncu dram__bytes_read.sum of one launch over the 10^7-row DB = 1.280 GB,
-                                          # exactly the algorithmic bytes (profiles/r1_topk_ncu_summary.md)
-                                          "traffic": 1.28e9 if args.db_rows == 10000000 else None}
-            line["piece_identification"] = piece_id_leg(torch, dev, rank, world)
-        except Exception as ex:  # report, never hide
-            line["retrieval_error"] = repr(ex)
-    if rank == 0 and world == 1 and not args.skip_extras:
+        legs = [
+            ("retrieval_sweep", lambda: retrieval_sweep_leg(
+                torch, dist, dev, pk, rank, world,
+                [r for r in (100000, 1000000, 10000000, 100000000) if r <= args.sweep_max_rows], quick=args.quick)),
+            ("piece_identification", lambda: piece_id_leg(torch, dist, dev, rank, world, with_cpu, quick=args.quick)),
+            ("config3_refit", lambda: config3_leg(torch, dist, dev, rank, world, with_cpu)),
+        ]
+        if world == 1:
+            legs.append(("config1_rsz_eval", lambda: config1_leg(torch, dev, with_cpu)))
+        for name, fn in legs:
+            try:
+                line[name] = fn()
+            except Exception as ex:  # report, never hide
+                line[name + "_error"] = repr(ex)
+        sw = line.get("retrieval_sweep")
+        if sw:
+            big = [c for c in sw["cells"] if c["q"] == 1]
+            if big:
+                top = max(big, key=lambda c: c["rows"])
+                line["roofline_retrieval"] = {"bound": "hbm", "kernel": "topk_stream_kernel (Q=1, k=25, %d-row fp32 DB over %d GPU(s))"
+                                                                        % (top["rows"], world),
+                                              "achieved": top["algorithmic_gbs"], "peak": pk["hbm_gbs"] * world, "unit": "GB/s",
+                                              "frac": top["hbm_frac"],
+                                              "traffic": None, "traffic_note": "ncu dram__bytes_read.sum of one launch over a 10^7-row DB = "
+                                              "1.280 GB = the algorithmic bytes (profiles/r1_topk_ncu_summary.md)"}
+    if with_cpu and not args.skip_extras:
         try:
             cpu_n = args.cpu_sample or 4096             # ~10-15 s of CPU work on 16 cores
             cpu_reference_pairs_per_s(128, steps=1, warmup=0)   # warm the thread pool / allocator on a small sample
-            v, dt_cpu, cores = cpu_reference_pairs_per_s(cpu_n, steps=1, warmup=0)
+            v, dt_cpu, cores = cpu_reference_pairs_per_s(cpu_n, steps=1, warmup=0, chunk=mb)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "%d pairs (%.1f s), torch-CPU fp32 oracle port of the reference path" % (cpu_n, dt_cpu)}
+                                    "sample": "%d pairs (%.1f s), torch-CPU fp32 oracle port of the reference path, the generator "
+                                              "of the GPU arm" % (cpu_n, dt_cpu)}
         except Exception as ex:
             line["cpu_baseline"] = {"error": repr(ex)}
     if rank == 0:
