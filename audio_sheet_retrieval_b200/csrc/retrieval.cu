@@ -385,7 +385,7 @@ topk_merge_kernel(const float *__restrict__ in_s, const uint32_t *__restrict__ i
 // every candidate becomes a unique 64-bit key (order-preserving score bits | ~row: larger = better, i.e. score
 // descending then row ascending), each thread keeps its keys in registers, an 8-pass byte-wise radix select finds
 // the k-th largest key exactly, and the k survivors are ranked by counting.  Deterministic, no overflow case.
-constexpr int MS_THREADS = 1024, MS_KPT = 12;     // up to 12288 candidates per query
+constexpr int MS_THREADS = 1024;                  // MS_KPT keys per thread: 12 (<= 12288 candidates per query) or 16 (<= 16384)
 __device__ __forceinline__ uint32_t f2ord(float f) {
     const uint32_t u = __float_as_uint(f);
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
@@ -393,6 +393,7 @@ __device__ __forceinline__ uint32_t f2ord(float f) {
 __device__ __forceinline__ float ord2f(uint32_t o) {
     return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
 }
+template <int MS_KPT>
 __global__ void __launch_bounds__(MS_THREADS)
 topk_merge_select_kernel(const float *__restrict__ in_s, const uint32_t *__restrict__ in_i32, int64_t idx_base, int n_cand,
                          int k, float *__restrict__ out_s, int64_t *__restrict__ out_i) {
@@ -492,8 +493,13 @@ topk_merge_select_kernel(const float *__restrict__ in_s, const uint32_t *__restr
 // few queries over many per-slice lists: radix-select merge; otherwise the 4-warp fold
 static void launch_merge(const float *in_s, const uint32_t *in_i32, const int64_t *in_i64, int64_t idx_base, int n_lists, int k,
                          float *out_s, int64_t *out_i, int64_t nq, cudaStream_t st) {
-    if (in_i32 && nq <= 8 && n_lists >= 64 && (int64_t)n_lists * k <= (int64_t)MS_THREADS * MS_KPT) {
-        topk_merge_select_kernel<<<(unsigned)nq, MS_THREADS, 0, st>>>(in_s, in_i32, idx_base, n_lists * k, k, out_s, out_i);
+    const int64_t n_cand = (int64_t)n_lists * k;
+    if (in_i32 && nq <= 8 && n_lists >= 64 && n_cand <= (int64_t)MS_THREADS * 12) {
+        topk_merge_select_kernel<12><<<(unsigned)nq, MS_THREADS, 0, st>>>(in_s, in_i32, idx_base, (int)n_cand, k, out_s, out_i);
+    } else if (in_i32 && nq <= 256 && n_lists >= 64 && n_cand <= (int64_t)MS_THREADS * 16) {
+        // few queries over very many lists (the pre-filter's lists per column range x slices): the fold below is a
+        // chain of dependent passes per list, the radix select is one pass over the candidates
+        topk_merge_select_kernel<16><<<(unsigned)nq, MS_THREADS, 0, st>>>(in_s, in_i32, idx_base, (int)n_cand, k, out_s, out_i);
     } else {
         const size_t smem = (size_t)4 * 2 * k * (sizeof(int64_t) + sizeof(float));
         topk_merge_kernel<4><<<(unsigned)nq, 4 * 32, smem, st>>>(in_s, in_i32, in_i64, idx_base, n_lists, k, out_s, out_i,
@@ -664,12 +670,21 @@ constexpr int TC_QM = 128;
 constexpr int TC_ROWS = 256;
 constexpr int TC_STAGES = 3;
 constexpr int TC_KMAX = 32;
-constexpr int TC_THREADS = 192;      // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue (one query per thread)
+constexpr int TC_EPI_WARPS = 8;      // two per TMEM lane quarter (column halves)
+constexpr int TC_THREADS = 32 * (2 + TC_EPI_WARPS);   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+
+constexpr int TC_LSTRIDE = TC_KMAX + 1;   // list stride in keys: odd, so that the same position of different lists hits different banks
+constexpr int TC_QCAP = 64;               // candidate queue entries per epilogue warp (drained 32 at a time)
 
 struct TcSmem {
     float stage[TC_STAGES][TC_ROWS * 32];     // normalised DB rows, SWIZZLE_128B (written by TMA)
     float q[TC_QM * 32];                      // normalised queries, same swizzle (written by threads)
-    unsigned short cand[16][TC_QM];           // pending-candidate masks: [16-column group][query]
+    unsigned short cand[16][TC_QM];           // pending-candidate masks of the current tile: [16-column group][TMEM lane]
+    unsigned long long lists[2 * TC_QM * TC_LSTRIDE];   // sorted top-k list of every epilogue thread (column half, TMEM lane) as 64-bit keys
+    unsigned long long floor_key[2 * TC_QM];  // threshold floor of the list (first-tile bisection)
+    float tau[2 * TC_QM];                     // approximate-score filter threshold of the list
+    uint32_t cq_row[TC_EPI_WARPS][TC_QCAP];   // candidate queues: DB row ...
+    unsigned char cq_lane[TC_EPI_WARPS][TC_QCAP];   // ... and the lane (within the warp) whose list it is for
     uint64_t full[TC_STAGES], empty[TC_STAGES], tfull[2], tempty[2];
     uint32_t tmem_ptr;
     unsigned item;
@@ -740,21 +755,98 @@ __device__ __forceinline__ float tc_exact_score(const float *qsm, const float *s
     return (acc != acc) ? -CUDART_INF_F : acc;
 }
 
+// exact pinned-order score of query row `ql` (swizzled smem tile) against a normalised DB row in global memory
+__device__ __forceinline__ float tc_exact_score_g(const float *qsm, const float *__restrict__ drow, int ql) {
+    float acc = 0.f;
+    const float4 *qp = reinterpret_cast<const float4 *>(qsm + ql * 32);
+    const float4 *dp = reinterpret_cast<const float4 *>(drow);
+    float4 b[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) b[c] = __ldg(dp + c);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float4 a = qp[c ^ (ql & 7)];
+        acc = __fadd_rn(acc, __fmul_rn(a.x, b[c].x));
+        acc = __fadd_rn(acc, __fmul_rn(a.y, b[c].y));
+        acc = __fadd_rn(acc, __fmul_rn(a.z, b[c].z));
+        acc = __fadd_rn(acc, __fmul_rn(a.w, b[c].w));
+    }
+    return (acc != acc) ? -CUDART_INF_F : acc;
+}
+
+// Drain `n` (<= 32) queued candidates of one epilogue warp, ONE PER LANE: exact score (the row comes back from L2,
+// where the TMA load of its tile just put it), then insertion into the owner lane's sorted list in shared memory.
+// Lanes whose candidates belong to the same list take turns (lowest lane first); lists of different lanes are
+// independent, so a round inserts up to 32 candidates at once.
+// gkey[q]: fkey of a LOWER BOUND of query q's final k-th best exact score, shared by every list of the query on this
+// GPU (other DB slices, column halves, lane copies): each list publishes its own k-th best with atomicMax as soon as it
+// holds k real entries.  A row scoring strictly below the bound cannot be in the query's top-k, so every list filters
+// with the best bound anybody has found -- the per-item threshold warm-up (k ln(rows / k) insertions per list) is paid
+// about once per query instead of once per list.
+__device__ __forceinline__ void tc_drain(TcSmem &sm, const float *__restrict__ rows, int n, int ew, int quarter, int lbase, int k,
+                                         float eps, int lane, unsigned *__restrict__ gkey, int q0, int nqt_mask) {
+    const bool have = lane < n;
+    int owner = 64 + lane;                                   // distinct dummy owners for idle lanes
+    unsigned long long key = 0ull;
+    bool todo = false;
+    if (have) {
+        owner = sm.cq_lane[ew][lane];
+        const uint32_t row = sm.cq_row[ew][lane];
+        const int ql = quarter * 32 + owner;
+        const float sc = tc_exact_score_g(sm.q, rows + (size_t)row * 32, ql);
+        key = ((unsigned long long)fkey(sc) << 32) | (unsigned long long)(~row);
+        const unsigned long long kth = sm.lists[(lbase + owner) * TC_LSTRIDE + k - 1], fl = sm.floor_key[lbase + owner];
+        todo = key > (kth > fl ? kth : fl) && fkey(sc) >= __ldcg(gkey + q0 + (ql & nqt_mask));
+    }
+    while (__any_sync(0xffffffffu, todo)) {
+        const unsigned peers = __match_any_sync(0xffffffffu, todo ? owner : 64 + lane);
+        if (todo && (int)(__ffs(peers) - 1) == lane) {
+            unsigned long long *l = sm.lists + (lbase + owner) * TC_LSTRIDE;
+            if (key > l[k - 1]) {                            // an earlier round may have raised the k-th entry
+                int j = k - 1;
+                for (; j > 0; --j) {
+                    const unsigned long long up = l[j - 1];
+                    if (up > key) break;
+                    l[j] = up;
+                }
+                l[j] = key;
+                const unsigned long long kth = l[k - 1], fl = sm.floor_key[lbase + owner];
+                sm.tau[lbase + owner] = fkey_inv((uint32_t)((kth > fl ? kth : fl) >> 32)) - eps;
+                if ((uint32_t)kth != 0u)                     // a real k-th entry (empty slots have lo = 0): publish the bound
+                    atomicMax(gkey + q0 + ((quarter * 32 + owner) & nqt_mask), (unsigned)(kth >> 32));
+            }
+            todo = false;
+        }
+        __syncwarp();
+    }
+}
+
 // Persistent 1-D grid; work items (query tile, DB slice) are handed out by an atomic counter so that
-// any (nq, n_db) shape fills all SMs.  qn = normalised queries (nq,32); tmap over the normalised DB copy.
+// any (nq, n_db) shape fills all SMs.  qn = normalised queries (nq,32); tmap over the normalised DB rows.
+//
+// Epilogue layout.  A score tile is 128 TMEM lanes x 256 columns (DB rows).  Reading it out of TMEM and scanning it
+// bounds this kernel, and with one warp per lane quarter that is a latency-bound chain.  EIGHT epilogue warps share a
+// tile: the two warps of a lane quarter scan one half of the columns each, and for <= 64 queries the query tile is
+// REPLICATED over the lane quarters (rep = 2) so that no lane idles.  Every (TMEM lane, column half) thread owns a
+// sorted top-k list in SHARED memory; rows that pass the approximate filter go through a per-warp candidate queue and
+// are re-scored exactly / inserted 32 at a time, one candidate per lane, whichever list it belongs to (the old
+// thread-owns-its-list-in-registers form spent 2/3 of its instructions in a lock-step loop with ~1 active lane).
+// At item end the L = 2 * rep lists of a query are merged by rank counting.
 __global__ void __launch_bounds__(TC_THREADS, 1)
 topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles_per_slice, int n_slices,
-               const float *__restrict__ qn, int nq, int k, float eps, float *__restrict__ part_s,
-               uint32_t *__restrict__ part_i, unsigned *__restrict__ work_counter, float *dbg) {
+               const float *__restrict__ rows, const float *__restrict__ qn, int nq, int k, float eps, int rep,
+               float *__restrict__ part_s, uint32_t *__restrict__ part_i, unsigned *__restrict__ work_counter,
+               unsigned *__restrict__ gkey, float *dbg) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     TcSmem &sm = *reinterpret_cast<TcSmem *>(smem_raw);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // provably warp-uniform: uniform role branches
     if (smem_u32(smem_raw) & 1023u) __trap();
     const int64_t n_tiles = (n_db + TC_ROWS - 1) / TC_ROWS;
 
     if (tid == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 4); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&sm.tfull[s], 1); mbar_init(&sm.tempty[s], 4); }
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&sm.tfull[s], 1); mbar_init(&sm.tempty[s], TC_EPI_WARPS); }
         mbar_fence_init();
         tma_prefetch_desc(&tmap);
     }
@@ -766,7 +858,10 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles
     // kind::tf32: a/b format 2 (TF32), fp32 accumulate, K-major both, M = 128, N = 256
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_ROWS >> 3) << 17) | ((uint32_t)(TC_QM >> 4) << 24);
 
-    const int n_qt = (nq + TC_QM - 1) / TC_QM;
+    const int nqt = TC_QM / rep;                     // distinct queries per tile
+    const int L = 2 * rep;                           // lists per (query, item): rep lane copies x 2 column halves
+    const int ncols = TC_ROWS / L;                   // columns per epilogue thread: 128 or 64
+    const int n_qt = (nq + nqt - 1) / nqt;
     const unsigned n_items = (unsigned)n_qt * (unsigned)n_slices;
     int64_t itg = 0;                 // running tile counter (barrier phases continue across work items)
     for (;;) {
@@ -780,12 +875,13 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles
         int64_t my_tiles = n_tiles - tile0;
         if (my_tiles > tiles_per_slice) my_tiles = tiles_per_slice;
         if (my_tiles < 0) my_tiles = 0;
-        const int q0 = qt * TC_QM;
-        // stage the query tile, swizzled like a SWIZZLE_128B TMA load; rows beyond nq are zero
+        const int q0 = qt * nqt;
+        // stage the query tile (rep copies), swizzled like a SWIZZLE_128B TMA load; rows beyond nq are zero
         for (int i = tid; i < TC_QM * 8; i += TC_THREADS) {
             const int row = i >> 3, c = i & 7;
+            const int qi = row & (nqt - 1);
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (q0 + row < nq) v = *reinterpret_cast<const float4 *>(qn + (int64_t)(q0 + row) * 32 + c * 4);
+            if (q0 + qi < nq) v = *reinterpret_cast<const float4 *>(qn + (int64_t)(q0 + qi) * 32 + c * 4);
             *reinterpret_cast<float4 *>(sm.q + row * 32 + ((c ^ (row & 7)) << 2)) = v;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA (async proxy)
@@ -818,48 +914,50 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles
                         tc_mma_tf32(tmem_base + slot * 256u, umma_desc_sw128(qaddr + kk * 32), umma_desc_sw128(baddr + kk * 32),
                                     idesc, kk ? 1u : 0u);
                     tc_commit(&sm.tfull[slot]);
+                    tc_commit(&sm.empty[s]);       // the stage is only the MMA's B operand: candidates are re-read from L2
                 }
                 __syncwarp();
             }
         } else {
-            const int quarter = warp & 3;
-            const int ql = quarter * 32 + lane;
-            const bool qvalid = q0 + ql < nq;
-            // The query's sorted top-k list lives in REGISTERS (k <= 32, all indexing static) as 64-bit
-            // keys (hi = order-preserving map of the exact score, lo = ~row): one unsigned 64-bit compare
-            // is exactly "score desc, index asc".  Empty slots hold the smallest key (-inf, row 0xffffffff),
-            // which loses to every real row (a NaN row scores -inf but has a smaller index).
-            uint32_t kh[TC_KMAX], kl[TC_KMAX];
-            const uint32_t NEG_INF_KEY = 0x007fffffu;     // fkey(-inf)
-#pragma unroll
-            for (int j = 0; j < TC_KMAX; ++j) { kh[j] = NEG_INF_KEY; kl[j] = 0u; }
-            // (thr_h, thr_l): a row must beat this key to enter the list; tau: rows whose APPROXIMATE score
-            // is below tau cannot beat it.  Both start from a floor found on the first tile (below).
-            uint32_t thr_h = NEG_INF_KEY, thr_l = 0u;
-            float tau = -CUDART_INF_F;
+            const int quarter = warp & 3;                       // TMEM lane quarter this warp may read
+            const int ql = quarter * 32 + lane;                 // TMEM lane = row of the (replicated) query tile
+            const int qi = ql & (nqt - 1);                      // query within the tile
+            const int hsel = (warp - 2) >> 2;                   // which of the two warps of this lane quarter
+            const int sub = (ql / nqt) * 2 + hsel;              // which of the L column ranges of that query
+            const int li = hsel * TC_QM + ql;                   // this thread's list
+            const int col0 = sub * ncols;
+            const bool qvalid = q0 + qi < nq;
+            const int ew = warp - 2;
+            // The sorted top-k list of every lane lives in SHARED memory as 64-bit keys (hi = order-preserving map of
+            // the exact score, lo = ~row: one unsigned compare is exactly "score desc, index asc"; empty slots hold the
+            // smallest key, (-inf, row 0xffffffff)).  Pass 1 scans the approximate scores against the lane's tau;
+            // what passes goes into the warp's candidate queue and is re-scored / inserted 32 at a time (tc_drain).
+            const unsigned long long NEG_KEY = (unsigned long long)0x007fffffu << 32;      // (fkey(-inf), 0)
+            for (int j = 0; j < k; ++j) sm.lists[li * TC_LSTRIDE + j] = NEG_KEY;
+            sm.floor_key[li] = NEG_KEY;
+            sm.tau[li] = -CUDART_INF_F;
+            __syncwarp();
+            int qcount = 0;                                      // warp-uniform
             for (int64_t it = 0; it < my_tiles; ++it) {
                 const int64_t g = itg + it;
-                const int s = (int)(g % TC_STAGES);
                 const uint32_t slot = (uint32_t)(g & 1);
                 mbar_wait(&sm.tfull[slot], (uint32_t)((g >> 1) & 1));
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + slot * 256u + ((uint32_t)(quarter * 32) << 16);
+                const uint32_t taddr = tmem_base + slot * 256u + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col0;
                 const int64_t row0 = (tile0 + it) * TC_ROWS;
-                const float *stage = sm.stage[s];
-                if (it == 0 && row0 + TC_ROWS <= n_db) {
-                    // Threshold floor from the first (full) tile: bisect for a value `lo` such that at least k
-                    // of its 256 approximate scores are >= lo.  Those k rows have exact scores >= lo - eps,
-                    // so the final k-th best is >= lo - eps: a valid floor that removes the warm-up, where
-                    // every row would otherwise be scored exactly and inserted.
+                if (it == 0 && row0 + TC_ROWS <= n_db && ncols >= k) {
+                    // Threshold floor from the first (full) tile: bisect for a value `lo` such that at least k of this
+                    // lane's approximate scores are >= lo.  Those k rows have exact scores >= lo - eps, so the final
+                    // k-th best of this list is >= lo - eps: a valid floor that removes most of the warm-up.
                     float lo = -2.0f, hi = 2.0f;
 #pragma unroll 1
                     for (int iter = 0; iter < 12; ++iter) {
                         const float mid = 0.5f * (lo + hi);
                         int cnt = 0;
 #pragma unroll 1
-                        for (int g4 = 0; g4 < 4; ++g4) {
+                        for (int c64 = 0; c64 < ncols; c64 += 64) {
                             float v[64];
-                            tmem_ld64(taddr + (uint32_t)(g4 * 64), v);
+                            tmem_ld64(taddr + (uint32_t)c64, v);
 #pragma unroll
                             for (int j = 0; j < 64; ++j) cnt += v[j] >= mid ? 1 : 0;
                         }
@@ -867,100 +965,135 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles
                     }
                     if (lo > -2.0f) {          // found (queries of all-NaN / degenerate tiles keep -inf)
                         const float floor_s = lo - eps;
-                        thr_h = fkey(floor_s);
-                        thr_l = 0u;            // ties with the floor itself still enter (row index < 0xffffffff)
-                        tau = floor_s - eps;
+                        sm.floor_key[li] = (unsigned long long)fkey(floor_s) << 32;   // ties with the floor itself still enter
+                        sm.tau[li] = floor_s - eps;
                     }
                 }
-                // Pass 1 (cheap, converged): scan the 256 approximate scores, 64 columns per TMEM round trip,
-                // and remember which columns pass the filter as 16-bit masks in shared memory.  NaN
-                // approximations (zero DB rows) need no special case: they can only matter while tau is
-                // -inf, and then !(x < tau) is true for every x.
+                // the best bound anybody on this GPU has published for this query (read from L2 once per tile)
+                const float gtau = qvalid ? fkey_inv(__ldcg(gkey + q0 + qi)) - eps : -CUDART_INF_F;
+                const float tau = fmaxf(sm.tau[li], gtau);
+                // Pass 1: scan this lane's approximate scores, 64 columns per TMEM round trip, and remember which
+                // columns pass the filter as 16-bit masks.  NaN approximations (zero DB rows) need no special case:
+                // they can only matter while tau is -inf, and then !(x < tau) is true for every x.
                 unsigned pend = 0u;
-#pragma unroll 1
-                for (int g4 = 0; g4 < 4; ++g4) {
-                    float v[64];
-                    tmem_ld64(taddr + (uint32_t)(g4 * 64), v);
+                // software pipeline over the 64-column chunks: the TMEM round trip of chunk c + 1 runs under the scan of c
+                auto scan = [&](const uint32_t *vr, int c64) {
                     if (dbg && slice == 0 && qt == 0 && it == 0) {      // debug: dump the approximate scores of tile 0
 #pragma unroll
-                        for (int j = 0; j < 64; ++j) dbg[ql * TC_ROWS + g4 * 64 + j] = v[j];
+                        for (int j = 0; j < 64; ++j) dbg[qi * TC_ROWS + col0 + c64 + j] = __uint_as_float(vr[j]);
                     }
                     float m[4];
 #pragma unroll
-                    for (int sub = 0; sub < 4; ++sub) {
-                        m[sub] = v[sub * 16];
+                    for (int sb = 0; sb < 4; ++sb) {
+                        m[sb] = __uint_as_float(vr[sb * 16]);
 #pragma unroll
-                        for (int j = 1; j < 16; ++j) m[sub] = fmaxf(m[sub], v[sub * 16 + j]);
+                        for (int j = 1; j < 16; ++j) m[sb] = fmaxf(m[sb], __uint_as_float(vr[sb * 16 + j]));
                     }
                     const float mm = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
                     if (qvalid && !(mm < tau)) {
 #pragma unroll
-                        for (int sub = 0; sub < 4; ++sub) {
-                            if (!(m[sub] < tau)) {
-                                unsigned mask = 0u;        // static indexing keeps v[] in registers
+                        for (int sb = 0; sb < 4; ++sb) {
+                            if (!(m[sb] < tau)) {
+                                unsigned mask = 0u;        // static indexing keeps the chunk in registers
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) mask |= !(v[sub * 16 + j] < tau) ? (1u << j) : 0u;
-                                sm.cand[g4 * 4 + sub][ql] = (unsigned short)mask;
-                                pend |= 1u << (g4 * 4 + sub);
+                                for (int j = 0; j < 16; ++j) mask |= !(__uint_as_float(vr[sb * 16 + j]) < tau) ? (1u << j) : 0u;
+                                const int g16 = (col0 + c64) / 16 + sb;
+                                sm.cand[g16][ql] = (unsigned short)mask;
+                                pend |= 1u << ((c64 / 16) + sb);          // bit = 16-column group within this lane's range
                             }
                         }
                     }
-                }
-                // Pass 2 (rare): the lanes that have candidates drain them in lockstep, one candidate per
-                // lane per iteration, so the cost is the maximum (not the sum) over the warp's lanes.
-                while (__any_sync(0xffffffffu, pend != 0u)) {
-                    if (pend) {
-                        const int gq = __ffs(pend) - 1;
-                        unsigned mask = sm.cand[gq][ql];
-                        const int j = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        sm.cand[gq][ql] = (unsigned short)mask;
-                        if (!mask) pend &= ~(1u << gq);
-                        const int r = gq * 16 + j;
-                        const int64_t row = row0 + r;
-                        if (row < n_db) {
-                            uint32_t ch = fkey(tc_exact_score(sm.q, stage, ql, r));
-                            uint32_t cl = ~(uint32_t)row;
-                            if (key_gt(ch, cl, thr_h, thr_l)) {
-                                // bubble the candidate through the sorted list: whoever loses moves on
-#pragma unroll
-                                for (int jj = 0; jj < TC_KMAX; ++jj) {
-                                    if (jj < k) {
-                                        const bool b = key_gt(ch, cl, kh[jj], kl[jj]);
-                                        const uint32_t th = b ? kh[jj] : ch, tl = b ? kl[jj] : cl;
-                                        kh[jj] = b ? ch : kh[jj];
-                                        kl[jj] = b ? cl : kl[jj];
-                                        ch = th;
-                                        cl = tl;
-                                    }
-                                }
-                                uint32_t lh = NEG_INF_KEY, ll = 0u;      // the list's k-th entry
-#pragma unroll
-                                for (int jj = 0; jj < TC_KMAX; ++jj)
-                                    if (jj == k - 1) { lh = kh[jj]; ll = kl[jj]; }
-                                if (key_gt(lh, ll, thr_h, thr_l)) {       // thresholds only ever rise
-                                    thr_h = lh;
-                                    thr_l = ll;
-                                    tau = fkey_inv(lh) - eps;
-                                }
-                            }
+                };
+                {
+                    uint32_t va[64], vb[64];
+                    tmem_ld64_issue(taddr, va);
+#pragma unroll 1
+                    for (int c64 = 0; c64 < ncols; c64 += 128) {
+                        tmem_ld_wait();
+                        if (c64 + 64 < ncols) tmem_ld64_issue(taddr + (uint32_t)(c64 + 64), vb);
+                        scan(va, c64);
+                        if (c64 + 64 < ncols) {
+                            tmem_ld_wait();
+                            if (c64 + 128 < ncols) tmem_ld64_issue(taddr + (uint32_t)(c64 + 128), va);
+                            scan(vb, c64 + 64);
                         }
                     }
                 }
+                // the accumulator slot is free again as soon as every epilogue warp has scanned it
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(&sm.tempty[slot]); mbar_arrive(&sm.empty[s]); }
-            }
-            if (qvalid) {
-                const size_t o = ((size_t)(q0 + ql) * n_slices + slice) * k;
-#pragma unroll
-                for (int j = 0; j < TC_KMAX; ++j)
-                    if (j < k) {
-                        const bool real = !(kh[j] == NEG_INF_KEY && kl[j] == 0u);
-                        part_s[o + j] = real ? fkey_inv(kh[j]) : -CUDART_INF_F;
-                        part_i[o + j] = real ? ~kl[j] : 0xffffffffu;
+                if (lane == 0) mbar_arrive(&sm.tempty[slot]);
+                // Pass 2: move the candidates into the warp's queue (one per lane per round, a handful of instructions),
+                // draining 32 of them whenever that many are waiting.
+                while (__any_sync(0xffffffffu, pend != 0u)) {
+                    bool have = false;
+                    uint32_t row = 0u;
+                    if (pend) {
+                        const int gq = __ffs(pend) - 1;
+                        const int g16 = col0 / 16 + gq;
+                        unsigned mask = sm.cand[g16][ql];
+                        const int j = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        sm.cand[g16][ql] = (unsigned short)mask;
+                        if (!mask) pend &= ~(1u << gq);
+                        const int64_t r = row0 + g16 * 16 + j;
+                        have = r < n_db;
+                        row = (uint32_t)r;
                     }
+                    const unsigned bal = __ballot_sync(0xffffffffu, have);
+                    if (have) {
+                        const int pos = qcount + __popc(bal & ((1u << lane) - 1u));
+                        sm.cq_row[ew][pos] = row;
+                        sm.cq_lane[ew][pos] = (unsigned char)lane;
+                    }
+                    qcount += __popc(bal);
+                    __syncwarp();
+                    if (qcount >= 32) {
+                        tc_drain(sm, rows, 32, ew, quarter, hsel * TC_QM + quarter * 32, k, eps, lane, gkey, q0, nqt - 1);
+                        qcount -= 32;
+                        const uint32_t mr = sm.cq_row[ew][32 + lane];          // move the remainder (< 32 entries) to the front
+                        const unsigned char ml = sm.cq_lane[ew][32 + lane];
+                        __syncwarp();
+                        if (lane < qcount) { sm.cq_row[ew][lane] = mr; sm.cq_lane[ew][lane] = ml; }
+                        __syncwarp();
+                    }
+                }
+                // thresholds only ever rise, so a drain may be deferred; it must happen before the lists are read
+                if (qcount && (it + 1 == my_tiles || (it & 7) == 7)) {
+                    tc_drain(sm, rows, qcount, ew, quarter, hsel * TC_QM + quarter * 32, k, eps, lane, gkey, q0, nqt - 1);
+                    qcount = 0;
+                }
             }
+            // Item end: the rep lanes that served the same query merge their sorted lists by RANK COUNTING -- the merged
+            // position of an entry is its own index plus the number of entries of the other lists that beat it (binary
+            // search; keys are unique, so positions are too) -- and every lane writes its survivors straight to the
+            // item's single output list.
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+            if (qvalid) {
+                const size_t o = ((size_t)(q0 + qi) * n_slices + slice) * k;
+                const unsigned long long *ml = sm.lists + li * TC_LSTRIDE;
+                for (int j = 0; j < k; ++j) {
+                    const unsigned long long mine = ml[j];
+                    int rank = j;
+                    for (int t = 0; t < L; ++t) {
+                        const int other = (t & 1) * TC_QM + qi + (t >> 1) * nqt;
+                        if (other == li) continue;
+                        const unsigned long long *ol = sm.lists + other * TC_LSTRIDE;
+                        int lo = 0, hi = k;                   // number of entries of `ol` (sorted descending) greater than mine
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if (ol[mid] > mine) lo = mid + 1; else hi = mid;
+                        }
+                        rank += lo;
+                    }
+                    if (rank < k) {
+                        const bool real = mine != NEG_KEY;
+                        part_s[o + rank] = real ? fkey_inv((uint32_t)(mine >> 32)) : -CUDART_INF_F;
+                        part_i[o + rank] = real ? ~(uint32_t)mine : 0xffffffffu;
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");   // lists[] free for the next item
         }
         itg += my_tiles;
         __syncthreads();     // every role is done with sm.q / the lists before the next query tile
@@ -1218,34 +1351,38 @@ static int topk_tc(asr_db *db, const float *q_dev, int64_t nq, int k, float *out
     }
     normalise_rows_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(q_dev, nq, db->qn);
     ASR_LAUNCH_CHECK();
-    // slices: enough (query tile, slice) items to balance the persistent grid, but never shorter than
-    // 128 tiles (32k rows) so the per-item threshold warm-up stays negligible
+    // Replicate few queries over the TMEM lane quarters so that all eight epilogue warps share a score tile.
+    // (measured, 1e7 rows: 32 queries 1.01 ms replicated vs 1.07 ms not; 64 queries 1.40 vs 1.12 ms)
+    const int rep = getenv("ASR_TC_REP") ? std::min(2, std::max(1, atoi(getenv("ASR_TC_REP")))) : (nq <= 32 ? 2 : 1);
+    const int nqt = TC_QM / rep, L = 1;           // one list per (query, slice): the column ranges are merged in-kernel
+    // Work items = (query tile, DB slice), ~2 per SM (1 when there are only a few query tiles: every slice adds a list
+    // per query to the merge).  Since the lists of a query share their threshold bound (gkey), short items are cheap:
+    // 10k queries x 125k rows (one shard of an 8-GPU DB) 2.94 -> 1.79 ms, 10k x 1M 7.0 -> 5.2 ms with the sharing.
     const int64_t n_tiles = (db->n + TC_ROWS - 1) / TC_ROWS;
-    const int64_t n_qt_all = (nq + TC_QM - 1) / TC_QM;
-    // Every (query tile, slice) item pays a threshold warm-up (about k*ln(rows/256) exact re-scorings per
-    // query), so items should be long.  Many query tiles: slices of >= 1024 tiles, ~2 items per SM
-    // (measured best for 10k queries x 1M rows).  Few query tiles: the DB must be sliced to fill the SMs.
-    const bool many_q = n_qt_all * 2 >= db->sms;
-    const int items_per_sm = getenv("ASR_TC_ITEMS_PER_SM") ? atoi(getenv("ASR_TC_ITEMS_PER_SM")) : (many_q ? 2 : 1);
-    const int min_tiles = getenv("ASR_TC_MIN_TILES") ? atoi(getenv("ASR_TC_MIN_TILES")) : (many_q ? 1024 : 128);
+    const int64_t n_qt_all = (nq + nqt - 1) / nqt;
+    const int items_per_sm = getenv("ASR_TC_ITEMS_PER_SM") ? atoi(getenv("ASR_TC_ITEMS_PER_SM")) : (n_qt_all >= 8 ? 2 : 1);
+    const int min_tiles = getenv("ASR_TC_MIN_TILES") ? atoi(getenv("ASR_TC_MIN_TILES")) : (n_qt_all >= 8 ? 64 : 32);
     int64_t want = std::max<int64_t>(1, (items_per_sm * (int64_t)db->sms + n_qt_all - 1) / n_qt_all);
     want = std::min<int64_t>(want, std::max<int64_t>(1, n_tiles / min_tiles));
     const int tps = (int)((n_tiles + want - 1) / want);
     const int n_slices = (int)((n_tiles + tps - 1) / tps);
-    const int64_t per_q = (int64_t)n_slices * k * 8;
-    const int64_t q_chunk = std::max<int64_t>(TC_QM, (int64_t)((TK_SCRATCH_BYTES - 256) / per_q) / TC_QM * TC_QM);
+    const int64_t per_q = (int64_t)n_slices * L * k * 8;
+    const int64_t q_chunk = std::max<int64_t>(nqt, (int64_t)((TK_SCRATCH_BYTES - 256 - (db->qn_cap + 64) * 4) / per_q) / nqt * nqt);
     unsigned *counter = reinterpret_cast<unsigned *>(reinterpret_cast<uint8_t *>(db->scratch) + TK_SCRATCH_BYTES - 256);
+    // per-query bound shared by all lists of the query (see tc_drain): the last qn_cap words of the scratch before the counter
+    unsigned *gkey = counter - ((db->qn_cap + 63) / 64 * 64);
+    ASR_CUDA(cudaMemsetAsync(gkey, 0, (size_t)nq * sizeof(unsigned), st));        // 0 = below fkey(-inf): no bound yet
     for (int64_t q0 = 0; q0 < nq; q0 += q_chunk) {
         const int64_t nqc = std::min<int64_t>(q_chunk, nq - q0);
-        const int64_t n_qt = (nqc + TC_QM - 1) / TC_QM;
+        const int64_t n_qt = (nqc + nqt - 1) / nqt;
         float *ps = reinterpret_cast<float *>(db->scratch);
-        uint32_t *pi = reinterpret_cast<uint32_t *>(ps + (size_t)nqc * n_slices * k);
+        uint32_t *pi = reinterpret_cast<uint32_t *>(ps + (size_t)nqc * n_slices * L * k);
         ASR_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
         const int grid = (int)std::min<int64_t>(db->sms, n_qt * n_slices);
-        topk_tc_kernel<<<grid, TC_THREADS, sizeof(TcSmem), st>>>(db->tmap_n, db->n, tps, n_slices, db->qn + q0 * 32, (int)nqc,
-                                                                 k, 0.00390625f, ps, pi, counter, g_tc_dbg);
+        topk_tc_kernel<<<grid, TC_THREADS, sizeof(TcSmem), st>>>(db->tmap_n, db->n, tps, n_slices, db->rows_n, db->qn + q0 * 32,
+                                                                 (int)nqc, k, 0.00390625f, rep, ps, pi, counter, gkey + q0, g_tc_dbg);
         ASR_LAUNCH_CHECK();
-        launch_merge(ps, pi, nullptr, db->idx_base, n_slices, k, out_score_dev + q0 * k, out_idx_dev + q0 * k, nqc, st);
+        launch_merge(ps, pi, nullptr, db->idx_base, n_slices * L, k, out_score_dev + q0 * k, out_idx_dev + q0 * k, nqc, st);
         ASR_LAUNCH_CHECK();
     }
     return ASR_OK;
@@ -1268,7 +1405,9 @@ int asr_topk(asr_db_t *db, const float *q_dev, int64_t nq, int k, int normalise,
     DeviceGuard guard(db->device);
     ASR_CHECK_ARG(normalise || !(db->flags & ASR_DB_NORMALISE_IN_PLACE),
                   "the raw rows are gone: this DB was created with ASR_DB_NORMALISE_IN_PLACE");
-    const bool want_tc = force ? (strcmp(force, "tc") == 0) : (nq > 24 && (double)nq * (double)db->n >= 1.6e8);
+    static const int tc_min_q = getenv("ASR_TC_MIN_Q") ? atoi(getenv("ASR_TC_MIN_Q")) : 12;
+    static const double tc_min_scores = getenv("ASR_TC_MIN_SCORES") ? atof(getenv("ASR_TC_MIN_SCORES")) : 1.0e8;
+    const bool want_tc = force ? (strcmp(force, "tc") == 0) : (nq >= tc_min_q && (double)nq * (double)db->n >= tc_min_scores);
     if (want_tc && normalise && k <= TC_KMAX && db->rows_n) return topk_tc(db, q_dev, nq, k, out_score_dev, out_idx_dev, st);
     // cosine queries stream the pinned-normalised rows (kernel flag bit 0: normalise queries, bit 1: normalise rows
     // in-kernel -- only for handles created without them)
