@@ -2,7 +2,8 @@
 import os, sys, time
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
+import _use_so  # noqa: F401
 from audio_sheet_retrieval_b200 import _lib, network
 from audio_sheet_retrieval_b200.models import mutopia_ccal_cont as model
 from audio_sheet_retrieval_b200.params import load_params
