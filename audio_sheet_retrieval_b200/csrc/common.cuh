@@ -345,6 +345,32 @@ __device__ __forceinline__ void tmem_ld64_issue(uint32_t taddr, uint32_t *r) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 16 columns without the wait (valid after tmem_ld_wait())
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+// volatile shared-memory accesses for the hand-rolled queues (no caching in registers, no reordering by the compiler)
+__device__ __forceinline__ uint32_t lds_volatile_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long lds_volatile_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_volatile_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_volatile_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(smem_u32(p)), "l"(v) : "memory");
+}
 
 // Shared-memory matrix descriptor, K-major, no swizzle ("interleaved" core matrices of
 // 8 rows x 16 bytes):  element (row r, k) lives at

@@ -665,26 +665,34 @@ rank_count_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int64_
 // score and eps = 2^-8.  Every true top-k row satisfies s >= tau_final >= tau_q, hence
 // s~ >= tau_q - eps, so it is always re-scored; lists, thresholds and the final order use exact
 // scores only.  Results are therefore identical to topk_stream_kernel / the oracle.
-// Layout: thread = query (= TMEM lane); each thread keeps its query's sorted top-k list in registers.
+// Layout: TMEM lane = query.  SCANNER warps read the score tile out of TMEM and only FILTER it against the query's
+// current threshold; what passes goes, as (row, query) entries, into shared-memory rings that OWNER warps consume:
+// exact re-scoring and insertion into the query's sorted top-k list (one list per query and work item).
 constexpr int TC_QM = 128;
 constexpr int TC_ROWS = 256;
 constexpr int TC_STAGES = 3;
 constexpr int TC_KMAX = 32;
-constexpr int TC_EPI_WARPS = 8;      // two per TMEM lane quarter (column halves)
-constexpr int TC_THREADS = 32 * (2 + TC_EPI_WARPS);   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int TC_SCAN_WARPS = 16;    // four per TMEM lane quarter: each scans one 64-column chunk of every tile
+constexpr int TC_OWN_WARPS = 8;      // list owners: query qi of the tile belongs to owner qi % TC_OWN_WARPS
+constexpr int TC_SCAN_WARP0 = 2, TC_OWN_WARP0 = 2 + TC_SCAN_WARPS;   // warp 0 TMA, warp 1 MMA
+constexpr int TC_THREADS = 32 * (2 + TC_SCAN_WARPS + TC_OWN_WARPS);   // 832
 
-constexpr int TC_LSTRIDE = TC_KMAX + 1;   // list stride in keys: odd, so that the same position of different lists hits different banks
-constexpr int TC_QCAP = 64;               // candidate queue entries per epilogue warp (drained 32 at a time)
+constexpr int TC_LSTRIDE = 2 * TC_KMAX + 1;   // per query: sorted list [0, 32) + append buffer [32, 64); odd stride spreads the lists over the banks
+constexpr int TC_RING = 256;              // candidate ring entries per owner warp (power of two)
 
 struct TcSmem {
     float stage[TC_STAGES][TC_ROWS * 32];     // normalised DB rows, SWIZZLE_128B (written by TMA)
     float q[TC_QM * 32];                      // normalised queries, same swizzle (written by threads)
-    unsigned short cand[16][TC_QM];           // pending-candidate masks of the current tile: [16-column group][TMEM lane]
-    unsigned long long lists[2 * TC_QM * TC_LSTRIDE];   // sorted top-k list of every epilogue thread (column half, TMEM lane) as 64-bit keys
-    unsigned long long floor_key[2 * TC_QM];  // threshold floor of the list (first-tile bisection)
-    float tau[2 * TC_QM];                     // approximate-score filter threshold of the list
-    uint32_t cq_row[TC_EPI_WARPS][TC_QCAP];   // candidate queues: DB row ...
-    unsigned char cq_lane[TC_EPI_WARPS][TC_QCAP];   // ... and the lane (within the warp) whose list it is for
+    unsigned long long lists[TC_QM * TC_LSTRIDE];   // per query: sorted top-k list + unsorted buffer of accepted candidates, 64-bit keys
+    uint32_t fmin_key[TC_QM];                 // first-tile floor: minimum over the query's scanner threads (atomicMin)
+    uint32_t pub[TC_QM];                      // the list has published its jpub-th best at least once
+    uint32_t bcnt[TC_QM];                     // entries appended to the buffer since its last compaction (may overshoot 32)
+    unsigned long long floor_key[TC_QM];      // threshold floor of the list (first-tile bisection; atomicMax by the scanners)
+    unsigned long long ring[TC_OWN_WARPS][TC_RING];   // candidates: tag (24) | query (8) | row (32); tag = lap + 1 marks a written slot
+    uint32_t tau_key[TC_QM];                  // fkey of the approximate-score filter threshold of the query (atomicMax)
+    uint32_t resv[TC_OWN_WARPS];              // ring positions handed out to producers (monotonic)
+    uint32_t head[TC_OWN_WARPS];              // ring positions consumed by the owner (monotonic; producers wait on it when full)
+    uint32_t scan_done;                       // scanner warps that finished pushing an item (monotonic)
     uint64_t full[TC_STAGES], empty[TC_STAGES], tfull[2], tempty[2];
     uint32_t tmem_ptr;
     unsigned item;
@@ -774,82 +782,199 @@ __device__ __forceinline__ float tc_exact_score_g(const float *qsm, const float 
     return (acc != acc) ? -CUDART_INF_F : acc;
 }
 
-// Drain `n` (<= 32) queued candidates of one epilogue warp, ONE PER LANE: exact score (the row comes back from L2,
-// where the TMA load of its tile just put it), then insertion into the owner lane's sorted list in shared memory.
-// Lanes whose candidates belong to the same list take turns (lowest lane first); lists of different lanes are
-// independent, so a round inserts up to 32 candidates at once.
-// gkey[q]: fkey of a LOWER BOUND of query q's final k-th best exact score, shared by every list of the query on this
-// GPU (other DB slices, column halves, lane copies): each list publishes its own k-th best with atomicMax as soon as it
-// holds k real entries.  A row scoring strictly below the bound cannot be in the query's top-k, so every list filters
-// with the best bound anybody has found -- the per-item threshold warm-up (k ln(rows / k) insertions per list) is paid
-// about once per query instead of once per list.
-__device__ __forceinline__ void tc_drain(TcSmem &sm, const float *__restrict__ rows, int n, int ew, int quarter, int lbase, int k,
-                                         float eps, int lane, unsigned *__restrict__ gkey, int q0, int nqt_mask) {
-    const bool have = lane < n;
-    int owner = 64 + lane;                                   // distinct dummy owners for idle lanes
+// Bounds shared between the lists of a query.  A query has one list per DB slice (S slices = S work items, usually on
+// S different SMs at the same time), and every list starts cold: a row enters a list with probability ~ k / (rows the
+// list has seen), so S cold lists re-score ~ S k ln(rows / (S k)) rows where one list over all rows would re-score
+// k ln(rows / k).  What helps is a bound on the query's FINAL k-th best that uses all lists at once:
+//   * every list publishes its j-th best exact score, j = ceil(k / min(S, k)), in slots[q][slice] (single writer);
+//   * if m lists have published, m j >= k, there are k distinct rows scoring at least the SMALLEST of those m values, so
+//     the m-th largest published value is a lower bound of the final k-th best.  S <= 8: j = ceil(k / S) and the
+//     minimum over all S slots (tc_bound_small, one lane per list).  S > 8: the m-th largest of S values by bisection
+//     on the key bits (tc_bound_large, one warp per list; for S >= k that is the k-th largest of the lists' BEST rows,
+//     which is within a few ranks of the true k-th best of everything seen so far).
+// The bound goes into gkey[q] (atomicMax; the scanners read it one tile ahead) and into the query's tau_key.
+// A row scoring strictly below the bound cannot be in the query's top-k.
+constexpr int TC_SLOT_SMALL = 8;
+
+__device__ unsigned long long *g_tc_stats_dev = nullptr;
+__device__ __forceinline__ void tc_apply_bound(TcSmem &sm, unsigned *__restrict__ gkey, int q0, int qi, unsigned b, float eps) {
+    if (g_tc_stats_dev) atomicAdd(g_tc_stats_dev + 10, 1ull);
+    if (b == 0u) return;                                     // not enough lists have published yet
+    const unsigned old = atomicMax(gkey + q0 + qi, b);
+    if (g_tc_stats_dev) { atomicAdd(g_tc_stats_dev + 11, 1ull); if (b > old) atomicAdd(g_tc_stats_dev + 12, 1ull); }
+    atomicMax(&sm.tau_key[qi], fkey(fkey_inv(b) - eps));
+}
+
+// S > 8: the warp finds the m-th largest of the S slot values of query qi (16 bisection steps on the high key bits:
+// the result is rounded DOWN to a multiple of 2^16 key units, still a valid bound)
+__device__ __forceinline__ unsigned tc_bound_large(const unsigned *__restrict__ slots_q, int S, int m, int lane) {
+    unsigned v[8];                                           // S <= 256
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = lane + 32 * i < S ? __ldcg(slots_q + lane + 32 * i) : 0u;
+    unsigned lo = 0u;                                        // invariant: at least m values are >= lo
+#pragma unroll 1
+    for (int bit = 31; bit >= 16; --bit) {
+        const unsigned mid = lo | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) c += v[i] >= mid ? 1 : 0;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c >= m) lo = mid;
+    }
+    return lo;
+}
+
+// Descending bitonic sort of one 64-bit key per lane, and the merge step of two descending runs.
+__device__ __forceinline__ unsigned long long tc_cmpx(unsigned long long x, int stride, bool take_max) {
+    const unsigned long long p = __shfl_xor_sync(0xffffffffu, x, stride);
+    return (x > p) == take_max ? x : p;
+}
+__device__ __forceinline__ unsigned long long tc_sort32_desc(unsigned long long x, int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1)
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1)
+            x = tc_cmpx(x, stride, ((lane & stride) == 0) == ((lane & size) == 0));
+    return x;
+}
+// top 32 of two descending runs (one key per lane each), descending
+__device__ __forceinline__ unsigned long long tc_merge32_desc(unsigned long long y, unsigned long long x, int lane) {
+    const unsigned long long xr = __shfl_sync(0xffffffffu, x, 31 - lane);
+    unsigned long long z = y > xr ? y : xr;                  // bitonic: holds the 32 largest of the 64
+#pragma unroll
+    for (int stride = 16; stride > 0; stride >>= 1) z = tc_cmpx(z, stride, (lane & stride) == 0);
+    return z;
+}
+
+// Compaction of query qc's list (whole warp): sort the append buffer, merge it with the sorted list, keep the best k,
+// empty the buffer, raise the query's thresholds and publish the entries the other slices use (see above).
+// ~200 instructions for up to 32 new entries, whatever their positions -- against ~60 per candidate for an insertion
+// of one candidate at a time and ~300 per round for lane-serial shifting (the cost of this kernel is its instruction
+// count: the owner warps get about one issue slot in ten).
+__device__ __forceinline__ void tc_compact(TcSmem &sm, int qc, int k, float eps, int lane, unsigned *__restrict__ gkey,
+                                           unsigned *__restrict__ slots, int S, int spad, int slice, int jpub, int q0) {
+    unsigned long long *l = sm.lists + qc * TC_LSTRIDE;
+    const int n = min((int)lds_volatile_u32(&sm.bcnt[qc]), 32);
+    if (n == 0) return;                                      // warp-uniform
+    const unsigned long long x = tc_sort32_desc(lane < n ? l[32 + lane] : 0ull, lane);
+    const unsigned long long z = tc_merge32_desc(lane < k ? l[lane] : 0ull, x, lane);
+    if (lane < k) l[lane] = z;
+    const unsigned long long kth = __shfl_sync(0xffffffffu, z, k - 1), pj = __shfl_sync(0xffffffffu, z, jpub - 1);
+    if (lane == 0) {
+        sts_volatile_u32(&sm.bcnt[qc], 0u);
+        const unsigned long long fl = lds_volatile_u64(&sm.floor_key[qc]);
+        atomicMax(&sm.tau_key[qc], fkey(fkey_inv((uint32_t)((kth > fl ? kth : fl) >> 32)) - eps));
+        if ((uint32_t)kth != 0u) atomicMax(gkey + q0 + qc, (unsigned)(kth >> 32));     // a real k-th entry: the list's own bound
+        if (S > 1 && (uint32_t)pj != 0u) {
+            __stcg(slots + (size_t)(q0 + qc) * spad + slice, (unsigned)(pj >> 32));
+            sts_volatile_u32(&sm.pub[qc], 1u);
+            if (g_tc_stats_dev) atomicAdd(g_tc_stats_dev + 13, 1ull);
+        }
+    }
+    __syncwarp();
+}
+
+// Owner warp: up to 32 ring entries, ONE PER LANE: exact score (the row comes back from L2, where the TMA load of its
+// tile just put it); what beats the list's current k-th entry, floor and shared bound is APPENDED to the list's buffer
+// (one shared-memory atomic); a buffer that is full is compacted (tc_compact) and the lanes it turned away try again.
+// Every list has exactly one owner warp, so list accesses need no locking.
+__device__ __forceinline__ void tc_own_drain(TcSmem &sm, const float *__restrict__ rows, unsigned long long ent, bool have, int k,
+                                             float eps, int lane, unsigned *__restrict__ gkey, unsigned *__restrict__ slots, int S,
+                                             int spad, int slice, int jpub, int q0, unsigned long long *stats, uint32_t bcap) {
+    const long long ts0 = stats ? clock64() : 0;
+    int qi = 0;
     unsigned long long key = 0ull;
     bool todo = false;
     if (have) {
-        owner = sm.cq_lane[ew][lane];
-        const uint32_t row = sm.cq_row[ew][lane];
-        const int ql = quarter * 32 + owner;
-        const float sc = tc_exact_score_g(sm.q, rows + (size_t)row * 32, ql);
+        const uint32_t row = (uint32_t)ent;
+        qi = (int)((ent >> 32) & 0xffu);
+        unsigned gbound = __ldcg(gkey + q0 + qi);                // in flight together with the row
+        uint4 sa = make_uint4(~0u, ~0u, ~0u, ~0u), sb = sa;
+        if (S > 1 && S <= TC_SLOT_SMALL) {
+            sa = __ldcg(reinterpret_cast<const uint4 *>(slots + (size_t)(q0 + qi) * spad));
+            sb = __ldcg(reinterpret_cast<const uint4 *>(slots + (size_t)(q0 + qi) * spad) + 1);
+        }
+        const float sc = tc_exact_score_g(sm.q, rows + (size_t)row * 32, qi);
         key = ((unsigned long long)fkey(sc) << 32) | (unsigned long long)(~row);
-        const unsigned long long kth = sm.lists[(lbase + owner) * TC_LSTRIDE + k - 1], fl = sm.floor_key[lbase + owner];
-        todo = key > (kth > fl ? kth : fl) && fkey(sc) >= __ldcg(gkey + q0 + (ql & nqt_mask));
+        if (S > 1 && S <= TC_SLOT_SMALL) {                       // S <= 8: the minimum over the S slots is a bound
+            const unsigned v[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+            unsigned b = 0xffffffffu;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) b = i < S ? min(b, v[i]) : b;
+            if (b > gbound) { tc_apply_bound(sm, gkey, q0, qi, b, eps); gbound = b; }
+        }
+        const unsigned long long kth = sm.lists[qi * TC_LSTRIDE + k - 1], fl = lds_volatile_u64(&sm.floor_key[qi]);
+        todo = key > (kth > fl ? kth : fl) && fkey(sc) >= gbound;
     }
-    while (__any_sync(0xffffffffu, todo)) {
-        const unsigned peers = __match_any_sync(0xffffffffu, todo ? owner : 64 + lane);
-        if (todo && (int)(__ffs(peers) - 1) == lane) {
-            unsigned long long *l = sm.lists + (lbase + owner) * TC_LSTRIDE;
-            if (key > l[k - 1]) {                            // an earlier round may have raised the k-th entry
-                int j = k - 1;
-                for (; j > 0; --j) {
-                    const unsigned long long up = l[j - 1];
-                    if (up > key) break;
-                    l[j] = up;
-                }
-                l[j] = key;
-                const unsigned long long kth = l[k - 1], fl = sm.floor_key[lbase + owner];
-                sm.tau[lbase + owner] = fkey_inv((uint32_t)((kth > fl ? kth : fl) >> 32)) - eps;
-                if ((uint32_t)kth != 0u)                     // a real k-th entry (empty slots have lo = 0): publish the bound
-                    atomicMax(gkey + q0 + ((quarter * 32 + owner) & nqt_mask), (unsigned)(kth >> 32));
+    if (stats) {
+        const unsigned bl = __ballot_sync(0xffffffffu, todo);
+        if (lane == 0) { atomicAdd(stats + 7, (unsigned long long)(clock64() - ts0)); atomicAdd(stats + 8, (unsigned long long)__popc(bl)); }
+    }
+    for (;;) {
+        bool full = false, early = false;
+        if (todo) {
+            const uint32_t pos = atomicAdd(&sm.bcnt[qi], 1u);
+            if (pos < (bcap & 0xffu)) {
+                sm.lists[qi * TC_LSTRIDE + 32 + pos] = key;
+                todo = false;
+                // a young list is compacted as soon as it can publish: the bound the slices share (see above) is worth
+                // most at the start of an item, when every list is cold
+                early = S > 1 && pos + 1u >= (uint32_t)max(jpub, 4) && lds_volatile_u32(&sm.pub[qi]) == 0u;
+            } else {
+                full = true;
             }
-            todo = false;
         }
         __syncwarp();
+        unsigned fm = __ballot_sync(0xffffffffu, full || early);
+        if (!fm) break;
+        while (fm) {                                             // every distinct full (or young) list once
+            const int qc = __shfl_sync(0xffffffffu, qi, __ffs(fm) - 1);
+            fm &= ~__ballot_sync(0xffffffffu, (full || early) && qi == qc);
+            tc_compact(sm, qc, k, eps, lane, gkey, slots, S, spad, slice, jpub, q0);
+        }
+        if (!__any_sync(0xffffffffu, full)) break;
+        // a lane that was turned away re-checks its key against the raised k-th entry before it tries again
+        if (todo) todo = key > sm.lists[qi * TC_LSTRIDE + k - 1];
     }
 }
 
 // Persistent 1-D grid; work items (query tile, DB slice) are handed out by an atomic counter so that
 // any (nq, n_db) shape fills all SMs.  qn = normalised queries (nq,32); tmap over the normalised DB rows.
 //
-// Epilogue layout.  A score tile is 128 TMEM lanes x 256 columns (DB rows).  Reading it out of TMEM and scanning it
-// bounds this kernel, and with one warp per lane quarter that is a latency-bound chain.  EIGHT epilogue warps share a
-// tile: the two warps of a lane quarter scan one half of the columns each, and for <= 64 queries the query tile is
-// REPLICATED over the lane quarters (rep = 2) so that no lane idles.  Every (TMEM lane, column half) thread owns a
-// sorted top-k list in SHARED memory; rows that pass the approximate filter go through a per-warp candidate queue and
-// are re-scored exactly / inserted 32 at a time, one candidate per lane, whichever list it belongs to (the old
-// thread-owns-its-list-in-registers form spent 2/3 of its instructions in a lock-step loop with ~1 active lane).
-// At item end the L = 2 * rep lists of a query are merged by rank counting.
+// Roles.  A score tile is 128 TMEM lanes (queries) x 256 columns (DB rows).  TMEM read-out is fast (measured ~1 KB per
+// cycle and SM, tools/tmem_probe.cu); what bounds this kernel is the dependent-instruction latency of the warps that
+// look at the scores, so there are many of them and they do as little as possible:
+//   16 scanner warps  lane quarter x 64-column chunk.  Per tile: load the chunk, max-reduce it in 16-column blocks,
+//                     compare with the query's threshold; the (rare) passing columns are pushed as (row, query)
+//                     entries into the ring of the query's owner (space reserved with one shared-memory atomic per
+//                     lane that has hits).  The accumulator slot is released as soon as the chunk is in registers.
+//   8 owner warps     pop up to 32 entries, re-score them exactly (one per lane) and insert them into the sorted
+//                     top-k lists, ONE list per query and item (tc_own_drain); thresholds go back to the scanners
+//                     through sm.tau_key.  At item end the owner writes its lists to the item's output slot.
+// For <= 64 (<= 32) queries the query tile is replicated over the lane quarters (rep = 2, 4) and the replicas split
+// each chunk's columns, so that all scanner warps stay busy.
 __global__ void __launch_bounds__(TC_THREADS, 1)
 topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles_per_slice, int n_slices,
                const float *__restrict__ rows, const float *__restrict__ qn, int nq, int k, float eps, int rep,
                float *__restrict__ part_s, uint32_t *__restrict__ part_i, unsigned *__restrict__ work_counter,
-               unsigned *__restrict__ gkey, float *dbg) {
+               unsigned *__restrict__ gkey, unsigned *__restrict__ slots, float *dbg, unsigned long long *stats, uint32_t bcap, int ring_lim) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     TcSmem &sm = *reinterpret_cast<TcSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // provably warp-uniform: uniform role branches
     if (smem_u32(smem_raw) & 1023u) __trap();
     const int64_t n_tiles = (n_db + TC_ROWS - 1) / TC_ROWS;
+    const unsigned long long NEG_KEY = (unsigned long long)0x007fffffu << 32;      // (fkey(-inf), row 0xffffffff)
 
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&sm.tfull[s], 1); mbar_init(&sm.tempty[s], TC_EPI_WARPS); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&sm.tfull[s], 1); mbar_init(&sm.tempty[s], TC_SCAN_WARPS); }
         mbar_fence_init();
         tma_prefetch_desc(&tmap);
+        sm.scan_done = 0u;
     }
+    for (int i = tid; i < TC_OWN_WARPS * TC_RING; i += TC_THREADS) (&sm.ring[0][0])[i] = 0ull;     // tag 0 = never written
+    if (tid < TC_OWN_WARPS) { sm.resv[tid] = 0u; sm.head[tid] = 0u; }
     if (warp == 1) { tmem_alloc(&sm.tmem_ptr, 512); tmem_relinquish(); }
     tc_fence_before();
     __syncthreads();
@@ -858,19 +983,22 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles
     // kind::tf32: a/b format 2 (TF32), fp32 accumulate, K-major both, M = 128, N = 256
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_ROWS >> 3) << 17) | ((uint32_t)(TC_QM >> 4) << 24);
 
-    const int nqt = TC_QM / rep;                     // distinct queries per tile
-    const int L = 2 * rep;                           // lists per (query, item): rep lane copies x 2 column halves
-    const int ncols = TC_ROWS / L;                   // columns per epilogue thread: 128 or 64
+    const int nqt = TC_QM / rep;                     // distinct queries per tile (128, 64 or 32)
+    const int ncols = 64 / rep;                      // columns per scanner thread and tile (64, 32 or 16)
     const int n_qt = (nq + nqt - 1) / nqt;
     const unsigned n_items = (unsigned)n_qt * (unsigned)n_slices;
     int64_t itg = 0;                 // running tile counter (barrier phases continue across work items)
+    uint32_t item_seq = 0;           // work items this CTA has finished
+    uint32_t ring_h = 0;             // owner warps: consumed ring positions
     for (;;) {
         if (tid == 0) sm.item = atomicAdd(work_counter, 1u);
         __syncthreads();
         const unsigned item = sm.item;
         if (item >= n_items) break;
-        // consecutive items share the DB slice (L2 reuse across CTAs), query tile varies fastest
-        const int slice = (int)(item / (unsigned)n_qt), qt = (int)(item % (unsigned)n_qt);
+        // The slice varies fastest: all lists of a query tile run at the same time (on neighbouring SMs), so the bound
+        // they share (tc_own_drain) is fed by every slice from the first tiles on; a slice is still streamed by
+        // gridDim / n_slices CTAs at once, which is what gives the L2 reuse.
+        const int qt = (int)(item / (unsigned)n_slices), slice = (int)(item % (unsigned)n_slices);
         const int64_t tile0 = (int64_t)slice * tiles_per_slice;
         int64_t my_tiles = n_tiles - tile0;
         if (my_tiles > tiles_per_slice) my_tiles = tiles_per_slice;
@@ -884,6 +1012,11 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles
             if (q0 + qi < nq) v = *reinterpret_cast<const float4 *>(qn + (int64_t)(q0 + qi) * 32 + c * 4);
             *reinterpret_cast<float4 *>(sm.q + row * 32 + ((c ^ (row & 7)) << 2)) = v;
         }
+        // The sorted top-k list of every query lives in shared memory as 64-bit keys (hi = order-preserving map of the
+        // exact score, lo = ~row: one unsigned compare is exactly "score desc, index asc"; empty slots hold the
+        // smallest key, (-inf, row 0xffffffff)).
+        for (int i = tid; i < nqt * TC_LSTRIDE; i += TC_THREADS) sm.lists[i] = NEG_KEY;
+        if (tid < TC_QM) { sm.floor_key[tid] = NEG_KEY; sm.tau_key[tid] = 0x007fffffu; sm.bcnt[tid] = 0u; sm.pub[tid] = 0u; sm.fmin_key[tid] = 0xffffffffu; }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA (async proxy)
         __syncthreads();
 
@@ -918,184 +1051,222 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles
                 }
                 __syncwarp();
             }
-        } else {
+        } else if (warp < TC_OWN_WARP0) {
+            // ================= scanners =================
             const int quarter = warp & 3;                       // TMEM lane quarter this warp may read
+            const int cidx = (warp - TC_SCAN_WARP0) >> 2;       // 64-column chunk of the tile
             const int ql = quarter * 32 + lane;                 // TMEM lane = row of the (replicated) query tile
             const int qi = ql & (nqt - 1);                      // query within the tile
-            const int hsel = (warp - 2) >> 2;                   // which of the two warps of this lane quarter
-            const int sub = (ql / nqt) * 2 + hsel;              // which of the L column ranges of that query
-            const int li = hsel * TC_QM + ql;                   // this thread's list
-            const int col0 = sub * ncols;
+            const int col0 = 64 * cidx + ncols * (ql / nqt);    // the replicas of a query split the chunk
             const bool qvalid = q0 + qi < nq;
-            const int ew = warp - 2;
-            // The sorted top-k list of every lane lives in SHARED memory as 64-bit keys (hi = order-preserving map of
-            // the exact score, lo = ~row: one unsigned compare is exactly "score desc, index asc"; empty slots hold the
-            // smallest key, (-inf, row 0xffffffff)).  Pass 1 scans the approximate scores against the lane's tau;
-            // what passes goes into the warp's candidate queue and is re-scored / inserted 32 at a time (tc_drain).
-            const unsigned long long NEG_KEY = (unsigned long long)0x007fffffu << 32;      // (fkey(-inf), 0)
-            for (int j = 0; j < k; ++j) sm.lists[li * TC_LSTRIDE + j] = NEG_KEY;
-            sm.floor_key[li] = NEG_KEY;
-            sm.tau[li] = -CUDART_INF_F;
-            __syncwarp();
-            int qcount = 0;                                      // warp-uniform
+            const bool warp_valid = __any_sync(0xffffffffu, qvalid);
+            const int own = qi & (TC_OWN_WARPS - 1);
+            // the best bound anybody on this GPU has published for this query: an L2 read (1000+ cycles while the TMA stream
+            // keeps the L2 busy), so it is issued one tile ahead and never waited for
+            unsigned gk_next = qvalid ? __ldcg(gkey + q0 + qi) : 0u;
             for (int64_t it = 0; it < my_tiles; ++it) {
                 const int64_t g = itg + it;
                 const uint32_t slot = (uint32_t)(g & 1);
+                const unsigned gk = gk_next;
+                if (qvalid) gk_next = __ldcg(gkey + q0 + qi);
+                const long long tw0 = stats ? clock64() : 0;
                 mbar_wait(&sm.tfull[slot], (uint32_t)((g >> 1) & 1));
+                const long long tsc0 = stats ? clock64() : 0;
+                if (stats && lane == 0) atomicAdd(stats + 4, (unsigned long long)(tsc0 - tw0));
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + slot * 256u + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col0;
                 const int64_t row0 = (tile0 + it) * TC_ROWS;
-                if (it == 0 && row0 + TC_ROWS <= n_db && ncols >= k) {
-                    // Threshold floor from the first (full) tile: bisect for a value `lo` such that at least k of this
-                    // lane's approximate scores are >= lo.  Those k rows have exact scores >= lo - eps, so the final
-                    // k-th best of this list is >= lo - eps: a valid floor that removes most of the warm-up.
-                    float lo = -2.0f, hi = 2.0f;
+                uint32_t hit0 = 0u, hit1 = 0u;
+                if (it == 0 && row0 + TC_ROWS <= n_db) {             // CTA-uniform
+                    // Threshold floor from the first (full) tile.  A query's 256 scores sit in P = 4 rep scanner threads
+                    // (ncols columns each): every thread bisects for a value such that at least jfl = ceil(k / P) of ITS
+                    // approximate scores are >= it; the minimum `lo` over the P threads then has >= k rows at or above it,
+                    // whose exact scores are >= lo - eps.  So the final k-th best of the list is >= lo - eps: a floor
+                    // at the ~k/256 quantile of a tile, which removes most of the list's warm-up.
+                    const int jfl = (k + 4 * rep - 1) / (4 * rep);
+                    if (warp_valid) {
+                        float lo = -2.0f, hi = 2.0f;
 #pragma unroll 1
-                    for (int iter = 0; iter < 12; ++iter) {
-                        const float mid = 0.5f * (lo + hi);
-                        int cnt = 0;
+                        for (int iter = 0; iter < 12; ++iter) {
+                            const float mid = 0.5f * (lo + hi);
+                            int cnt = 0;
 #pragma unroll 1
-                        for (int c64 = 0; c64 < ncols; c64 += 64) {
-                            float v[64];
-                            tmem_ld64(taddr + (uint32_t)c64, v);
+                            for (int c16 = 0; c16 < ncols; c16 += 16) {
+                                float v[16];
+                                tmem_ld16(taddr + (uint32_t)c16, v);
 #pragma unroll
-                            for (int j = 0; j < 64; ++j) cnt += v[j] >= mid ? 1 : 0;
-                        }
-                        if (cnt >= k) lo = mid; else hi = mid;
-                    }
-                    if (lo > -2.0f) {          // found (queries of all-NaN / degenerate tiles keep -inf)
-                        const float floor_s = lo - eps;
-                        sm.floor_key[li] = (unsigned long long)fkey(floor_s) << 32;   // ties with the floor itself still enter
-                        sm.tau[li] = floor_s - eps;
-                    }
-                }
-                // the best bound anybody on this GPU has published for this query (read from L2 once per tile)
-                const float gtau = qvalid ? fkey_inv(__ldcg(gkey + q0 + qi)) - eps : -CUDART_INF_F;
-                const float tau = fmaxf(sm.tau[li], gtau);
-                // Pass 1: scan this lane's approximate scores, 64 columns per TMEM round trip, and remember which
-                // columns pass the filter as 16-bit masks.  NaN approximations (zero DB rows) need no special case:
-                // they can only matter while tau is -inf, and then !(x < tau) is true for every x.
-                unsigned pend = 0u;
-                // software pipeline over the 64-column chunks: the TMEM round trip of chunk c + 1 runs under the scan of c
-                auto scan = [&](const uint32_t *vr, int c64) {
-                    if (dbg && slice == 0 && qt == 0 && it == 0) {      // debug: dump the approximate scores of tile 0
-#pragma unroll
-                        for (int j = 0; j < 64; ++j) dbg[qi * TC_ROWS + col0 + c64 + j] = __uint_as_float(vr[j]);
-                    }
-                    float m[4];
-#pragma unroll
-                    for (int sb = 0; sb < 4; ++sb) {
-                        m[sb] = __uint_as_float(vr[sb * 16]);
-#pragma unroll
-                        for (int j = 1; j < 16; ++j) m[sb] = fmaxf(m[sb], __uint_as_float(vr[sb * 16 + j]));
-                    }
-                    const float mm = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
-                    if (qvalid && !(mm < tau)) {
-#pragma unroll
-                        for (int sb = 0; sb < 4; ++sb) {
-                            if (!(m[sb] < tau)) {
-                                unsigned mask = 0u;        // static indexing keeps the chunk in registers
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) mask |= !(__uint_as_float(vr[sb * 16 + j]) < tau) ? (1u << j) : 0u;
-                                const int g16 = (col0 + c64) / 16 + sb;
-                                sm.cand[g16][ql] = (unsigned short)mask;
-                                pend |= 1u << ((c64 / 16) + sb);          // bit = 16-column group within this lane's range
+                                for (int j = 0; j < 16; ++j) cnt += v[j] >= mid ? 1 : 0;
                             }
+                            if (cnt >= jfl) lo = mid; else hi = mid;
                         }
+                        if (qvalid) atomicMin(&sm.fmin_key[qi], lo > -2.0f ? fkey(lo) : 0u);   // 0: no floor (all-NaN / degenerate tiles)
                     }
-                };
-                {
-                    uint32_t va[64], vb[64];
-                    tmem_ld64_issue(taddr, va);
+                    asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_SCAN_WARPS) : "memory");
+                    const uint32_t fm = sm.fmin_key[qi];
+                    if (qvalid && fm != 0u && fm != 0xffffffffu && (ql / nqt) == 0 && cidx == 0) {   // one thread per query
+                        const float floor_s = fkey_inv(fm) - eps;
+                        atomicMax(&sm.floor_key[qi], (unsigned long long)fkey(floor_s) << 32);   // ties with the floor itself still enter
+                        atomicMax(&sm.tau_key[qi], fkey(floor_s - eps));
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_SCAN_WARPS) : "memory");     // floors visible before the tile is scanned
+                }
+                if (warp_valid) {
+                    const float tau = (qvalid && !(bcap & 0x100u)) ? fmaxf(fkey_inv(lds_volatile_u32(&sm.tau_key[qi])), fkey_inv(gk) - eps) : CUDART_INF_F;   // bcap bit 8: diagnosis, nothing passes
+                    // Scan 32 columns per TMEM round trip (16 when the chunk is split four ways).  NaN approximations
+                    // (zero DB rows) need no special case: they can only matter while tau is -inf, and then
+                    // !(x < tau) is true for every x.
 #pragma unroll 1
-                    for (int c64 = 0; c64 < ncols; c64 += 128) {
+                    for (int u = 0; u < ncols; u += 32) {
+                        uint32_t v[32];
+                        tmem_ld16_issue(taddr + (uint32_t)u, v);
+                        if (ncols >= 32) tmem_ld16_issue(taddr + (uint32_t)(u + 16), v + 16);
                         tmem_ld_wait();
-                        if (c64 + 64 < ncols) tmem_ld64_issue(taddr + (uint32_t)(c64 + 64), vb);
-                        scan(va, c64);
-                        if (c64 + 64 < ncols) {
-                            tmem_ld_wait();
-                            if (c64 + 128 < ncols) tmem_ld64_issue(taddr + (uint32_t)(c64 + 128), va);
-                            scan(vb, c64 + 64);
+                        if (dbg && slice == 0 && qt == 0 && it == 0) {      // debug: dump the approximate scores of tile 0
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < ncols) dbg[qi * TC_ROWS + col0 + u + j] = __uint_as_float(v[j]);
                         }
+                        // 16-column blocks: max-reduce, and only where some lane of the warp has a block maximum that
+                        // passes (one vote per block) are the block's 16 columns compared one by one
+                        float m0 = __uint_as_float(v[0]), m1 = -CUDART_INF_F;
+#pragma unroll
+                        for (int j = 1; j < 16; ++j) m0 = fmaxf(m0, __uint_as_float(v[j]));
+                        if (ncols >= 32) {
+                            m1 = __uint_as_float(v[16]);
+#pragma unroll
+                            for (int j = 17; j < 32; ++j) m1 = fmaxf(m1, __uint_as_float(v[j]));
+                        }
+                        uint32_t mask = 0u;
+                        if (__any_sync(0xffffffffu, qvalid && !(m0 < tau))) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) mask |= !(__uint_as_float(v[j]) < tau) ? (1u << j) : 0u;
+                        }
+                        if (ncols >= 32 && __any_sync(0xffffffffu, qvalid && !(m1 < tau))) {
+#pragma unroll
+                            for (int j = 16; j < 32; ++j) mask |= !(__uint_as_float(v[j]) < tau) ? (1u << j) : 0u;
+                        }
+                        if (!qvalid) mask = 0u;
+                        if (u == 0) hit0 = mask; else hit1 = mask;
                     }
                 }
-                // the accumulator slot is free again as soon as every epilogue warp has scanned it
+                // the accumulator slot is free again as soon as every scanner warp has its chunk in registers
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.tempty[slot]);
-                // Pass 2: move the candidates into the warp's queue (one per lane per round, a handful of instructions),
-                // draining 32 of them whenever that many are waiting.
-                while (__any_sync(0xffffffffu, pend != 0u)) {
-                    bool have = false;
-                    uint32_t row = 0u;
-                    if (pend) {
-                        const int gq = __ffs(pend) - 1;
-                        const int g16 = col0 / 16 + gq;
-                        unsigned mask = sm.cand[g16][ql];
-                        const int j = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        sm.cand[g16][ql] = (unsigned short)mask;
-                        if (!mask) pend &= ~(1u << gq);
-                        const int64_t r = row0 + g16 * 16 + j;
-                        have = r < n_db;
-                        row = (uint32_t)r;
-                    }
-                    const unsigned bal = __ballot_sync(0xffffffffu, have);
-                    if (have) {
-                        const int pos = qcount + __popc(bal & ((1u << lane) - 1u));
-                        sm.cq_row[ew][pos] = row;
-                        sm.cq_lane[ew][pos] = (unsigned char)lane;
-                    }
-                    qcount += __popc(bal);
-                    __syncwarp();
-                    if (qcount >= 32) {
-                        tc_drain(sm, rows, 32, ew, quarter, hsel * TC_QM + quarter * 32, k, eps, lane, gkey, q0, nqt - 1);
-                        qcount -= 32;
-                        const uint32_t mr = sm.cq_row[ew][32 + lane];          // move the remainder (< 32 entries) to the front
-                        const unsigned char ml = sm.cq_lane[ew][32 + lane];
-                        __syncwarp();
-                        if (lane < qcount) { sm.cq_row[ew][lane] = mr; sm.cq_lane[ew][lane] = ml; }
-                        __syncwarp();
-                    }
+                if (stats && lane == 0) atomicAdd(stats + 9, (unsigned long long)(clock64() - tsc0));
+                // push what passed: rows beyond the DB (zero-filled by TMA) are dropped here
+                if (row0 + TC_ROWS > n_db) {
+                    const int64_t l64 = n_db - row0 - col0;       // valid columns of this thread's range
+                    const int left = l64 < 0 ? 0 : (l64 > 64 ? 64 : (int)l64);
+                    if (left < 32) hit0 &= (1u << left) - 1u;
+                    if (left < 64) hit1 &= left <= 32 ? 0u : ((1u << (left - 32)) - 1u);
                 }
-                // thresholds only ever rise, so a drain may be deferred; it must happen before the lists are read
-                if (qcount && (it + 1 == my_tiles || (it & 7) == 7)) {
-                    tc_drain(sm, rows, qcount, ew, quarter, hsel * TC_QM + quarter * 32, k, eps, lane, gkey, q0, nqt - 1);
-                    qcount = 0;
-                }
-            }
-            // Item end: the rep lanes that served the same query merge their sorted lists by RANK COUNTING -- the merged
-            // position of an entry is its own index plus the number of entries of the other lists that beat it (binary
-            // search; keys are unique, so positions are too) -- and every lane writes its survivors straight to the
-            // item's single output list.
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
-            if (qvalid) {
-                const size_t o = ((size_t)(q0 + qi) * n_slices + slice) * k;
-                const unsigned long long *ml = sm.lists + li * TC_LSTRIDE;
-                for (int j = 0; j < k; ++j) {
-                    const unsigned long long mine = ml[j];
-                    int rank = j;
-                    for (int t = 0; t < L; ++t) {
-                        const int other = (t & 1) * TC_QM + qi + (t >> 1) * nqt;
-                        if (other == li) continue;
-                        const unsigned long long *ol = sm.lists + other * TC_LSTRIDE;
-                        int lo = 0, hi = k;                   // number of entries of `ol` (sorted descending) greater than mine
-                        while (lo < hi) {
-                            const int mid = (lo + hi) >> 1;
-                            if (ol[mid] > mine) lo = mid + 1; else hi = mid;
+                const int cnt = __popc(hit0) + __popc(hit1);
+                const long long tp0 = stats ? clock64() : 0;
+                if (__any_sync(0xffffffffu, cnt != 0)) {
+                    // Reserve ring space with one atomic per lane that has hits, then write once the whole range fits.
+                    // The wait is a CONVERGED loop (one shared-memory load per warp and poll): lanes that spin on their
+                    // own flood the LSU and starve the owners.  A lane whose range fits writes at once, whatever the
+                    // other lanes of the warp are waiting for -- the lane at a ring's head always fits, so the owners
+                    // always make progress.
+                    uint32_t pos = 0u;
+                    if (cnt) pos = atomicAdd(&sm.resv[own], (uint32_t)cnt);
+                    const uint32_t need = pos + (uint32_t)cnt;
+                    bool pending = cnt != 0;
+                    for (;;) {
+                        if (pending && (int32_t)(need - lds_volatile_u32(&sm.head[own])) <= ring_lim) {
+                            const unsigned long long qbits = (unsigned long long)qi << 32;
+                            const uint32_t rbase = (uint32_t)(row0 + col0);
+#pragma unroll 1
+                            for (int half = 0; half < 2; ++half) {
+                                uint32_t m = half ? hit1 : hit0;
+                                while (m) {
+                                    const int j = __ffs(m) - 1;
+                                    m &= m - 1;
+                                    const unsigned long long tag = (unsigned long long)(((pos / TC_RING) + 1u) & 0xffffffu) << 40;
+                                    sts_volatile_u64(&sm.ring[own][pos & (TC_RING - 1)], tag | qbits | (unsigned long long)(rbase + 32 * half + j));
+                                    ++pos;
+                                }
+                            }
+                            pending = false;
                         }
-                        rank += lo;
-                    }
-                    if (rank < k) {
-                        const bool real = mine != NEG_KEY;
-                        part_s[o + rank] = real ? fkey_inv((uint32_t)(mine >> 32)) : -CUDART_INF_F;
-                        part_i[o + rank] = real ? ~(uint32_t)mine : 0xffffffffu;
+                        if (!__any_sync(0xffffffffu, pending)) break;
+                        __nanosleep(100);
                     }
                 }
+                __syncwarp();
+                if (stats && lane == 0) atomicAdd(stats + 3, (unsigned long long)(clock64() - tp0));
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");   // lists[] free for the next item
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) atomicAdd(&sm.scan_done, 1u);
+        } else {
+            // ================= owners =================
+            const int o = warp - TC_OWN_WARP0;
+            const uint32_t done_target = (uint32_t)TC_SCAN_WARPS * (item_seq + 1u);
+            const int S = n_slices, spad = (n_slices + 7) & ~7;
+            const int jpub = (k + min(S, k) - 1) / min(S, k);          // which entry of its list every slice publishes
+            const int m_need = (k + jpub - 1) / jpub;                  // published lists needed for a bound
+            uint32_t drains = 0u, next_refresh = 1u;
+            bool flush = false;
+            for (;;) {
+                // cheap poll: how much has been reserved beyond what this warp has consumed
+                const uint32_t rv = lds_volatile_u32(&sm.resv[o]);
+                const uint32_t sd = lds_volatile_u32(&sm.scan_done);
+                const int st8 = __shfl_sync(0xffffffffu, ((uint32_t)(rv - ring_h) >= 32u ? 4 : 0) | (sd == done_target ? 1 : 0) |
+                                                             (rv == ring_h ? 2 : 0), 0);
+                if ((st8 & 3) == 3) break;                             // scanners done, everything consumed
+                if (!(st8 & 4) && !(st8 & 1)) {                        // partial batch, item still running: wait (a drain costs
+                    __nanosleep(300);                                  // thousands of cycles whatever its size)
+                    continue;
+                }
+                const uint32_t pos = ring_h + (uint32_t)lane;
+                const unsigned long long ent = lds_volatile_u64(&sm.ring[o][pos & (TC_RING - 1)]);
+                const bool valid = (uint32_t)(ent >> 40) == (((pos / TC_RING) + 1u) & 0xffffffu);
+                const unsigned bal = __ballot_sync(0xffffffffu, valid);
+                const int n = bal == 0xffffffffu ? 32 : __ffs(~bal) - 1;
+                if (n == 0 || (n < 32 && !(st8 & 1)) || (n < 32 && !flush)) {   // reserved but not written yet / last entries: look again
+                    flush = (st8 & 1) != 0;
+                    __nanosleep(100);
+                    continue;
+                }
+                const long long td0 = stats ? clock64() : 0;
+                tc_own_drain(sm, rows, ent, lane < n, k, eps, lane, gkey, slots, S, spad, slice, jpub, q0, stats, bcap);
+                if (stats && lane == 0) {
+                    atomicAdd(stats + 0, (unsigned long long)n);
+                    atomicAdd(stats + 1, 1ull);
+                    atomicAdd(stats + 2, (unsigned long long)(clock64() - td0));
+                }
+                ring_h += (uint32_t)n;
+                if (lane == 0) sts_volatile_u32(&sm.head[o], ring_h);
+                // S > 8: after drains 1, 2, 3, 5, 8, 12, ... of the item, recompute the bound of every list of this owner from
+                // what all slices have published so far (the bound improves with the logarithm of the rows seen)
+                if (S > TC_SLOT_SMALL && ++drains == next_refresh) {
+                    next_refresh += (next_refresh + 1u) / 2u;            // drains 1, 2, 3, 5, 8, 12, 18, 27, ...
+                    for (int qi = o; qi < nqt; qi += TC_OWN_WARPS) {
+                        if (q0 + qi >= nq) break;
+                        const unsigned b = tc_bound_large(slots + (size_t)(q0 + qi) * spad, S, m_need, lane);
+                        if (lane == 0) tc_apply_bound(sm, gkey, q0, qi, b, eps);
+                    }
+                    __syncwarp();
+                }
+            }
+            // item end: fold the remaining buffers in; this owner's lists go straight to the item's output slot
+            __syncwarp();
+            for (int qi = o; qi < nqt; qi += TC_OWN_WARPS) {
+                tc_compact(sm, qi, k, eps, lane, gkey, slots, S, spad, slice, jpub, q0);
+                if (q0 + qi < nq && lane < k) {
+                    const unsigned long long mine = sm.lists[qi * TC_LSTRIDE + lane];
+                    const size_t oo = ((size_t)(q0 + qi) * n_slices + slice) * k + lane;
+                    const bool real = mine != NEG_KEY;
+                    part_s[oo] = real ? fkey_inv((uint32_t)(mine >> 32)) : -CUDART_INF_F;
+                    part_i[oo] = real ? ~(uint32_t)mine : 0xffffffffu;
+                }
+            }
         }
+        if (stats && tid == 0) { atomicAdd(stats + 5, (unsigned long long)my_tiles); atomicAdd(stats + 6, 1ull); }
         itg += my_tiles;
+        ++item_seq;
         __syncthreads();     // every role is done with sm.q / the lists before the next query tile
     }
     tc_fence_before();
@@ -1203,6 +1374,8 @@ struct asr_db {
     CUtensorMap tmap_n;
     float *qn = nullptr;    // normalised queries of the current call (pre-filter path), qn_cap rows, sized at create
     int64_t qn_cap = 0;
+    unsigned *slots = nullptr;   // pre-filter path: per (query, DB slice) published list entries (see tc_own_drain), slots_cap words
+    int64_t slots_cap = 0;
 };
 
 using namespace asr;
@@ -1299,6 +1472,11 @@ int asr_db_create_ex(asr_db_t **out, const float *codes_dev, int64_t n, int64_t 
         set_error("asr_db_create: cudaMalloc of the query workspace failed");
         DB_FAIL(ASR_ERR_CUDA);
     }
+    db->slots_cap = db->qn_cap * 8 + 262144;
+    if (cudaMalloc(&db->slots, (size_t)db->slots_cap * 4) != cudaSuccess) {
+        set_error("asr_db_create: cudaMalloc of the bound-sharing workspace failed");
+        DB_FAIL(ASR_ERR_CUDA);
+    }
 #undef DB_FAIL
     *out = db;
     return ASR_OK;
@@ -1313,6 +1491,7 @@ int asr_db_destroy(asr_db_t *db) {
     cudaFree(db->scratch);
     cudaFree(db->codes_n);
     cudaFree(db->qn);
+    cudaFree(db->slots);
     delete db;
     return ASR_OK;
 }
@@ -1338,6 +1517,7 @@ static void plan_grid(const asr_db *db, int64_t nq, int qt, int ctas_per_sm, int
 }
 
 static float *g_tc_dbg = nullptr;   // set by asr_debug_tc_scores
+static unsigned long long *g_tc_stats = nullptr;   // ASR_TC_STATS=1: device counters of the pre-filter kernel (diagnosis only)
 
 static int topk_tc(asr_db *db, const float *q_dev, int64_t nq, int k, float *out_score_dev, int64_t *out_idx_dev,
                    cudaStream_t st) {
@@ -1351,23 +1531,45 @@ static int topk_tc(asr_db *db, const float *q_dev, int64_t nq, int k, float *out
     }
     normalise_rows_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(q_dev, nq, db->qn);
     ASR_LAUNCH_CHECK();
+    if (!g_tc_stats && getenv("ASR_TC_STATS")) {
+        ASR_CUDA(cudaMalloc(&g_tc_stats, 128));
+        ASR_CUDA(cudaMemset(g_tc_stats, 0, 128));
+        ASR_CUDA(cudaMemcpyToSymbol(g_tc_stats_dev, &g_tc_stats, sizeof(g_tc_stats)));
+    }
     // Replicate few queries over the TMEM lane quarters so that all eight epilogue warps share a score tile.
     // (measured, 1e7 rows: 32 queries 1.01 ms replicated vs 1.07 ms not; 64 queries 1.40 vs 1.12 ms)
-    const int rep = getenv("ASR_TC_REP") ? std::min(2, std::max(1, atoi(getenv("ASR_TC_REP")))) : (nq <= 32 ? 2 : 1);
+    int rep = nq <= 32 ? 4 : (nq <= 64 ? 2 : 1);
+    if (getenv("ASR_TC_REP")) { const int r = atoi(getenv("ASR_TC_REP")); rep = r >= 4 ? 4 : (r >= 2 ? 2 : 1); }
     const int nqt = TC_QM / rep, L = 1;           // one list per (query, slice): the column ranges are merged in-kernel
     // Work items = (query tile, DB slice), ~2 per SM (1 when there are only a few query tiles: every slice adds a list
     // per query to the merge).  Since the lists of a query share their threshold bound (gkey), short items are cheap:
     // 10k queries x 125k rows (one shard of an 8-GPU DB) 2.94 -> 1.79 ms, 10k x 1M 7.0 -> 5.2 ms with the sharing.
     const int64_t n_tiles = (db->n + TC_ROWS - 1) / TC_ROWS;
     const int64_t n_qt_all = (nq + nqt - 1) / nqt;
-    const int items_per_sm = getenv("ASR_TC_ITEMS_PER_SM") ? atoi(getenv("ASR_TC_ITEMS_PER_SM")) : (n_qt_all >= 8 ? 2 : 1);
-    const int min_tiles = getenv("ASR_TC_MIN_TILES") ? atoi(getenv("ASR_TC_MIN_TILES")) : (n_qt_all >= 8 ? 64 : 32);
-    int64_t want = std::max<int64_t>(1, (items_per_sm * (int64_t)db->sms + n_qt_all - 1) / n_qt_all);
-    want = std::min<int64_t>(want, std::max<int64_t>(1, n_tiles / min_tiles));
-    const int tps = (int)((n_tiles + want - 1) / want);
+    // Slices: the work items (query tile, slice) are handed out dynamically, but they are all about equally long, so the
+    // kernel runs in rounds of `sms` items.  Choose the slice count S that minimises rounds x (tiles per slice + the
+    // fixed cost of an item).  Measured, 10k queries x 1e6 rows (79 query tiles, 3907 DB tiles), S = 3 / 4 / 5 / 7 / 8:
+    // 4.46 / 5.29 / 4.44 / 4.68 / 5.36 ms = rounds x (tiles per slice x 1.43 us + 0.37 ms): an item costs as much as
+    // 256 tiles on top of its own (the warm-up of its 128 lists).
+    const int min_tiles = getenv("ASR_TC_MIN_TILES") ? atoi(getenv("ASR_TC_MIN_TILES")) : 24;
+    const int64_t s_max = std::max<int64_t>(1, std::min<int64_t>(n_qt_all >= 4 ? 8 : 256, n_tiles / min_tiles));   // <= 256: tc_bound_large
+    int64_t best_s = 1;
+    double best_cost = 1e300;
+    for (int64_t sc = 1; sc <= s_max; ++sc) {
+        const int64_t tps_c = (n_tiles + sc - 1) / sc, ns_c = (n_tiles + tps_c - 1) / tps_c;
+        const int64_t rounds = (n_qt_all * ns_c + db->sms - 1) / db->sms;
+        const double cost = (double)rounds * ((double)tps_c + 256.0);
+        if (cost < best_cost * 0.995) { best_cost = cost; best_s = sc; }
+    }
+    if (getenv("ASR_TC_SLICES")) best_s = std::max<int64_t>(1, std::min<int64_t>(s_max, atoi(getenv("ASR_TC_SLICES"))));
+    const int tps = (int)((n_tiles + best_s - 1) / best_s);
     const int n_slices = (int)((n_tiles + tps - 1) / tps);
     const int64_t per_q = (int64_t)n_slices * L * k * 8;
-    const int64_t q_chunk = std::max<int64_t>(nqt, (int64_t)((TK_SCRATCH_BYTES - 256 - (db->qn_cap + 64) * 4) / per_q) / nqt * nqt);
+    const int spad = (n_slices + 7) & ~7;
+    unsigned *slots = db->slots;
+    int64_t q_chunk = std::max<int64_t>(nqt, (int64_t)((TK_SCRATCH_BYTES - 256 - (db->qn_cap + 64) * 4) / per_q) / nqt * nqt);
+    q_chunk = std::max<int64_t>(nqt, std::min<int64_t>(q_chunk, db->slots_cap / spad / nqt * nqt));
+    ASR_CHECK_ARG((int64_t)nqt * spad <= db->slots_cap, "bound-sharing workspace too small");
     unsigned *counter = reinterpret_cast<unsigned *>(reinterpret_cast<uint8_t *>(db->scratch) + TK_SCRATCH_BYTES - 256);
     // per-query bound shared by all lists of the query (see tc_drain): the last qn_cap words of the scratch before the counter
     unsigned *gkey = counter - ((db->qn_cap + 63) / 64 * 64);
@@ -1378,12 +1580,26 @@ static int topk_tc(asr_db *db, const float *q_dev, int64_t nq, int k, float *out
         float *ps = reinterpret_cast<float *>(db->scratch);
         uint32_t *pi = reinterpret_cast<uint32_t *>(ps + (size_t)nqc * n_slices * L * k);
         ASR_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
+        ASR_CUDA(cudaMemsetAsync(slots, 0, (size_t)(n_qt * nqt) * spad * 4, st));      // nothing published yet
         const int grid = (int)std::min<int64_t>(db->sms, n_qt * n_slices);
         topk_tc_kernel<<<grid, TC_THREADS, sizeof(TcSmem), st>>>(db->tmap_n, db->n, tps, n_slices, db->rows_n, db->qn + q0 * 32,
-                                                                 (int)nqc, k, 0.00390625f, rep, ps, pi, counter, gkey + q0, g_tc_dbg);
+                                                                 (int)nqc, k, 0.00390625f, rep, ps, pi, counter, gkey + q0, slots, g_tc_dbg, g_tc_stats,
+                                                                 (uint32_t)std::min(32, std::max(1, getenv("ASR_TC_BCAP") ? atoi(getenv("ASR_TC_BCAP")) : 32)) | (getenv("ASR_TC_NOHITS") ? 0x100u : 0u),
+                                                                 std::min(TC_RING, std::max(64, getenv("ASR_TC_RING") ? atoi(getenv("ASR_TC_RING")) : TC_RING)));
         ASR_LAUNCH_CHECK();
         launch_merge(ps, pi, nullptr, db->idx_base, n_slices * L, k, out_score_dev + q0 * k, out_idx_dev + q0 * k, nqc, st);
         ASR_LAUNCH_CHECK();
+        if (g_tc_stats) {
+            unsigned long long h[16];
+            ASR_CUDA(cudaStreamSynchronize(st));
+            ASR_CUDA(cudaMemcpy(h, g_tc_stats, sizeof(h), cudaMemcpyDeviceToHost));
+            ASR_CUDA(cudaMemset(g_tc_stats, 0, sizeof(h)));
+            fprintf(stderr, "[asr] tc stats: nq %lld rows %lld slices %d tps %d rep %d | items %llu tiles %llu | candidates %llu drains %llu "
+                    "(%.1f per drain, %.0f cycles per drain: scoring %.0f, then %.1f insertions) | scanner cycles per tile and warp: wait-for-tile %.0f, scan %.0f, push %.0f | bounds: %llu computed, %llu non-zero, %llu raised gkey; %llu publications\n",
+                    (long long)nqc, (long long)db->n, n_slices, tps, rep, h[6], h[5], h[0], h[1], h[1] ? (double)h[0] / h[1] : 0.0,
+                    h[1] ? (double)h[2] / h[1] : 0.0, h[1] ? (double)h[7] / h[1] : 0.0, h[1] ? (double)h[8] / h[1] : 0.0, h[5] ? (double)h[4] / (h[5] * TC_SCAN_WARPS) : 0.0, h[5] ? (double)h[9] / (h[5] * TC_SCAN_WARPS) : 0.0,
+                    h[5] ? (double)h[3] / (h[5] * TC_SCAN_WARPS) : 0.0, h[10], h[11], h[12], h[13]);
+        }
     }
     return ASR_OK;
 }
