@@ -1536,14 +1536,11 @@ static int topk_tc(asr_db *db, const float *q_dev, int64_t nq, int k, float *out
         ASR_CUDA(cudaMemset(g_tc_stats, 0, 128));
         ASR_CUDA(cudaMemcpyToSymbol(g_tc_stats_dev, &g_tc_stats, sizeof(g_tc_stats)));
     }
-    // Replicate few queries over the TMEM lane quarters so that all eight epilogue warps share a score tile.
-    // (measured, 1e7 rows: 32 queries 1.01 ms replicated vs 1.07 ms not; 64 queries 1.40 vs 1.12 ms)
+    // Replicate few queries over the TMEM lane quarters (the replicas split the columns) so that all scanner warps
+    // have work: <= 32 queries four times, <= 64 twice.
     int rep = nq <= 32 ? 4 : (nq <= 64 ? 2 : 1);
     if (getenv("ASR_TC_REP")) { const int r = atoi(getenv("ASR_TC_REP")); rep = r >= 4 ? 4 : (r >= 2 ? 2 : 1); }
-    const int nqt = TC_QM / rep, L = 1;           // one list per (query, slice): the column ranges are merged in-kernel
-    // Work items = (query tile, DB slice), ~2 per SM (1 when there are only a few query tiles: every slice adds a list
-    // per query to the merge).  Since the lists of a query share their threshold bound (gkey), short items are cheap:
-    // 10k queries x 125k rows (one shard of an 8-GPU DB) 2.94 -> 1.79 ms, 10k x 1M 7.0 -> 5.2 ms with the sharing.
+    const int nqt = TC_QM / rep, L = 1;           // one list per (query, slice)
     const int64_t n_tiles = (db->n + TC_ROWS - 1) / TC_ROWS;
     const int64_t n_qt_all = (nq + nqt - 1) / nqt;
     // Slices: the work items (query tile, slice) are handed out dynamically, but they are all about equally long, so the
@@ -1615,15 +1612,18 @@ int asr_topk(asr_db_t *db, const float *q_dev, int64_t nq, int k, int normalise,
     ASR_CHECK_ARG(q_dev && out_score_dev && out_idx_dev, "NULL buffer");
     cudaStream_t st = (cudaStream_t)stream;
     const char *force = getenv("ASR_TOPK_PATH");       // "exact" | "tc" (tests exercise both)
-    // measured crossovers (k = 25): the exact QT=16 kernel wins up to ~24 queries, and for small problems
-    // whatever the query count: exact ~ 0.05 ms + 7.3 ms per 1e9 scores, pre-filter ~ 1.15 ms + 0.55 ms per 1e9
-    // (profiles/r1_configs_3_5.json: its work items are at least 128 tiles long) -> equal at 1.6e8 scores
+    // measured crossovers (k = 25, ms, exact / pre-filter; profiles/r2_topk_summary.md): 1e5 rows: the exact kernel wins at
+    // every query count (Q = 256: 0.34 / 0.61); 1e6 rows: the pre-filter from Q ~ 6 (Q = 8: 0.137 / 0.116, Q = 100:
+    // 0.91 / 0.39); 1e7 rows: Q = 8 0.56 / 0.38, Q = 16 1.19 / 0.42; 1e8 rows: Q = 4 2.31 / 2.60, Q = 8 4.5 / 2.8.
+    // Many queries over a short shard (10k x 125k rows) are the pre-filter's as well: 1e8 scores and more.
     DeviceGuard guard(db->device);
     ASR_CHECK_ARG(normalise || !(db->flags & ASR_DB_NORMALISE_IN_PLACE),
                   "the raw rows are gone: this DB was created with ASR_DB_NORMALISE_IN_PLACE");
-    static const int tc_min_q = getenv("ASR_TC_MIN_Q") ? atoi(getenv("ASR_TC_MIN_Q")) : 12;
+    static const int tc_min_q = getenv("ASR_TC_MIN_Q") ? atoi(getenv("ASR_TC_MIN_Q")) : 6;
     static const double tc_min_scores = getenv("ASR_TC_MIN_SCORES") ? atof(getenv("ASR_TC_MIN_SCORES")) : 1.0e8;
-    const bool want_tc = force ? (strcmp(force, "tc") == 0) : (nq >= tc_min_q && (double)nq * (double)db->n >= tc_min_scores);
+    static const double tc_min_rows = getenv("ASR_TC_MIN_ROWS") ? atof(getenv("ASR_TC_MIN_ROWS")) : 4.0e5;
+    const bool want_tc = force ? (strcmp(force, "tc") == 0)
+                               : (nq >= tc_min_q && ((double)db->n >= tc_min_rows || (double)nq * (double)db->n >= tc_min_scores));
     if (want_tc && normalise && k <= TC_KMAX && db->rows_n) return topk_tc(db, q_dev, nq, k, out_score_dev, out_idx_dev, st);
     // cosine queries stream the pinned-normalised rows (kernel flag bit 0: normalise queries, bit 1: normalise rows
     // in-kernel -- only for handles created without them)

@@ -173,6 +173,36 @@ def test_topk_both_kernel_paths_bit_exact(monkeypatch, path, n, nq, k):
     assert (i - 77 == i_ref).all() and (s == s_ref).all()
 
 
+@pytest.mark.parametrize("n,nq,k", [(300001, 20, 25), (300001, 50, 32), (150000, 100, 25), (800003, 7, 1)])
+def test_prefilter_few_queries_many_slices_bit_exact(monkeypatch, n, nq, k):
+    """The pre-filter kernel's few-query regimes: the query tile replicated over the TMEM lane quarters (4x for
+    <= 32 queries, 2x for <= 64), one list per (query, slice) with the bound the slices share (the m-th largest of
+    the slices' published entries), a partial last tile, duplicated and zero rows."""
+    from audio_sheet_retrieval_b200.retrieval import EmbeddingDB
+    monkeypatch.setenv("ASR_TOPK_PATH", "tc")
+    D, Q = _db(n, 41), _db(nq, 42, unit=False)
+    D[n - 1] = D[5] = D[n // 3]
+    D[11] = 0
+    Q[0] = D[n // 3] * 3.0
+    s_ref, i_ref = clib.topk(Q, D, k)
+    s, i = EmbeddingDB(D, idx_base=5).topk(Q, k)
+    assert (i - 5 == i_ref).all() and (s == s_ref).all()
+
+
+def test_prefilter_identical_rows_pure_index_order(monkeypatch):
+    """Every score equal: the shared bounds and the first-tile floor all coincide with the scores themselves; the
+    result must be the k lowest indices, for every query."""
+    from audio_sheet_retrieval_b200.retrieval import EmbeddingDB
+    monkeypatch.setenv("ASR_TOPK_PATH", "tc")
+    row = _db(1, 43)
+    D = np.repeat(row, 70000, axis=0)
+    Q = _db(40, 44, unit=False)
+    s_ref, i_ref = clib.topk(Q, D, 25)
+    s, i = EmbeddingDB(D).topk(Q, 25)
+    assert (i == i_ref).all() and (s == s_ref).all()
+    assert (i == np.arange(25)[None, :]).all()
+
+
 @pytest.mark.parametrize("path", ["exact", "tc"])
 def test_topk_near_ties_within_prefilter_margin(monkeypatch, path):
     """Adversarial for the approximate pre-filter: thousands of rows whose exact scores differ by far
