@@ -189,27 +189,26 @@ class AudioSheetServer(object):
         return ret_result, ret_votes
 
     def detect_score(self, spectrogram, top_k=1, n_candidates=1, verbose=False):
-        """ detect piece from audio """
+        """ detect piece from audio (:213-253): 100 windows; the spectrogram goes to the device once and the
+        windows are cut (asr_extract_windows) and embedded there, the codes never come back to the host """
         n_samples = 100
         start_indices = np.linspace(start=0, stop=spectrogram.shape[1] - self.spec_shape[1], num=n_samples)
         start_indices = start_indices.astype(int)
-        spec_excerpts = np.zeros((len(start_indices), 1, self.spec_shape[0], self.spec_shape[1]), dtype=np.float32)
-        for i, idx in enumerate(start_indices):
-            spec_excerpts[i, 0] = spectrogram[:, idx:idx + self.spec_shape[1]]
-        spec_codes = self.embed_network.compute_view_2(spec_excerpts)
+        spec_codes = self._embed_windows(2, np.asarray(spectrogram, dtype=np.float32), start_indices, 0,
+                                         self.spec_shape[0], self.spec_shape[1])
         return self._vote(self._sheet_db, spec_codes, self.id_to_piece, top_k, n_candidates, verbose)
 
     def detect_performance(self, sheet, top_k=1, n_candidates=1, verbose=False):
-        """ detect performance from sheet """
+        """ detect performance from sheet (:255-300): 100 snippets from the vertical centre of the unrolled sheet,
+        cut and embedded on the device like detect_score """
         n_samples = 100
         start_indices = np.linspace(start=0, stop=sheet.shape[1] - self.sheet_shape[1], num=n_samples)
         start_indices = start_indices.astype(int)
         r0 = sheet.shape[0] // 2 - self.sheet_shape[0] // 2
-        r1 = r0 + self.sheet_shape[0]
-        sheet_snippets = np.zeros((len(start_indices), 1, self.sheet_shape[0], self.sheet_shape[1]), dtype=np.float32)
-        for i, idx in enumerate(start_indices):
-            sheet_snippets[i, 0] = sheet[r0:r1, idx:idx + self.sheet_shape[1]]
-        sheet_codes = self.embed_network.compute_view_1(sheet_snippets)
+        sheet = np.asarray(sheet)
+        if sheet.dtype != np.uint8:
+            sheet = sheet.astype(np.float32)      # the reference copies the windows into a float32 array
+        sheet_codes = self._embed_windows(1, sheet, start_indices, r0, self.sheet_shape[0], self.sheet_shape[1])
         return self._vote(self._audio_db, sheet_codes, self.id_to_perform, top_k, n_candidates, verbose)
 
     # -- streaming identification (the vote of `run`, :118-138, without the GUI) ----------------------
@@ -224,7 +223,7 @@ class AudioSheetServer(object):
         spec_code = self.embed_network.compute_view_2(running_spec[np.newaxis, np.newaxis, :, :])
         piece_ids, _ = self._retrieve_sheet_snippet_ids(spec_code, n_candidates=n_candidates)
         self._stream_ids = np.concatenate((self._stream_ids, piece_ids))
-        first_idx = running_frames * n_candidates
+        first_idx = running_frames * n_candidates if running_frames is not None else 0
         if running_frames is not None and self._stream_ids.shape[0] > first_idx:
             self._stream_ids = self._stream_ids[-first_idx:]
         dev = self._sheet_db.device
@@ -236,6 +235,41 @@ class AudioSheetServer(object):
         keep = out_ids >= 0
         probs = out_cnt[keep].astype(float) / len(self._stream_ids)
         return [self.id_to_piece[i] for i in out_ids[keep]], probs
+
+    def run(self, spec, top_k=5, n_candidates=5, running_frames=None, gui=False, target_piece=None, verbose=True):
+        """ run sheet retrieval service over a recorded spectrogram (:83-211 without the GUI and the microphone;
+        the music detector of `_detect_music` is a separate network that is not part of this path, every frame
+        counts as music).  One frame = one spectrogram column; from the first full window on, every frame is
+        embedded, its n_candidates nearest sheet snippets vote.  Prints the reference's fps line and returns
+        (names, probabilities, frames per second over the frames that did retrieval). """
+        import sys
+        import time
+        if gui:
+            raise NotImplementedError("the matplotlib GUI of the reference is not part of this package")
+        if verbose:
+            print("Running server ...")
+        running_spec = np.zeros((self.spec_shape[0], self.spec_shape[1]), dtype=np.float32)
+        self.reset_stream()
+        frame_times = np.zeros(10)
+        names, probs, t_retrieval, n_retrieval = [], np.zeros(0), 0.0, 0
+        for i_frame in range(spec.shape[1]):
+            start = time.time()
+            running_spec = np.hstack((running_spec[:, 1::], spec[:, i_frame:i_frame + 1])).astype(np.float32)
+            if i_frame >= running_spec.shape[1]:
+                names, probs = self.process_frame(running_spec, top_k=top_k, n_candidates=n_candidates,
+                                                  running_frames=running_frames)
+                t_retrieval += time.time() - start
+                n_retrieval += 1
+            stop = time.time()
+            frame_times[1:] = frame_times[0:-1]
+            frame_times[0] = stop - start
+            fps = 1.0 / np.mean(frame_times)
+            if verbose:
+                print("Server is running at %.2f fps." % fps, end='\r')
+                sys.stdout.flush()
+        if verbose:
+            print("")
+        return names, probs, (n_retrieval / t_retrieval if t_retrieval > 0 else 0.0)
 
     # -- batched identification over many recordings (config "piece identification") -----------
     def identify_from_codes(self, query_codes, n_recordings, top_k=1, n_candidates=25, direction="A2S"):

@@ -129,6 +129,63 @@ def test_detect_score_end_to_end():
     assert names[0] == "rec2" and votes[0] > 0.5 and abs(votes.sum() - 1.0) < 1e-12
 
 
+def test_detect_on_device_windows_equals_host_window_loop():
+    """detect_score / detect_performance cut their 100 windows on the device (one upload, asr_extract_windows) and
+    keep the codes there; the reference's loop (audio_sheet_server.py:216-223, 260-271: host slices -> compute_view_x
+    -> per-window retrieval -> vote) must give the same names and vote shares."""
+    from audio_sheet_retrieval_b200.audio_sheet_server import AudioSheetServer
+    from audio_sheet_retrieval_b200.models import mutopia_ccal_cont_rsz as model
+    rng = np.random.RandomState(7)
+    srv = AudioSheetServer()
+    srv.initialize_embedding_network(model, PKL)
+    specs = [np.abs(rng.normal(0, 0.3, (92, 420))).astype(np.float32) * (rng.rand(92, 1) > 0.6) for _ in range(5)]
+    sheets = [(rng.rand(180, 1400) > 0.8).astype(np.uint8) * 255 for _ in range(5)]
+    srv.initialize_audio_db_from_specs(["p%d" % i for i in range(5)], specs)
+    a_codes, a_ids = srv.perform_excerpt_codes, srv.perform_excerpt_ids
+    srv.initialize_sheet_db_from_imges(["p%d" % i for i in range(5)], sheets)
+    srv.set_sheet_db(a_codes, a_ids, srv.id_to_perform)          # audio windows as the DB of detect_score
+    sh_codes = srv.embed_network.compute_view_1(np.stack(
+        [sheets[i][None, 10:170, s:s + 200] for i in range(5) for s in range(0, 1200, 50)]).astype(np.float32))
+    srv.set_audio_db(sh_codes, np.repeat(np.arange(5), 24), srv.id_to_perform)   # sheet windows as the DB of detect_performance
+    # host-window restatement of the two reference loops
+    for which, src, shape in (("score", specs[3], (92, 42)), ("perf", sheets[1].astype(np.float32), (160, 200))):
+        starts = np.linspace(0, src.shape[1] - shape[1], 100).astype(int)
+        r0 = 0 if which == "score" else src.shape[0] // 2 - 80
+        wins = np.stack([src[None, r0:r0 + shape[0], s:s + shape[1]] for s in starts]).astype(np.float32)
+        if which == "score":
+            codes = srv.embed_network.compute_view_2(wins)
+            ref = srv._vote(srv._sheet_db, codes, srv.id_to_piece, 3, 5, False)
+            got = srv.detect_score(src, top_k=3, n_candidates=5)
+        else:
+            codes = srv.embed_network.compute_view_1(wins)
+            ref = srv._vote(srv._audio_db, codes, srv.id_to_perform, 3, 5, False)
+            got = srv.detect_performance(src, top_k=3, n_candidates=5)
+        assert got[0] == ref[0] and np.array_equal(got[1], ref[1])
+    assert srv.detect_score(specs[3], 1, 5)[0][0] == "p3" and srv.detect_performance(sheets[1], 1, 5)[0][0] == "p1"
+
+
+def test_headless_run_equals_process_frame_sequence():
+    """AudioSheetServer.run over a recorded spectrogram (the reference's loop without GUI, microphone and music
+    detector) ends with the ranking of the frame-by-frame calls and reports a frame rate."""
+    from audio_sheet_retrieval_b200.audio_sheet_server import AudioSheetServer
+    from audio_sheet_retrieval_b200.models import mutopia_ccal_cont_rsz as model
+    rng = np.random.RandomState(8)
+    srv = AudioSheetServer()
+    srv.initialize_embedding_network(model, PKL)
+    srv.set_sheet_db(rng.normal(size=(400, 32)).astype(np.float32), np.repeat(np.arange(8), 50),
+                     dict((i, "p%d" % i) for i in range(8)))
+    spec = np.abs(rng.normal(0, 0.3, (92, 60))).astype(np.float32)
+    names, probs, fps = srv.run(spec, top_k=3, n_candidates=5, running_frames=10, verbose=False)
+    srv.reset_stream()
+    running = np.zeros((92, 42), np.float32)
+    ref = None
+    for f in range(60):
+        running = np.hstack((running[:, 1:], spec[:, f:f + 1]))
+        if f >= 42:
+            ref = srv.process_frame(running, top_k=3, n_candidates=5, running_frames=10)
+    assert names == ref[0] and np.array_equal(probs, ref[1]) and fps > 0
+
+
 def test_db_from_raw_material_matches_reference_loop(tmp_path):
     """initialize_*_db_from_* (audio_sheet_server.py:403-494): same window grid, same codes, same ids."""
     from audio_sheet_retrieval_b200.audio_sheet_server import AudioSheetServer, extract_windows_device
