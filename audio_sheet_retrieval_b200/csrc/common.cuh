@@ -120,6 +120,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     }
 }
 
+// Relaxed wait for roles that run ahead of the critical path (a producer waiting for a free stage): try_wait with a
+// suspend-time hint parks the warp in hardware instead of spinning, which gives its issue slots to the warps that work
+// (at the price of some wake-up latency).  Same bounded-wait guarantee.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const uint64_t t0 = globaltimer_ns();
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(2000u)
+            : "memory");
+        if (ok) return;
+        if (globaltimer_ns() - t0 > 4000000000ull) {
+            printf("asr: mbarrier timeout block %d thread %d parity %u\n", blockIdx.x, threadIdx.x, parity);
+            __trap();
+        }
+    }
+}
+
 // the same with a caller-supplied tag in the timeout message (which role waited, at which step)
 __device__ __forceinline__ void mbar_wait_tag(uint64_t *bar, uint32_t parity, int tag) {
     if (mbar_try_wait(bar, parity)) return;

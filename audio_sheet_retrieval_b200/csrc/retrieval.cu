@@ -1025,7 +1025,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles
                 for (int64_t it = 0; it < my_tiles; ++it) {
                     const int64_t g = itg + it;
                     const int s = (int)(g % TC_STAGES);
-                    mbar_wait(&sm.empty[s], (uint32_t)(((g / TC_STAGES) & 1) ^ 1));
+                    mbar_wait_relaxed(&sm.empty[s], (uint32_t)(((g / TC_STAGES) & 1) ^ 1));
                     mbar_expect_tx(&sm.full[s], TC_ROWS * 128);
                     tma_load_2d(sm.stage[s], &tmap, 0, (int)((tile0 + it) * TC_ROWS), &sm.full[s]);
                 }
@@ -1037,8 +1037,8 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles
                 const int64_t g = itg + it;
                 const int s = (int)(g % TC_STAGES);
                 const uint32_t slot = (uint32_t)(g & 1);
-                mbar_wait(&sm.full[s], (uint32_t)((g / TC_STAGES) & 1));
-                mbar_wait(&sm.tempty[slot], (uint32_t)(((g >> 1) & 1) ^ 1));
+                mbar_wait_relaxed(&sm.full[s], (uint32_t)((g / TC_STAGES) & 1));
+                mbar_wait_relaxed(&sm.tempty[slot], (uint32_t)(((g >> 1) & 1) ^ 1));
                 tc_fence_after();
                 if (leader) {
                     const uint32_t baddr = smem_u32(sm.stage[s]);
@@ -1070,7 +1070,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles
                 const unsigned gk = gk_next;
                 if (qvalid) gk_next = __ldcg(gkey + q0 + qi);
                 const long long tw0 = stats ? clock64() : 0;
-                mbar_wait(&sm.tfull[slot], (uint32_t)((g >> 1) & 1));
+                mbar_wait_relaxed(&sm.tfull[slot], (uint32_t)((g >> 1) & 1));
                 const long long tsc0 = stats ? clock64() : 0;
                 if (stats && lane == 0) atomicAdd(stats + 4, (unsigned long long)(tsc0 - tw0));
                 tc_fence_after();
@@ -1207,7 +1207,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles
             const int S = n_slices, spad = (n_slices + 7) & ~7;
             const int jpub = (k + min(S, k) - 1) / min(S, k);          // which entry of its list every slice publishes
             const int m_need = (k + jpub - 1) / jpub;                  // published lists needed for a bound
-            uint32_t drains = 0u, next_refresh = 1u;
+            uint32_t drains = 0u, next_refresh = 1u, idle_ns = 200u;
             bool flush = false;
             for (;;) {
                 // cheap poll: how much has been reserved beyond what this warp has consumed
@@ -1217,9 +1217,11 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles
                                                              (rv == ring_h ? 2 : 0), 0);
                 if ((st8 & 3) == 3) break;                             // scanners done, everything consumed
                 if (!(st8 & 4) && !(st8 & 1)) {                        // partial batch, item still running: wait (a drain costs
-                    __nanosleep(300);                                  // thousands of cycles whatever its size)
+                    __nanosleep(idle_ns);                              // thousands of cycles whatever its size), backing off:
+                    idle_ns = min(idle_ns * 2u, 2000u);                // polling took a fifth of the SM's issue slots
                     continue;
                 }
+                idle_ns = 200u;
                 const uint32_t pos = ring_h + (uint32_t)lane;
                 const unsigned long long ent = lds_volatile_u64(&sm.ring[o][pos & (TC_RING - 1)]);
                 const bool valid = (uint32_t)(ent >> 40) == (((pos / TC_RING) + 1u) & 0xffffffu);
