@@ -328,16 +328,19 @@ def config1_leg(torch, dev, with_cpu):
         w = RetrievalWrapper(model, PKL_RSZ, prepare_view_1=model.prepare, prepare_view_2=None)
     w.compute_view_1(X1[:200]); w.compute_view_2(X2[:200])
     torch.cuda.synchronize()
-    t = time.perf_counter()
-    c1, c2 = w.compute_view_1(X1), w.compute_view_2(X2)
-    t_embed = time.perf_counter() - t
+    t_embed = t_eval = float("inf")
+    for _ in range(3):                      # 20 + 20 latency-bound calls of 100 rows each (the reference's batching): best of 3
+        t = time.perf_counter()
+        c1, c2 = w.compute_view_1(X1), w.compute_view_2(X2)
+        t_embed = min(t_embed, time.perf_counter() - t)
     eval_retrieval(c1[:100], c2[:100])
-    t = time.perf_counter()
-    mr, med, md, hr, mrr = eval_retrieval(c1, c2)
-    t_eval = time.perf_counter() - t
+    for _ in range(3):
+        t = time.perf_counter()
+        mr, med, md, hr, mrr = eval_retrieval(c1, c2)
+        t_eval = min(t_eval, time.perf_counter() - t)
     out = {"model": "mutopia_ccal_cont_rsz (tutorial pickle)", "pairs": n, "embed_pairs_per_s": n / t_embed,
            "embed_ms": t_embed * 1e3, "eval_retrieval_ms": t_eval * 1e3,
-           "api": "RetrievalWrapper.compute_view_1/2 (NumPy in, NumPy out) + eval_retrieval",
+           "api": "RetrievalWrapper.compute_view_1/2 (NumPy in, NumPy out, 100 rows per call like the reference) + eval_retrieval; best of 3",
            "metrics": {"mrr": float(mrr), "median_rank": float(med), "mean_rank": float(mr),
                        "recall_at_k": dict((str(k), 100.0 * hr[k] / n) for k in (1, 5, 10, 25))}}
     if with_cpu:
