@@ -41,6 +41,27 @@ int ensure_device() {
 
 int sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
 
+// Does this process hold an active primary context on `dev`?  (Driver entry point through the runtime: the library
+// does not link libcuda.)  Unknown -> true: restoring the caller's device is the conservative answer.
+bool device_context_active(int dev) {
+    typedef int (*PFN_state)(int, unsigned int *, int *);
+    static PFN_state fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuDevicePrimaryCtxGetState", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_state>(p);
+        tried = true;
+    }
+    if (!fn) return true;
+    unsigned int flags = 0;
+    int active = 1;
+    if (fn(dev, &flags, &active) != 0) return true;      // CUdevice handles are the ordinals
+    return active != 0;
+}
+
 }  // namespace asr
 
 extern "C" {

@@ -55,6 +55,11 @@ inline int current_device() {
 // Handles are bound to the device that was current at create.  The CUDA runtime's current device is per host thread
 // (a new thread starts on device 0), so every entry point that takes a handle switches to the handle's device for the
 // duration of the call and restores the caller's device afterwards.
+// The previous device is only restored when this process already has a primary context there: since CUDA 12
+// cudaSetDevice CREATES the context, and a fresh host thread "was" on device 0 without ever having used it -- restoring
+// that would build a context on GPU 0 in every rank of a multi-GPU job (measured: 0.5-1 s and a few hundred MB, once
+// per process, in the middle of the first call from a worker thread).
+bool device_context_active(int dev);   // abi.cu (cuDevicePrimaryCtxGetState)
 struct DeviceGuard {
     int prev = -1;
     explicit DeviceGuard(int dev) {
@@ -65,7 +70,7 @@ struct DeviceGuard {
         }
     }
     ~DeviceGuard() {
-        if (prev >= 0) cudaSetDevice(prev);
+        if (prev >= 0 && device_context_active(prev)) cudaSetDevice(prev);
     }
 };
 

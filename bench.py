@@ -582,7 +582,11 @@ def main():
     c1h, c2h = res["v1"], res["v2"]
     dt = torch.tensor([(time.perf_counter() - t0) / k_e2e], device=dev, dtype=torch.float64)
     ms_v1, ms_v2 = t_br["v1"] / k_e2e * 1e3, t_br["v2"] / k_e2e * 1e3
+    dt_all = [float(dt.item())]
     if world > 1:
+        gathered = [torch.zeros_like(dt) for _ in range(world)]
+        dist.all_gather(gathered, dt)
+        dt_all = [float(g.item()) for g in gathered]
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_value = world * n_e2e / float(dt.item())
     same = bool(np.array_equal(c1h, codes1[:n_e2e].cpu().numpy()) and np.array_equal(c2h, codes2[:n_e2e].cpu().numpy()))
@@ -604,6 +608,7 @@ def main():
            "api": "asr_encoder_embed_host (what RetrievalWrapper.compute_view_1/2 call)", "codes_equal_device_path": same,
            "ms_per_step_sheet_branch": ms_v1, "ms_per_step_spectrogram_branch": ms_v2,
            "concurrency": "the two branch calls run concurrently from two host threads",
+           "ms_per_step_by_rank": [x * 1e3 for x in dt_all],
            "h2d_gbs_used": h2d / float(dt.item()) / 1e9,
            "h2d_gbs_plain_pinned_copy": link_gbs,
            "host_link_note": "min over ranks of a plain pinned copy with all %d rank(s) copying at once; e2e needs "
