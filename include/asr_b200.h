@@ -136,7 +136,8 @@ typedef struct asr_db asr_db_t;
  * handle exists.  idx_base: global index of row 0 (this shard's offset in a sharded DB).
  * Everything the handle ever needs is allocated HERE (asr_topk / asr_rank_of_target never allocate):
  *   - 64 MB of scratch for per-slice partial lists,
- *   - a query workspace of max_queries rows (more queries per call are processed in chunks of that size),
+ *   - a query workspace of max_queries rows (more queries per call are processed in chunks of that size) and
+ *     (8 * max_queries + 262144) words in which the DB slices of a query share their threshold bounds,
  *   - the rows normalised with the pinned definition, which cosine queries stream:
  *       flags = 0                        an owned copy, n * 128 bytes (a 1e8-row DB: 12.8 GB + 12.8 GB)
  *       ASR_DB_NORMALISE_IN_PLACE        the caller donates its buffer: rows are overwritten with their normalised
@@ -145,7 +146,9 @@ typedef struct asr_db asr_db_t;
  *                                        the tensor-core pre-filter needs the normalised rows)
  * The create call runs one kernel on the default stream and synchronises; the handle is bound to the current
  * device.  One stream at a time per handle: its scratch is shared by consecutive calls (calls on the SAME stream
- * serialise naturally; concurrent use from two streams needs two handles). */
+ * serialise naturally; concurrent use from two streams needs two handles).  Entry points may be called from any
+ * host thread: they switch to the handle's device for the call and leave the thread on a device the process already
+ * uses (a fresh thread's implicit device 0 is not touched, so no context is ever created as a side effect). */
 #define ASR_DB_NORMALISE_IN_PLACE 1
 #define ASR_DB_NO_COSINE_COPY 2
 int asr_db_create_ex(asr_db_t **out, const float *codes_dev, int64_t n, int64_t idx_base, int flags, int64_t max_queries);
