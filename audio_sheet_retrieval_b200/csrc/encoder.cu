@@ -90,6 +90,7 @@ constexpr int EPI_THREADS = N_EPI_GROUPS * 128;
 constexpr int CONV_THREADS = 32 * EPI_WARP0 + EPI_THREADS;   // warp 0 TMA, warps 1..4 MMA, warps 5..20 epilogue
 constexpr int TAIL_SLACK = 2080;
 constexpr int MAX_SLOTS = 8;
+constexpr int MAX_STAGES = 6;          // input ring of the raster kernel (2 for bands that are big, more for small ones)
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 // --------------------------------------------------------------------------------------
@@ -112,16 +113,16 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(const ConvP
     uint8_t *stage_sm = smem + p.off_stage;
     uint8_t *staging_sm = smem + p.off_staging;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + p.off_bar);
-    uint64_t *w_full = bars;                       // 1
-    uint64_t *in_full = bars + 1;                  // [2]
-    uint64_t *in_empty = bars + 3;                 // [2]
-    uint64_t *acc_full = bars + 5;                 // [MAX_SLOTS]
-    uint64_t *acc_empty = bars + 5 + MAX_SLOTS;    // [MAX_SLOTS]
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 5 + 2 * MAX_SLOTS);
+    uint64_t *w_full = bars;                                        // 1
+    uint64_t *in_full = bars + 1;                                   // [MAX_STAGES]
+    uint64_t *in_empty = bars + 1 + MAX_STAGES;                     // [MAX_STAGES]
+    uint64_t *acc_full = bars + 1 + 2 * MAX_STAGES;                 // [MAX_SLOTS]
+    uint64_t *acc_empty = bars + 1 + 2 * MAX_STAGES + MAX_SLOTS;    // [MAX_SLOTS]
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 1 + 2 * MAX_STAGES + 2 * MAX_SLOTS);
 
     if (tid == 0) {
         mbar_init(w_full, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&in_full[s], 1); mbar_init(&in_empty[s], N_MMA_WARPS); }
+        for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&in_full[s], 1); mbar_init(&in_empty[s], N_MMA_WARPS); }
         for (int s = 0; s < MAX_SLOTS; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
         mbar_fence_init();
     }
@@ -1369,6 +1370,17 @@ static bool plan_conv(const LayerGeom &g, ConvPlan &pl) {
             break;
         }
         if (ns == 1) return false;
+    }
+    {   // Small bands (the narrow deep layers: a whole 22x27 or 13x7 image is 1-5 tiles) finish faster than a bulk copy
+        // arrives, so two stages leave the MMA warps waiting for data: use the shared memory that is left for a deeper
+        // ring (ASR_CONV_STAGES caps it; 2 = the previous behaviour).
+        static const int cap = getenv("ASR_CONV_STAGES") ? std::max(1, std::min(MAX_STAGES, atoi(getenv("ASR_CONV_STAGES")))) : MAX_STAGES;
+        const long long sps = (long long)(pl.TH + 2) * Wp * 16;
+        const long long stage = ((16 + KC * sps + TAIL_SLACK) + 127) / 128 * 128;
+        const long long staging = g.pool ? (long long)NCH * pl.TH * Wp * 16 : 0;
+        while (pl.n_stages >= 2 && pl.n_stages < cap &&
+               pl.wbytes + NP * 4 + 128 + (pl.n_stages + 1) * stage + 128 + staging + 256 + 256 <= SMEM_LIMIT)
+            ++pl.n_stages;
     }
     pl.bands = (Hc + pl.TH - 1) / pl.TH;
     pl.MT = (pl.TH * Wp + 127) / 128;
