@@ -957,7 +957,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles_per_slice, int n_slices,
                const float *__restrict__ rows, const float *__restrict__ qn, int nq, int k, float eps, int rep,
                float *__restrict__ part_s, uint32_t *__restrict__ part_i, unsigned *__restrict__ work_counter,
-               unsigned *__restrict__ gkey, unsigned *__restrict__ slots, float *dbg, unsigned long long *stats, uint32_t bcap, int ring_lim) {
+               unsigned *__restrict__ gkey, unsigned *__restrict__ slots, float *dbg, unsigned long long *stats, uint32_t bcap, int ring_lim, int warm_max) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     TcSmem &sm = *reinterpret_cast<TcSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
@@ -1004,6 +1004,23 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles
         if (my_tiles > tiles_per_slice) my_tiles = tiles_per_slice;
         if (my_tiles < 0) my_tiles = 0;
         const int q0 = qt * nqt;
+        // Warm-up pass: the first T tiles of the item are scored TWICE.  The first time (virtual tiles 0 .. T-1) the
+        // scanners only collect, per thread, the largest approximate score of each tile's chunk; from those group
+        // maxima they derive a floor for the query's k-th best (below) before a single candidate is emitted.  The
+        // second time round (virtual tiles T ...) is the normal scan from tile 0 on.  T tiles of MMA + scan buy a
+        // floor at the ~k / (256 T) quantile instead of starting at -inf: without it the first tiles of an item
+        // flood the owners with candidates, and while those are worked off the scanners run on stale thresholds.
+        int T = 0;
+        {
+            int64_t full_tiles = n_db / TC_ROWS - tile0;            // complete tiles at the start of the item
+            if (full_tiles > my_tiles) full_tiles = my_tiles;
+            if (full_tiles >= 8 && warm_max > 0) {
+                int64_t t = my_tiles / 8;
+                t = t < 8 ? 8 : (t > warm_max ? warm_max : t);
+                T = (int)(t > full_tiles ? full_tiles : t);
+            }
+        }
+        const int64_t v_tiles = my_tiles + T;                       // virtual tiles of the item
         // stage the query tile (rep copies), swizzled like a SWIZZLE_128B TMA load; rows beyond nq are zero
         for (int i = tid; i < TC_QM * 8; i += TC_THREADS) {
             const int row = i >> 3, c = i & 7;
@@ -1022,8 +1039,8 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles
 
         if (warp == 0) {
             if (lane == 0) {
-                for (int64_t it = 0; it < my_tiles; ++it) {
-                    const int64_t g = itg + it;
+                for (int64_t v = 0; v < v_tiles; ++v) {
+                    const int64_t g = itg + v, it = v < T ? v : v - T;
                     const int s = (int)(g % TC_STAGES);
                     mbar_wait_relaxed(&sm.empty[s], (uint32_t)(((g / TC_STAGES) & 1) ^ 1));
                     mbar_expect_tx(&sm.full[s], TC_ROWS * 128);
@@ -1033,8 +1050,8 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles
         } else if (warp == 1) {
             const uint32_t leader = elect_one() ? 1u : 0u;
             const uint32_t qaddr = smem_u32(sm.q);
-            for (int64_t it = 0; it < my_tiles; ++it) {
-                const int64_t g = itg + it;
+            for (int64_t v = 0; v < v_tiles; ++v) {
+                const int64_t g = itg + v;
                 const int s = (int)(g % TC_STAGES);
                 const uint32_t slot = (uint32_t)(g & 1);
                 mbar_wait_relaxed(&sm.full[s], (uint32_t)((g / TC_STAGES) & 1));
@@ -1064,8 +1081,67 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles
             // the best bound anybody on this GPU has published for this query: an L2 read (1000+ cycles while the TMA stream
             // keeps the L2 busy), so it is issued one tile ahead and never waited for
             unsigned gk_next = qvalid ? __ldcg(gkey + q0 + qi) : 0u;
+            if (T > 0) {
+                // ---- pass A (virtual tiles 0 .. T-1): group maxima only, then the floor ----
+                float top[8];                                    // this thread's largest per-tile maxima, descending
+#pragma unroll
+                for (int j = 0; j < 8; ++j) top[j] = -CUDART_INF_F;
+                for (int64_t v = 0; v < T; ++v) {
+                    const int64_t g = itg + v;
+                    const uint32_t slot = (uint32_t)(g & 1);
+                    mbar_wait_relaxed(&sm.tfull[slot], (uint32_t)((g >> 1) & 1));
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + slot * 256u + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col0;
+                        // Pass A.  A query's scores of one tile sit in P = 4 rep scanner threads (ncols columns each).  Every
+                        // thread keeps the 8 largest of its per-tile maxima; after T tiles its jfl-th largest, jfl =
+                        // ceil(k / P), has jfl DISTINCT rows at or above it, so the minimum `lo` over the P threads has
+                        // P jfl >= k rows at or above it, whose exact scores are >= lo - eps: the final k-th best of the
+                        // list is >= lo - eps.  (All tiles of the pass are complete: no zero-filled rows are counted.)
+                        if (warp_valid) {
+                            float gm = -CUDART_INF_F;
+#pragma unroll 1
+                            for (int u = 0; u < ncols; u += 32) {
+                                uint32_t vv[32];
+                                tmem_ld16_issue(taddr + (uint32_t)u, vv);
+                                if (ncols >= 32) tmem_ld16_issue(taddr + (uint32_t)(u + 16), vv + 16);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) gm = fmaxf(gm, __uint_as_float(vv[j]));      // fmaxf drops NaNs (zero rows)
+                                if (ncols >= 32) {
+#pragma unroll
+                                    for (int j = 16; j < 32; ++j) gm = fmaxf(gm, __uint_as_float(vv[j]));
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {                // insertion into the descending array, branch-free
+                                const float hi = fmaxf(top[j], gm), lo2 = fminf(top[j], gm);
+                                top[j] = hi;
+                                gm = lo2;
+                            }
+                        }
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&sm.tempty[slot]);
+                        if (v == T - 1) {
+                            const int jfl = (k + 4 * rep - 1) / (4 * rep);
+                            float mine = top[0];
+#pragma unroll
+                            for (int j = 1; j < 8; ++j) mine = j == jfl - 1 ? top[j] : mine;
+                            if (jfl > T) mine = -CUDART_INF_F;           // fewer groups than needed (cannot happen: T >= 8 >= jfl)
+                            if (qvalid) atomicMin(&sm.fmin_key[qi], mine > -CUDART_INF_F ? fkey(mine) : 0u);   // 0: no floor
+                            asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_SCAN_WARPS) : "memory");
+                            const uint32_t fm = sm.fmin_key[qi];
+                            if (qvalid && fm != 0u && fm != 0xffffffffu && (ql / nqt) == 0 && cidx == 0) {   // one thread per query
+                                const float floor_s = fkey_inv(fm) - eps;
+                                atomicMax(&sm.floor_key[qi], (unsigned long long)fkey(floor_s) << 32);   // ties with the floor itself still enter
+                                atomicMax(&sm.tau_key[qi], fkey(floor_s - eps));
+                            }
+                            asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_SCAN_WARPS) : "memory");     // floors visible before pass B
+                        }
+                }
+            }
             for (int64_t it = 0; it < my_tiles; ++it) {
-                const int64_t g = itg + it;
+                const int64_t g = itg + T + it;
                 const uint32_t slot = (uint32_t)(g & 1);
                 const unsigned gk = gk_next;
                 if (qvalid) gk_next = __ldcg(gkey + q0 + qi);
@@ -1077,39 +1153,6 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles
                 const uint32_t taddr = tmem_base + slot * 256u + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col0;
                 const int64_t row0 = (tile0 + it) * TC_ROWS;
                 uint32_t hit0 = 0u, hit1 = 0u;
-                if (it == 0 && row0 + TC_ROWS <= n_db) {             // CTA-uniform
-                    // Threshold floor from the first (full) tile.  A query's 256 scores sit in P = 4 rep scanner threads
-                    // (ncols columns each): every thread bisects for a value such that at least jfl = ceil(k / P) of ITS
-                    // approximate scores are >= it; the minimum `lo` over the P threads then has >= k rows at or above it,
-                    // whose exact scores are >= lo - eps.  So the final k-th best of the list is >= lo - eps: a floor
-                    // at the ~k/256 quantile of a tile, which removes most of the list's warm-up.
-                    const int jfl = (k + 4 * rep - 1) / (4 * rep);
-                    if (warp_valid) {
-                        float lo = -2.0f, hi = 2.0f;
-#pragma unroll 1
-                        for (int iter = 0; iter < 12; ++iter) {
-                            const float mid = 0.5f * (lo + hi);
-                            int cnt = 0;
-#pragma unroll 1
-                            for (int c16 = 0; c16 < ncols; c16 += 16) {
-                                float v[16];
-                                tmem_ld16(taddr + (uint32_t)c16, v);
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) cnt += v[j] >= mid ? 1 : 0;
-                            }
-                            if (cnt >= jfl) lo = mid; else hi = mid;
-                        }
-                        if (qvalid) atomicMin(&sm.fmin_key[qi], lo > -2.0f ? fkey(lo) : 0u);   // 0: no floor (all-NaN / degenerate tiles)
-                    }
-                    asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_SCAN_WARPS) : "memory");
-                    const uint32_t fm = sm.fmin_key[qi];
-                    if (qvalid && fm != 0u && fm != 0xffffffffu && (ql / nqt) == 0 && cidx == 0) {   // one thread per query
-                        const float floor_s = fkey_inv(fm) - eps;
-                        atomicMax(&sm.floor_key[qi], (unsigned long long)fkey(floor_s) << 32);   // ties with the floor itself still enter
-                        atomicMax(&sm.tau_key[qi], fkey(floor_s - eps));
-                    }
-                    asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_SCAN_WARPS) : "memory");     // floors visible before the tile is scanned
-                }
                 if (warp_valid) {
                     const float tau = (qvalid && !(bcap & 0x100u)) ? fmaxf(fkey_inv(lds_volatile_u32(&sm.tau_key[qi])), fkey_inv(gk) - eps) : CUDART_INF_F;   // bcap bit 8: diagnosis, nothing passes
                     // Scan 32 columns per TMEM round trip (16 when the chunk is split four ways).  NaN approximations
@@ -1121,7 +1164,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles
                         tmem_ld16_issue(taddr + (uint32_t)u, v);
                         if (ncols >= 32) tmem_ld16_issue(taddr + (uint32_t)(u + 16), v + 16);
                         tmem_ld_wait();
-                        if (dbg && slice == 0 && qt == 0 && it == 0) {      // debug: dump the approximate scores of tile 0
+                        if (dbg && slice == 0 && qt == 0 && it == 0) {      // debug: dump the approximate scores of tile 0 (pass B)
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
                                 if (j < ncols) dbg[qi * TC_ROWS + col0 + u + j] = __uint_as_float(v[j]);
@@ -1266,8 +1309,8 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles
                 }
             }
         }
-        if (stats && tid == 0) { atomicAdd(stats + 5, (unsigned long long)my_tiles); atomicAdd(stats + 6, 1ull); }
-        itg += my_tiles;
+        if (stats && tid == 0) { atomicAdd(stats + 5, (unsigned long long)v_tiles); atomicAdd(stats + 6, 1ull); }
+        itg += v_tiles;
         ++item_seq;
         __syncthreads();     // every role is done with sm.q / the lists before the next query tile
     }
@@ -1547,17 +1590,18 @@ static int topk_tc(asr_db *db, const float *q_dev, int64_t nq, int k, float *out
     const int64_t n_qt_all = (nq + nqt - 1) / nqt;
     // Slices: the work items (query tile, slice) are handed out dynamically, but they are all about equally long, so the
     // kernel runs in rounds of `sms` items.  Choose the slice count S that minimises rounds x (tiles per slice + the
-    // fixed cost of an item).  Measured, 10k queries x 1e6 rows (79 query tiles, 3907 DB tiles), S = 3 / 4 / 5 / 7 / 8:
-    // 4.46 / 5.29 / 4.44 / 4.68 / 5.36 ms = rounds x (tiles per slice x 1.43 us + 0.37 ms): an item costs as much as
-    // 256 tiles on top of its own (the warm-up of its 128 lists).
+    // fixed cost of an item).  Measured, 10k queries x 1e6 rows (79 query tiles, 3907 DB tiles), S = 2 / 3 / 4 / 5 / 7:
+    // 5.52 / 3.89 / 4.54 / 3.75 / 3.81 ms = rounds x (tiles per slice x 1.33 us + 0.22 ms): an item costs as much as
+    // 165 tiles on top of its own (warm-up pass + list warm-up).
     const int min_tiles = getenv("ASR_TC_MIN_TILES") ? atoi(getenv("ASR_TC_MIN_TILES")) : 24;
-    const int64_t s_max = std::max<int64_t>(1, std::min<int64_t>(n_qt_all >= 4 ? 8 : 256, n_tiles / min_tiles));   // <= 256: tc_bound_large
+    const int64_t s_max = std::max<int64_t>(1, std::min<int64_t>(256, n_tiles / min_tiles));   // <= 256: tc_bound_large
     int64_t best_s = 1;
     double best_cost = 1e300;
     for (int64_t sc = 1; sc <= s_max; ++sc) {
         const int64_t tps_c = (n_tiles + sc - 1) / sc, ns_c = (n_tiles + tps_c - 1) / tps_c;
         const int64_t rounds = (n_qt_all * ns_c + db->sms - 1) / db->sms;
-        const double cost = (double)rounds * ((double)tps_c + 256.0);
+        if (ns_c > TC_SLOT_SMALL && rounds > 1) continue;     // more than 8 slices share their bound only while ALL lists of a query run at once
+        const double cost = (double)rounds * ((double)tps_c + 165.0);
         if (cost < best_cost * 0.995) { best_cost = cost; best_s = sc; }
     }
     if (getenv("ASR_TC_SLICES")) best_s = std::max<int64_t>(1, std::min<int64_t>(s_max, atoi(getenv("ASR_TC_SLICES"))));
@@ -1584,7 +1628,8 @@ static int topk_tc(asr_db *db, const float *q_dev, int64_t nq, int k, float *out
         topk_tc_kernel<<<grid, TC_THREADS, sizeof(TcSmem), st>>>(db->tmap_n, db->n, tps, n_slices, db->rows_n, db->qn + q0 * 32,
                                                                  (int)nqc, k, 0.00390625f, rep, ps, pi, counter, gkey + q0, slots, g_tc_dbg, g_tc_stats,
                                                                  (uint32_t)std::min(32, std::max(1, getenv("ASR_TC_BCAP") ? atoi(getenv("ASR_TC_BCAP")) : 32)) | (getenv("ASR_TC_NOHITS") ? 0x100u : 0u),
-                                                                 std::min(TC_RING, std::max(64, getenv("ASR_TC_RING") ? atoi(getenv("ASR_TC_RING")) : TC_RING)));
+                                                                 std::min(TC_RING, std::max(64, getenv("ASR_TC_RING") ? atoi(getenv("ASR_TC_RING")) : TC_RING)),
+                                                                 getenv("ASR_TC_WARM") ? atoi(getenv("ASR_TC_WARM")) : 32);
         ASR_LAUNCH_CHECK();
         launch_merge(ps, pi, nullptr, db->idx_base, n_slices * L, k, out_score_dev + q0 * k, out_idx_dev + q0 * k, nqc, st);
         ASR_LAUNCH_CHECK();

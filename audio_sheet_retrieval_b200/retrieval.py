@@ -170,11 +170,13 @@ def merge_gathered_topk_device(gathered, nq, n_lists, k):
     return out_s, out_i
 
 
-def vote_device(cand_idx, row_ids, top_k):
-    """Vote over GLOBAL row indices with a replicated row->piece table (sharded DBs)."""
+def vote_device(cand_idx, row_ids, top_k, out_ids=None, out_counts=None):
+    """Vote over GLOBAL row indices with a replicated row->piece table (sharded DBs).  out_ids / out_counts: optional
+    contiguous (n_rec, top_k) int32 CUDA tensors to write into (e.g. this rank's part of a gather buffer)."""
     n_rec, m = int(cand_idx.shape[0]), int(cand_idx.shape[1])
-    out_ids = torch.empty((n_rec, top_k), dtype=torch.int32, device=cand_idx.device)
-    out_cnt = torch.empty((n_rec, top_k), dtype=torch.int32, device=cand_idx.device)
+    out_ids = torch.empty((n_rec, top_k), dtype=torch.int32, device=cand_idx.device) if out_ids is None else out_ids
+    out_cnt = torch.empty((n_rec, top_k), dtype=torch.int32, device=cand_idx.device) if out_counts is None else out_counts
+    assert out_ids.is_contiguous() and out_cnt.is_contiguous() and out_ids.dtype == torch.int32 and out_cnt.dtype == torch.int32
     _lib.check(_lib.lib.asr_vote(_lib.dptr(cand_idx.contiguous()), _lib.dptr(row_ids), int(row_ids.numel()), n_rec, m,
                                  int(top_k), _lib.dptr(out_ids), _lib.dptr(out_cnt), _lib.stream_ptr()))
     return out_ids, out_cnt

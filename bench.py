@@ -285,10 +285,45 @@ def piece_id_leg(torch, dist, dev, rank, world, with_cpu, quick=False):
     else:
         phases = {"local_topk_and_vote_ms": v0.elapsed_time(v1)}
     acc = float((pid[:, 0].long() == true_piece).float().mean().item())
-    out = {"db_rows": n_db, "queries": n_rec * win, "k": 25, "ms": float(ms.item()),
-           "queries_per_s": n_rec * win / (float(ms.item()) * 1e-3), "top1_piece_accuracy": acc, "phases": phases,
+    ms_sharded = float(ms.item())
+    out = {"db_rows": n_db, "queries": n_rec * win, "k": 25, "ms": ms_sharded,
+           "queries_per_s": n_rec * win / (ms_sharded * 1e-3), "top1_piece_accuracy": acc, "phases": phases,
+           "strategy": "DB rows sharded over the ranks",
            "regime": "tcgen05 tf32 pre-filter + exact fp32 re-scoring; DB sharded over %d GPU(s); "
                      "one all-gather of [scores | indices] chunks, merge kernel reads the rank-major chunks" % world}
+    if world > 1:
+        # The other way to use N GPUs when the DB fits on each of them (128 MB here): every rank holds the whole DB and
+        # identifies its share of the RECORDINGS (retrieval + vote), one all-gather of (recordings x top_k) results.
+        from audio_sheet_retrieval_b200.dist import ReplicatedDB
+        rdb = ReplicatedDB(D, ids, group=None)
+        for _ in range(2):
+            pid_r, cnt_r = rdb.identify(Q, n_rec, 5, 25)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0.record()
+        for _ in range(iters):
+            pid_r, cnt_r = rdb.identify(Q, n_rec, 5, 25)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_r = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
+        dist.all_reduce(ms_r, op=dist.ReduceOp.MAX)
+        evr = []
+        dist.barrier()
+        rdb.identify(Q, n_rec, 5, 25, events=evr)
+        torch.cuda.synchronize()
+        phr = torch.tensor([evr[0].elapsed_time(evr[1]), evr[1].elapsed_time(evr[2])], device=dev)
+        dist.all_reduce(phr, op=dist.ReduceOp.MAX)
+        ms_rep = float(ms_r.item())
+        out["by_strategy"] = {
+            "db_sharded": {"ms": ms_sharded, "phases": phases},
+            "recordings_sharded_db_replicated": {
+                "ms": ms_rep, "phases": {"local_topk_and_vote_ms": float(phr[0].item()), "allgather_results_ms": float(phr[1].item())},
+                "same_result_as_db_sharded": bool(torch.equal(pid_r, pid) and torch.equal(cnt_r, cnt))}}
+        if ms_rep < ms_sharded:
+            out.update({"ms": ms_rep, "queries_per_s": n_rec * win / (ms_rep * 1e-3),
+                        "phases": out["by_strategy"]["recordings_sharded_db_replicated"]["phases"],
+                        "strategy": "recordings sharded over the ranks, DB (128 MB) replicated: no candidate exchange, no merge"})
+        rdb.local.close()
     # parity at full size: a 64-query sample of the merged result (indices AND scores) vs the pinned-order C oracle
     s_all, i_all = sdb.topk_device(Q, 25)
     if rank == 0:

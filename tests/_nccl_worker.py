@@ -40,6 +40,23 @@ def main(out_dir):
         s2, i2 = sdb2.topk_device(Qg, k)
         res["topk_inplace_" + name] = bool(torch.equal(i2, i_ref) and torch.equal(s2, s_ref))
 
+    # 1b. piece identification with the recordings split over the ranks (whole DB on every rank) == single GPU == sharded DB
+    from audio_sheet_retrieval_b200.dist import ReplicatedDB
+    from audio_sheet_retrieval_b200.retrieval import vote_device
+    n_db, n_rec, win = 60000, 7, 30
+    D = rng.normal(size=(n_db, 32)).astype(np.float32)
+    ids = (np.arange(n_db) // 50).astype(np.int32)
+    rows_q = (rng.randint(0, n_db // 50, n_rec)[:, None] * 50 + rng.randint(0, 50, (n_rec, win))).reshape(-1)
+    Q = (D[rows_q] + 0.3 * rng.normal(size=(n_rec * win, 32))).astype(np.float32)
+    Dg, Qg = torch.as_tensor(D).to(dev), torch.as_tensor(Q).to(dev)
+    _, i_ref = EmbeddingDB(Dg).topk_device(Qg, 10)
+    p_ref, c_ref = vote_device(i_ref.view(n_rec, -1), torch.as_tensor(ids).to(dev), 4)
+    p_rep, c_rep = ReplicatedDB(Dg, ids, group=group).identify(Qg, n_rec, 4, 10)
+    lo, hi = shard_bounds(n_db, rank, world)
+    p_sh, c_sh = ShardedDB(Dg[lo:hi].contiguous(), lo, row_ids_global=ids, group=group).identify(Qg, n_rec, 4, 10)
+    res["identify_replicated"] = bool(torch.equal(p_rep, p_ref) and torch.equal(c_rep, c_ref))
+    res["identify_sharded"] = bool(torch.equal(p_sh, p_ref) and torch.equal(c_sh, c_ref))
+
     # 2. eval_retrieval with the view-2 rows sharded == unsharded (ranks and target scores bit-exact), grouped views too
     for name, n1, n2 in (("square", 1501, 1501), ("grouped", 500, 1500)):
         base = rng.normal(size=(max(n1, n2), 32))

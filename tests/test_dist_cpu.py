@@ -64,6 +64,19 @@ def _worker(rank, world, port, q):
     part = torch.cat([torch.as_tensor(H[lo2:hi2].T @ H[lo2:hi2]).view(-1), torch.tensor([float(hi2 - lo2)], dtype=torch.float64)])
     dist.all_reduce(part)
     ok = ok and bool(np.allclose(part[:-1].numpy().reshape(4, 4), H.T @ H)) and part[-1].item() == 501.0
+    # recordings split over the ranks (ReplicatedDB): uneven blocks, one all-gather, padding rows dropped
+    from audio_sheet_retrieval_b200.dist import gather_recording_results, recording_layout
+    n_rec, top_k = 7, 3
+    per, bounds, rowmap = recording_layout(n_rec, world)
+    expect_ids = np.arange(n_rec * top_k, dtype=np.int32).reshape(n_rec, top_k)
+    lo3, hi3 = bounds[rank]
+    mine = torch.full((2, per, top_k), -1, dtype=torch.int32)
+    mine[0, :hi3 - lo3] = torch.as_tensor(expect_ids[lo3:hi3])
+    mine[1, :hi3 - lo3] = torch.as_tensor(expect_ids[lo3:hi3] + 1000)
+    gathered = torch.empty((world, 2, per, top_k), dtype=torch.int32)
+    gi3, gc3 = gather_recording_results(mine, gathered, torch.as_tensor(rowmap, dtype=torch.int64))
+    ok = ok and per == 4 and sum(h - l for l, h in bounds) == n_rec
+    ok = ok and bool((gi3.numpy() == expect_ids).all() and (gc3.numpy() == expect_ids + 1000).all())
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 

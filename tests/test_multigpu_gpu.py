@@ -22,7 +22,7 @@ def test_two_rank_nccl_paths_equal_single_gpu(tmp_path):
     for r in res:
         assert r["world"] == 2
         for key in ("topk_exact", "topk_prefilter", "topk_inplace_exact", "topk_inplace_prefilter", "ranks_square",
-                    "ranks_grouped", "eval_square", "eval_grouped"):
+                    "ranks_grouped", "eval_square", "eval_grouped", "identify_replicated", "identify_sharded"):
             assert r[key] is True, (r["rank"], key)
         assert r["cca_sigma"] <= 1e-9 and r["cca_UV"] <= 1e-9 and r["cca_means"] <= 1e-12, r
     assert res[0]["refine_unchanged"] is True and res[0]["refine_diff"] <= 1e-6, res[0]
