@@ -322,6 +322,8 @@ def piece_id_leg(torch, dist, dev, rank, world, with_cpu, quick=False):
         if ms_rep < ms_sharded:
             out.update({"ms": ms_rep, "queries_per_s": n_rec * win / (ms_rep * 1e-3),
                         "phases": out["by_strategy"]["recordings_sharded_db_replicated"]["phases"],
+                        "regime": "tcgen05 tf32 pre-filter + exact fp32 re-scoring; every rank holds the whole DB and identifies "
+                                  "its share of the %d recordings; one all-gather of (recordings x top_k) results" % n_rec,
                         "strategy": "recordings sharded over the ranks, DB (128 MB) replicated: no candidate exchange, no merge"})
         rdb.local.close()
     # parity at full size: a 64-query sample of the merged result (indices AND scores) vs the pinned-order C oracle
