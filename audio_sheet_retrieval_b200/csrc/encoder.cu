@@ -1326,6 +1326,7 @@ struct asr_encoder {
     // host-buffer entry
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    cudaEvent_t ev_final = nullptr;     // blocking-sync event: the host thread sleeps until the call's results are back
     void *dev_in[2] = {nullptr, nullptr};
     void *pin_in[2] = {nullptr, nullptr};
     float *dev_codes = nullptr, *dev_lat = nullptr;
@@ -1495,6 +1496,7 @@ int asr_encoder_destroy(asr_encoder_t *e) {
     }
     cudaFree(e->dev_codes); cudaFree(e->dev_lat);
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
+    if (e->ev_final) cudaEventDestroy(e->ev_final);
     if (e->s_copy) cudaStreamDestroy(e->s_copy);
     if (e->s_comp) cudaStreamDestroy(e->s_comp);
     delete e;
@@ -2072,6 +2074,7 @@ int asr_encoder_embed_host(asr_encoder_t *e, const void *x_host, int x_dtype, in
     if (!e->s_copy) {
         ASR_CUDA(cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking));
         ASR_CUDA(cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking));
+        ASR_CUDA(cudaEventCreateWithFlags(&e->ev_final, cudaEventDisableTiming | cudaEventBlockingSync));
         for (int b = 0; b < 2; ++b) {
             ASR_CUDA(cudaEventCreateWithFlags(&e->ev_copied[b], cudaEventDisableTiming));
             ASR_CUDA(cudaEventCreateWithFlags(&e->ev_done[b], cudaEventDisableTiming));
@@ -2117,7 +2120,10 @@ int asr_encoder_embed_host(asr_encoder_t *e, const void *x_host, int x_dtype, in
         ASR_CUDA(cudaMemcpyAsync(codes_host, e->dev_codes, (size_t)n * 32 * 4, cudaMemcpyDeviceToHost, e->s_comp));
     if (latents_host)
         ASR_CUDA(cudaMemcpyAsync(latents_host, e->dev_lat, (size_t)n * 32 * 4, cudaMemcpyDeviceToHost, e->s_comp));
-    ASR_CUDA(cudaStreamSynchronize(e->s_comp));
+    // Wait on a blocking-sync event rather than cudaStreamSynchronize: the latter spins, and a spinning thread per
+    // branch and rank starves the launch threads of the other ranks on a box with fewer cores than busy threads.
+    ASR_CUDA(cudaEventRecord(e->ev_final, e->s_comp));
+    ASR_CUDA(cudaEventSynchronize(e->ev_final));
     return ASR_OK;
 }
 
