@@ -1021,6 +1021,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles
             }
         }
         const int64_t v_tiles = my_tiles + T;                       // virtual tiles of the item
+        const uint64_t t_item = globaltimer_ns();
         // stage the query tile (rep copies), swizzled like a SWIZZLE_128B TMA load; rows beyond nq are zero
         for (int i = tid; i < TC_QM * 8; i += TC_THREADS) {
             const int row = i >> 3, c = i & 7;
@@ -1092,52 +1093,52 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles
                     mbar_wait_relaxed(&sm.tfull[slot], (uint32_t)((g >> 1) & 1));
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + slot * 256u + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col0;
-                        // Pass A.  A query's scores of one tile sit in P = 4 rep scanner threads (ncols columns each).  Every
-                        // thread keeps the 8 largest of its per-tile maxima; after T tiles its jfl-th largest, jfl =
-                        // ceil(k / P), has jfl DISTINCT rows at or above it, so the minimum `lo` over the P threads has
-                        // P jfl >= k rows at or above it, whose exact scores are >= lo - eps: the final k-th best of the
-                        // list is >= lo - eps.  (All tiles of the pass are complete: no zero-filled rows are counted.)
-                        if (warp_valid) {
-                            float gm = -CUDART_INF_F;
+                    // Pass A.  A query's scores of one tile sit in P = 4 rep scanner threads (ncols columns each).  Every
+                    // thread keeps the 8 largest of its per-tile maxima; after T tiles its jfl-th largest, jfl =
+                    // ceil(k / P), has jfl DISTINCT rows at or above it, so the minimum `lo` over the P threads has
+                    // P jfl >= k rows at or above it, whose exact scores are >= lo - eps: the final k-th best of the
+                    // list is >= lo - eps.  (All tiles of the pass are complete: no zero-filled rows are counted.)
+                    if (warp_valid) {
+                        float gm = -CUDART_INF_F;
 #pragma unroll 1
-                            for (int u = 0; u < ncols; u += 32) {
-                                uint32_t vv[32];
-                                tmem_ld16_issue(taddr + (uint32_t)u, vv);
-                                if (ncols >= 32) tmem_ld16_issue(taddr + (uint32_t)(u + 16), vv + 16);
-                                tmem_ld_wait();
+                        for (int u = 0; u < ncols; u += 32) {
+                            uint32_t vv[32];
+                            tmem_ld16_issue(taddr + (uint32_t)u, vv);
+                            if (ncols >= 32) tmem_ld16_issue(taddr + (uint32_t)(u + 16), vv + 16);
+                            tmem_ld_wait();
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) gm = fmaxf(gm, __uint_as_float(vv[j]));      // fmaxf drops NaNs (zero rows)
-                                if (ncols >= 32) {
+                            for (int j = 0; j < 16; ++j) gm = fmaxf(gm, __uint_as_float(vv[j]));      // fmaxf drops NaNs (zero rows)
+                            if (ncols >= 32) {
 #pragma unroll
-                                    for (int j = 16; j < 32; ++j) gm = fmaxf(gm, __uint_as_float(vv[j]));
-                                }
-                            }
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {                // insertion into the descending array, branch-free
-                                const float hi = fmaxf(top[j], gm), lo2 = fminf(top[j], gm);
-                                top[j] = hi;
-                                gm = lo2;
+                                for (int j = 16; j < 32; ++j) gm = fmaxf(gm, __uint_as_float(vv[j]));
                             }
                         }
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&sm.tempty[slot]);
-                        if (v == T - 1) {
-                            const int jfl = (k + 4 * rep - 1) / (4 * rep);
-                            float mine = top[0];
 #pragma unroll
-                            for (int j = 1; j < 8; ++j) mine = j == jfl - 1 ? top[j] : mine;
-                            if (jfl > T) mine = -CUDART_INF_F;           // fewer groups than needed (cannot happen: T >= 8 >= jfl)
-                            if (qvalid) atomicMin(&sm.fmin_key[qi], mine > -CUDART_INF_F ? fkey(mine) : 0u);   // 0: no floor
-                            asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_SCAN_WARPS) : "memory");
-                            const uint32_t fm = sm.fmin_key[qi];
-                            if (qvalid && fm != 0u && fm != 0xffffffffu && (ql / nqt) == 0 && cidx == 0) {   // one thread per query
-                                const float floor_s = fkey_inv(fm) - eps;
-                                atomicMax(&sm.floor_key[qi], (unsigned long long)fkey(floor_s) << 32);   // ties with the floor itself still enter
-                                atomicMax(&sm.tau_key[qi], fkey(floor_s - eps));
-                            }
-                            asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_SCAN_WARPS) : "memory");     // floors visible before pass B
+                        for (int j = 0; j < 8; ++j) {                // insertion into the descending array, branch-free
+                            const float hi = fmaxf(top[j], gm), lo2 = fminf(top[j], gm);
+                            top[j] = hi;
+                            gm = lo2;
                         }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.tempty[slot]);
+                    if (v == T - 1) {
+                        const int jfl = (k + 4 * rep - 1) / (4 * rep);
+                        float mine = top[0];
+#pragma unroll
+                        for (int j = 1; j < 8; ++j) mine = j == jfl - 1 ? top[j] : mine;
+                        if (jfl > T) mine = -CUDART_INF_F;           // fewer groups than needed (cannot happen: T >= 8 >= jfl)
+                        if (qvalid) atomicMin(&sm.fmin_key[qi], mine > -CUDART_INF_F ? fkey(mine) : 0u);   // 0: no floor
+                        asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_SCAN_WARPS) : "memory");
+                        const uint32_t fm = sm.fmin_key[qi];
+                        if (qvalid && fm != 0u && fm != 0xffffffffu && (ql / nqt) == 0 && cidx == 0) {   // one thread per query
+                            const float floor_s = fkey_inv(fm) - eps;
+                            atomicMax(&sm.floor_key[qi], (unsigned long long)fkey(floor_s) << 32);   // ties with the floor itself still enter
+                            atomicMax(&sm.tau_key[qi], fkey(floor_s - eps));
+                        }
+                        asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_SCAN_WARPS) : "memory");     // floors visible before pass B
+                    }
                 }
             }
             for (int64_t it = 0; it < my_tiles; ++it) {
@@ -1235,6 +1236,10 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles
                         }
                         if (!__any_sync(0xffffffffu, pending)) break;
                         __nanosleep(100);
+                        if (globaltimer_ns() - t_item > 4000000000ull) {      // bounded wait: a protocol bug must not hang the GPU
+                            if (lane == 0) printf("asr: pre-filter ring wait timeout, block %d warp %d\n", blockIdx.x, warp);
+                            __trap();
+                        }
                     }
                 }
                 __syncwarp();
@@ -1259,6 +1264,10 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles
                 const int st8 = __shfl_sync(0xffffffffu, ((uint32_t)(rv - ring_h) >= 32u ? 4 : 0) | (sd == done_target ? 1 : 0) |
                                                              (rv == ring_h ? 2 : 0), 0);
                 if ((st8 & 3) == 3) break;                             // scanners done, everything consumed
+                if (globaltimer_ns() - t_item > 4000000000ull) {       // bounded wait (see mbar_wait)
+                    if (lane == 0) printf("asr: pre-filter owner timeout, block %d warp %d\n", blockIdx.x, warp);
+                    __trap();
+                }
                 if (!(st8 & 4) && !(st8 & 1)) {                        // partial batch, item still running: wait (a drain costs
                     __nanosleep(idle_ns);                              // thousands of cycles whatever its size), backing off:
                     idle_ns = min(idle_ns * 2u, 2000u);                // polling took a fifth of the SM's issue slots
