@@ -132,15 +132,18 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity
     if (mbar_try_wait(bar, parity)) return;
     const uint64_t t0 = globaltimer_ns();
     for (;;) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-            "selp.b32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity), "r"(2000u)
-            : "memory");
-        if (ok) return;
+#pragma unroll 1
+        for (int spin = 0; spin < 256; ++spin) {         // the clock is only read every 256 tries: the loop is 3 instructions
+            uint32_t ok;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                "selp.b32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok)
+                : "r"(smem_u32(bar)), "r"(parity), "r"(2000u)
+                : "memory");
+            if (ok) return;
+        }
         if (globaltimer_ns() - t0 > 4000000000ull) {
             printf("asr: mbarrier timeout block %d thread %d parity %u\n", blockIdx.x, threadIdx.x, parity);
             __trap();

@@ -1255,25 +1255,30 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int tiles
             const int S = n_slices, spad = (n_slices + 7) & ~7;
             const int jpub = (k + min(S, k) - 1) / min(S, k);          // which entry of its list every slice publishes
             const int m_need = (k + jpub - 1) / jpub;                  // published lists needed for a bound
-            uint32_t drains = 0u, next_refresh = 1u, idle_ns = 200u;
+            uint32_t drains = 0u, next_refresh = 1u;
             bool flush = false;
             for (;;) {
-                // cheap poll: how much has been reserved beyond what this warp has consumed
-                const uint32_t rv = lds_volatile_u32(&sm.resv[o]);
-                const uint32_t sd = lds_volatile_u32(&sm.scan_done);
-                const int st8 = __shfl_sync(0xffffffffu, ((uint32_t)(rv - ring_h) >= 32u ? 4 : 0) | (sd == done_target ? 1 : 0) |
-                                                             (rv == ring_h ? 2 : 0), 0);
+                // Cheap poll by ONE lane: how much has been reserved beyond what this warp has consumed, and whether the
+                // scanners are done with the item.  Partial batches wait (a drain costs thousands of cycles whatever its
+                // size), with exponential back-off: polling used to be a fifth of the SM's issued instructions.
+                int st8;
+                for (uint32_t idle_ns = 100u;;) {
+                    int st = 0;
+                    if (lane == 0) {
+                        const uint32_t rv = lds_volatile_u32(&sm.resv[o]);
+                        const uint32_t sd = lds_volatile_u32(&sm.scan_done);
+                        st = ((uint32_t)(rv - ring_h) >= 32u ? 4 : 0) | (sd == done_target ? 1 : 0) | (rv == ring_h ? 2 : 0);
+                    }
+                    st8 = __shfl_sync(0xffffffffu, st, 0);
+                    if (st8 & 5) break;                                // a full batch, or the item is over
+                    __nanosleep(idle_ns);
+                    idle_ns = min(idle_ns * 2u, 4000u);
+                    if (idle_ns == 4000u && globaltimer_ns() - t_item > 4000000000ull) {       // bounded wait (see mbar_wait)
+                        if (lane == 0) printf("asr: pre-filter owner timeout, block %d warp %d\n", blockIdx.x, warp);
+                        __trap();
+                    }
+                }
                 if ((st8 & 3) == 3) break;                             // scanners done, everything consumed
-                if (globaltimer_ns() - t_item > 4000000000ull) {       // bounded wait (see mbar_wait)
-                    if (lane == 0) printf("asr: pre-filter owner timeout, block %d warp %d\n", blockIdx.x, warp);
-                    __trap();
-                }
-                if (!(st8 & 4) && !(st8 & 1)) {                        // partial batch, item still running: wait (a drain costs
-                    __nanosleep(idle_ns);                              // thousands of cycles whatever its size), backing off:
-                    idle_ns = min(idle_ns * 2u, 2000u);                // polling took a fifth of the SM's issue slots
-                    continue;
-                }
-                idle_ns = 200u;
                 const uint32_t pos = ring_h + (uint32_t)lane;
                 const unsigned long long ent = lds_volatile_u64(&sm.ring[o][pos & (TC_RING - 1)]);
                 const bool valid = (uint32_t)(ent >> 40) == (((pos / TC_RING) + 1u) & 0xffffffu);
