@@ -54,6 +54,16 @@ class AudioSheetServer(object):
         self.snippet_shape = self.embed_network.shape_view1[1:]
         self.excerpt_shape = self.embed_network.shape_view2[1:]
 
+    # -- spectrogram front-end (the madmom chain of the tutorial, cell 28, and of `_mic_spec_gen`, :44-60) ----------
+    def compute_spectrogram(self, samples, sample_rate=22050):
+        """mono PCM samples (float in [-1, 1) or int16) -> (92, n_frames) float32 log-frequency spectrogram, computed
+        on the device (frame 2048, 20 fps, LogarithmicFilterbank(16 bands / octave, 30 Hz - 6 kHz), log10(1 + x))."""
+        from .utils.spectrogram import LogSpectrogramProcessor
+        key = int(sample_rate)
+        if getattr(self, "_spec_proc", None) is None or self._spec_proc.sample_rate != key:
+            self._spec_proc = LogSpectrogramProcessor(sample_rate=key)
+        return self._spec_proc.process(samples)
+
     # -- DB containers ------------------------------------------------------------------------
     def set_sheet_db(self, codes, ids, id_to_piece, snippets=None):
         self.sheet_snippet_codes = np.ascontiguousarray(codes, np.float32)

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libasr_b200.so")
-SOURCES = ["abi.cu", "retrieval.cu", "cca.cu", "encoder.cu", "align.cu", "loss.cu"]
+SOURCES = ["abi.cu", "retrieval.cu", "cca.cu", "encoder.cu", "align.cu", "loss.cu", "spectrogram.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

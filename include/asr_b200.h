@@ -218,6 +218,22 @@ int asr_cca_solve(const double *sums_dev, int64_t n_total, const float *shift1_d
                   double *U_dev, double *V_dev, double *sigma_dev, void *stream);
 
 /* ------------------------------------------------------------------------- *
+ * Spectrogram front-end (SURVEY 8f "next" row 4).  Replaces the madmom processor chain of
+ * tutorials/Embedding Tutorial.ipynb cell 28 (and of the microphone stream, asr/audio_sheet_server.py:44-60):
+ *   FramedSignalProcessor(frame_size, fps, origin='future') -> Hann window -> |FFT| (frame_size / 2 bins)
+ *   -> FilteredSpectrogramProcessor(filterbank) -> LogarithmicSpectrogramProcessor (log10(1 + x)).
+ * audio_dev: mono float32 samples in [-1, 1) on the device (int16 / 32768).  Frame i starts at
+ * int(i * sample_rate / fps); there are ceil(n_samples / (sample_rate / fps)) frames (asr_spectrogram_num_frames),
+ * samples beyond the end are zeros.  filterbank_dev: (frame_size / 2, n_bands) float32 row-major; band_lo/band_hi:
+ * per band the half-open range of bins with non-zero weight.  out_dev: (n_bands, n_frames) float32 -- the layout
+ * `processor.process(path).T` has in the reference, ready for asr_extract_windows.  frame_size: power of two <= 4096.
+ * ------------------------------------------------------------------------- */
+int asr_spectrogram_num_frames(int64_t n_samples, int sample_rate, double fps);
+int asr_log_spectrogram(const float *audio_dev, int64_t n_samples, int sample_rate, int frame_size, double fps,
+                        const float *filterbank_dev, const int32_t *band_lo_dev, const int32_t *band_hi_dev, int n_bands,
+                        float *out_dev, void *stream);
+
+/* ------------------------------------------------------------------------- *
  * Alignment (SURVEY 8f "next" row 3).  Replaces cdist(img_codes, spec_codes, 'cosine')
  * (asr/utils/alignment.py:149) and dtw_by_dist (asr/utils/dtw_by_dist.py:6-34, 69-83).
  * ------------------------------------------------------------------------- */
