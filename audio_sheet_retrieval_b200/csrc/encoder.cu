@@ -31,6 +31,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include <cuda_fp16.h>
@@ -1324,11 +1325,13 @@ struct asr_encoder {
     std::vector<int> ev_cat;              // category of pair i: 0 layer 0, 1 tcgen05 conv, 2 head
     size_t ev_used = 0;
     // host-buffer entry
-    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;   // host-buffer entry: shared per device (see host_streams) unless owned
+    bool streams_owned = false;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     cudaEvent_t ev_final = nullptr;     // blocking-sync event: the host thread sleeps until the call's results are back
     void *dev_in[2] = {nullptr, nullptr};
     void *pin_in[2] = {nullptr, nullptr};
+    void *pin_out[4] = {nullptr, nullptr, nullptr, nullptr};   // pinned result slots: codes [0,1], latents [2,3]
     float *dev_codes = nullptr, *dev_lat = nullptr;
     int64_t out_cap = 0;
 };
@@ -1491,14 +1494,16 @@ int asr_encoder_destroy(asr_encoder_t *e) {
     for (int b = 0; b < 2; ++b) {
         cudaFree(e->dev_in[b]);
         if (e->pin_in[b]) cudaFreeHost(e->pin_in[b]);
+        if (e->pin_out[b]) cudaFreeHost(e->pin_out[b]);
+        if (e->pin_out[2 + b]) cudaFreeHost(e->pin_out[2 + b]);
         if (e->ev_copied[b]) cudaEventDestroy(e->ev_copied[b]);
         if (e->ev_done[b]) cudaEventDestroy(e->ev_done[b]);
     }
     cudaFree(e->dev_codes); cudaFree(e->dev_lat);
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     if (e->ev_final) cudaEventDestroy(e->ev_final);
-    if (e->s_copy) cudaStreamDestroy(e->s_copy);
-    if (e->s_comp) cudaStreamDestroy(e->s_comp);
+    if (e->streams_owned && e->s_copy) cudaStreamDestroy(e->s_copy);
+    if (e->streams_owned && e->s_comp) cudaStreamDestroy(e->s_comp);
     delete e;
     return ASR_OK;
 }
@@ -2060,6 +2065,27 @@ int asr_extract_windows(const void *src_dev, int dtype, int src_h, int src_w, co
     return ASR_OK;
 }
 
+// The host-buffer entry of EVERY encoder handle on a device enqueues into one shared pair of streams (copies / kernels).
+// Two callers -- the two branches of a pair, called from two host threads -- then overlap one's copies with the other's
+// kernels, but their kernels never run concurrently: the conv kernels are persistent grids that own whole SMs (shared
+// memory, all 512 TMEM columns), and two of them sharing the GPU was measured bimodal (135 ms per 100 000 pairs in most
+// runs, 270-385 ms in one of four).  Each thread enqueues "copy k, then kernels k" in order and both streams are FIFO,
+// so every dependency (kernels wait for their copy, a copy waits for the kernels two chunks back) points backwards in
+// enqueue order: no deadlock.
+static cudaStream_t g_host_copy[ASR_MAX_DEVICES] = {nullptr}, g_host_comp[ASR_MAX_DEVICES] = {nullptr};
+static std::mutex g_host_stream_mutex;
+static int host_streams(int dev, cudaStream_t *copy, cudaStream_t *comp) {
+    std::lock_guard<std::mutex> lock(g_host_stream_mutex);
+    dev = std::max(0, std::min(dev, ASR_MAX_DEVICES - 1));
+    if (!g_host_copy[dev]) {
+        ASR_CUDA(cudaStreamCreateWithFlags(&g_host_copy[dev], cudaStreamNonBlocking));
+        ASR_CUDA(cudaStreamCreateWithFlags(&g_host_comp[dev], cudaStreamNonBlocking));
+    }
+    *copy = g_host_copy[dev];
+    *comp = g_host_comp[dev];
+    return ASR_OK;
+}
+
 int asr_encoder_embed_host(asr_encoder_t *e, const void *x_host, int x_dtype, int64_t n, float *codes_host,
                            float *latents_host, int path) {
     int rc = ensure_device();
@@ -2072,21 +2098,25 @@ int asr_encoder_embed_host(asr_encoder_t *e, const void *x_host, int x_dtype, in
     const size_t sample_bytes = (size_t)e->d.in_h * e->d.in_w * esz;
     const size_t max_bytes = (size_t)e->d.in_h * e->d.in_w * 4 * e->max_batch;
     if (!e->s_copy) {
-        ASR_CUDA(cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking));
-        ASR_CUDA(cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking));
+        static const int own_streams = getenv("ASR_HOST_OWN_STREAMS") ? atoi(getenv("ASR_HOST_OWN_STREAMS")) : 0;   // A/B switch
+        if (own_streams) {
+            ASR_CUDA(cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking));
+            ASR_CUDA(cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking));
+            e->streams_owned = true;
+        } else if ((rc = host_streams(e->device, &e->s_copy, &e->s_comp))) {
+            return rc;
+        }
         ASR_CUDA(cudaEventCreateWithFlags(&e->ev_final, cudaEventDisableTiming | cudaEventBlockingSync));
         for (int b = 0; b < 2; ++b) {
             ASR_CUDA(cudaEventCreateWithFlags(&e->ev_copied[b], cudaEventDisableTiming));
             ASR_CUDA(cudaEventCreateWithFlags(&e->ev_done[b], cudaEventDisableTiming));
             ASR_CUDA(cudaMalloc(&e->dev_in[b], max_bytes));
         }
-    }
-    if (e->out_cap < n) {
-        cudaFree(e->dev_codes); cudaFree(e->dev_lat);
-        e->dev_codes = e->dev_lat = nullptr;
-        ASR_CUDA(cudaMalloc(&e->dev_codes, (size_t)n * 32 * 4));
-        ASR_CUDA(cudaMalloc(&e->dev_lat, (size_t)n * 32 * 4));
-        e->out_cap = n;
+        // results leave the device chunk by chunk (two slots of max_batch rows): nothing here depends on n, so no call
+        // ever allocates again (a cudaFree / cudaMalloc in a later, larger call used to stall the first big call of a
+        // process for 0.05-0.7 s: cudaFree waits for every stream, including the other branch's whole pipeline)
+        ASR_CUDA(cudaMalloc(&e->dev_codes, (size_t)2 * e->max_batch * 32 * 4));
+        ASR_CUDA(cudaMalloc(&e->dev_lat, (size_t)2 * e->max_batch * 32 * 4));
     }
     cudaPointerAttributes pa;
     bool pinned = cudaPointerGetAttributes(&pa, x_host) == cudaSuccess && pa.type == cudaMemoryTypeHost;
@@ -2096,6 +2126,16 @@ int asr_encoder_embed_host(asr_encoder_t *e, const void *x_host, int x_dtype, in
                 pinned ? "pinned" : "PAGEABLE (staged through pinned buffers)", (int)pa.type, e->max_batch);
     if (!pinned && !e->pin_in[0])
         for (int b = 0; b < 2; ++b) ASR_CUDA(cudaMallocHost(&e->pin_in[b], max_bytes));
+    auto is_pinned = [](const void *p) {
+        cudaPointerAttributes a;
+        const bool r = p && cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        return r;
+    };
+    const bool stage_c = codes_host && !is_pinned(codes_host), stage_l = latents_host && !is_pinned(latents_host);
+    if ((stage_c || stage_l) && !e->pin_out[0])
+        for (int b = 0; b < 4; ++b) ASR_CUDA(cudaMallocHost(&e->pin_out[b], (size_t)e->max_batch * 128));
+    int64_t slot_s0[2] = {0, 0}, slot_nb[2] = {0, 0};
     // Chunk sizes ramp up (512, 1024, ... max_batch): the first host->device copy is the only one that no
     // compute hides, so it is kept short; every later copy overlaps the chunk before it.
     int64_t ci = 0, cur = std::min<int64_t>(e->max_batch, 512), nb = 0;
@@ -2112,18 +2152,40 @@ int asr_encoder_embed_host(asr_encoder_t *e, const void *x_host, int x_dtype, in
         ASR_CUDA(cudaMemcpyAsync(e->dev_in[b], src, (size_t)nb * sample_bytes, cudaMemcpyHostToDevice, e->s_copy));
         ASR_CUDA(cudaEventRecord(e->ev_copied[b], e->s_copy));
         ASR_CUDA(cudaStreamWaitEvent(e->s_comp, e->ev_copied[b], 0));
-        rc = asr_encoder_embed(e, e->dev_in[b], x_dtype, nb, e->dev_codes + s0 * 32, e->dev_lat + s0 * 32, path, e->s_comp);
+        float *dc = e->dev_codes + (size_t)b * e->max_batch * 32, *dl = e->dev_lat + (size_t)b * e->max_batch * 32;
+        // results of the chunk that used this slot two chunks ago: pageable destinations are filled from the pinned slot
+        // once that chunk is done (a device->pageable copy would block the host and with it the whole pipeline)
+        if (ci >= 2 && (stage_c || stage_l)) {
+            ASR_CUDA(cudaEventSynchronize(e->ev_done[b]));
+            if (stage_c) memcpy(codes_host + slot_s0[b] * 32, e->pin_out[b], (size_t)slot_nb[b] * 128);
+            if (stage_l) memcpy(latents_host + slot_s0[b] * 32, e->pin_out[2 + b], (size_t)slot_nb[b] * 128);
+        }
+        rc = asr_encoder_embed(e, e->dev_in[b], x_dtype, nb, dc, dl, path, e->s_comp);
         if (rc) return rc;
+        if (codes_host)
+            ASR_CUDA(cudaMemcpyAsync(stage_c ? e->pin_out[b] : codes_host + s0 * 32, dc, (size_t)nb * 128, cudaMemcpyDeviceToHost, e->s_comp));
+        if (latents_host)
+            ASR_CUDA(cudaMemcpyAsync(stage_l ? e->pin_out[2 + b] : latents_host + s0 * 32, dl, (size_t)nb * 128, cudaMemcpyDeviceToHost,
+                                     e->s_comp));
         ASR_CUDA(cudaEventRecord(e->ev_done[b], e->s_comp));
+        slot_s0[b] = s0;
+        slot_nb[b] = nb;
     }
-    if (codes_host)
-        ASR_CUDA(cudaMemcpyAsync(codes_host, e->dev_codes, (size_t)n * 32 * 4, cudaMemcpyDeviceToHost, e->s_comp));
-    if (latents_host)
-        ASR_CUDA(cudaMemcpyAsync(latents_host, e->dev_lat, (size_t)n * 32 * 4, cudaMemcpyDeviceToHost, e->s_comp));
+    for (int64_t c = std::max<int64_t>(0, ci - 2); c < ci && (stage_c || stage_l); ++c) {       // the last one or two chunks
+        const int b = (int)(c & 1);
+        ASR_CUDA(cudaEventSynchronize(e->ev_done[b]));
+        if (stage_c) memcpy(codes_host + slot_s0[b] * 32, e->pin_out[b], (size_t)slot_nb[b] * 128);
+        if (stage_l) memcpy(latents_host + slot_s0[b] * 32, e->pin_out[2 + b], (size_t)slot_nb[b] * 128);
+    }
     // Wait on a blocking-sync event rather than cudaStreamSynchronize: the latter spins, and a spinning thread per
     // branch and rank starves the launch threads of the other ranks on a box with fewer cores than busy threads.
-    ASR_CUDA(cudaEventRecord(e->ev_final, e->s_comp));
-    ASR_CUDA(cudaEventSynchronize(e->ev_final));
+    static const int host_spin = getenv("ASR_HOST_SPIN") ? atoi(getenv("ASR_HOST_SPIN")) : 0;
+    if (host_spin) {
+        ASR_CUDA(cudaStreamSynchronize(e->s_comp));
+    } else {
+        ASR_CUDA(cudaEventRecord(e->ev_final, e->s_comp));
+        ASR_CUDA(cudaEventSynchronize(e->ev_final));
+    }
     return ASR_OK;
 }
 

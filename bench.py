@@ -610,11 +610,14 @@ def main():
         res[name] = enc.embed_host(h)
         t_br[name] = t_br.get(name, 0.0) + time.perf_counter() - ta
 
+    step_ms = []
     for _ in range(k_e2e):
+        ts = time.perf_counter()
         th = threading.Thread(target=run_branch, args=("v2", e2, h2))
         th.start()
         run_branch("v1", e1, h1)
         th.join()
+        step_ms.append((time.perf_counter() - ts) * 1e3)
     torch.cuda.synchronize()
     c1h, c2h = res["v1"], res["v2"]
     dt = torch.tensor([(time.perf_counter() - t0) / k_e2e], device=dev, dtype=torch.float64)
@@ -645,7 +648,7 @@ def main():
            "api": "asr_encoder_embed_host (what RetrievalWrapper.compute_view_1/2 call)", "codes_equal_device_path": same,
            "ms_per_step_sheet_branch": ms_v1, "ms_per_step_spectrogram_branch": ms_v2,
            "concurrency": "the two branch calls run concurrently from two host threads",
-           "ms_per_step_by_rank": [x * 1e3 for x in dt_all],
+           "ms_per_step_by_rank": [x * 1e3 for x in dt_all], "ms_of_each_step_rank0": step_ms,
            "h2d_gbs_used": h2d / float(dt.item()) / 1e9,
            "h2d_gbs_plain_pinned_copy": link_gbs,
            "host_link_note": "min over ranks of a plain pinned copy with all %d rank(s) copying at once; e2e needs "
