@@ -228,6 +228,20 @@ def retrieval_sweep_leg(torch, dist, dev, pk, rank, world, rows_list, quick=Fals
             cells.append({"rows": rows, "q": nq, "ms": ms, "queries_per_s": nq / (ms * 1e-3), "algorithmic_gbs": gbs,
                           "hbm_frac": gbs / (world * pk["hbm_gbs"]),
                           "shard_fits_l2": bool((hi - lo) * 128 <= L2_BYTES)})
+            if nq > 1 and rows == rows_list[-1]:
+                # Full-size parity without a host copy of the DB: the default dispatch (the tensor-core pre-filter at this
+                # size) must return, index for index and bit for bit, what the exact streaming kernel returns -- two
+                # independent kernels, the exact one pinned against the oracle at the sizes the oracle can do.
+                s_a, i_a = sdb.topk_device(q, 25)
+                os.environ["ASR_TOPK_PATH"] = "exact"
+                try:
+                    s_b, i_b = sdb.topk_device(q[:4].contiguous(), 25)
+                finally:
+                    del os.environ["ASR_TOPK_PATH"]
+                same = torch.tensor([int(torch.equal(i_a[:4], i_b) and torch.equal(s_a[:4], s_b))], device=dev)
+                if world > 1:
+                    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+                cells[-1]["default_path_equals_exact_kernel_on_4_queries"] = bool(same.item())
         sdb.local.close()
         del sdb, shard
         torch.cuda.empty_cache()
