@@ -656,18 +656,20 @@ rank_count_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_db, int64_
 }
 
 // ---- tensor-core pre-filter + exact re-scoring ------------------------------------------
-// For many queries the pinned-order scoring (64 dependent fp32 instructions per (row, query)) is
+// From a handful of queries on the pinned-order scoring (64 dependent fp32 instructions per (row, query)) is
 // FP32-issue bound.  This path scores a 128-query x 256-row tile with four tcgen05 tf32 MMAs
 // (fp32 accumulators in TMEM), which is only an APPROXIMATION s~ of the pinned score s, with
 // |s~ - s| <= 2^-9 for unit vectors (each tf32 operand carries <= 2^-10 relative error and
 // sum |q_k d_k| <= 1).  Exactness is kept by filtering, not by trusting s~: a row is re-scored with
-// the pinned fp32 order iff s~ >= tau_q - eps, where tau_q is the query's current k-th best EXACT
-// score and eps = 2^-8.  Every true top-k row satisfies s >= tau_final >= tau_q, hence
+// the pinned fp32 order iff s~ >= tau_q - eps, where tau_q is any LOWER BOUND of the query's final k-th best EXACT
+// score (the list's current k-th entry, the warm-up floor, the bound the slices share) and eps = 2^-8.  Every true
+// top-k row satisfies s >= tau_final >= tau_q, hence
 // s~ >= tau_q - eps, so it is always re-scored; lists, thresholds and the final order use exact
 // scores only.  Results are therefore identical to topk_stream_kernel / the oracle.
 // Layout: TMEM lane = query.  SCANNER warps read the score tile out of TMEM and only FILTER it against the query's
 // current threshold; what passes goes, as (row, query) entries, into shared-memory rings that OWNER warps consume:
-// exact re-scoring and insertion into the query's sorted top-k list (one list per query and work item).
+// exact re-scoring and insertion into the query's top-k list (one list per query and work item: a sorted part plus an
+// append buffer that is folded in by a bitonic merge).
 constexpr int TC_QM = 128;
 constexpr int TC_ROWS = 256;
 constexpr int TC_STAGES = 3;
@@ -684,10 +686,10 @@ struct TcSmem {
     float stage[TC_STAGES][TC_ROWS * 32];     // normalised DB rows, SWIZZLE_128B (written by TMA)
     float q[TC_QM * 32];                      // normalised queries, same swizzle (written by threads)
     unsigned long long lists[TC_QM * TC_LSTRIDE];   // per query: sorted top-k list + unsorted buffer of accepted candidates, 64-bit keys
-    uint32_t fmin_key[TC_QM];                 // first-tile floor: minimum over the query's scanner threads (atomicMin)
+    uint32_t fmin_key[TC_QM];                 // warm-up floor: minimum over the query's scanner threads (atomicMin)
     uint32_t pub[TC_QM];                      // the list has published its jpub-th best at least once
     uint32_t bcnt[TC_QM];                     // entries appended to the buffer since its last compaction (may overshoot 32)
-    unsigned long long floor_key[TC_QM];      // threshold floor of the list (first-tile bisection; atomicMax by the scanners)
+    unsigned long long floor_key[TC_QM];      // threshold floor of the list (warm-up pass; atomicMax by the scanners)
     unsigned long long ring[TC_OWN_WARPS][TC_RING];   // candidates: tag (24) | query (8) | row (32); tag = lap + 1 marks a written slot
     uint32_t tau_key[TC_QM];                  // fkey of the approximate-score filter threshold of the query (atomicMax)
     uint32_t resv[TC_OWN_WARPS];              // ring positions handed out to producers (monotonic)
