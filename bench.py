@@ -367,6 +367,31 @@ def piece_id_leg(torch, dist, dev, rank, world, with_cpu, quick=False):
     return out
 
 
+def streaming_leg(torch, dev):
+    """The streaming loop of the reference's server (audio_sheet_server.py:83-211 without GUI / microphone): one
+    spectrogram column per frame, embed the running 92 x 42 window, retrieve 25 candidates from a 10^6-row sheet DB,
+    vote over the last 100 frames.  Reports the frame rate the reference prints ("Server is running at ... fps")."""
+    from audio_sheet_retrieval_b200.audio_sheet_server import AudioSheetServer
+    from audio_sheet_retrieval_b200.models import mutopia_ccal_cont_rsz as model
+    import contextlib
+    import io
+    rng = np.random.RandomState(3)
+    srv = AudioSheetServer()
+    with contextlib.redirect_stdout(io.StringIO()):
+        srv.initialize_embedding_network(model, PKL_RSZ)
+    n_db = 1000000
+    g = torch.Generator(device=dev).manual_seed(4)
+    D = torch.randn((n_db, 32), generator=g, device=dev)
+    srv.set_sheet_db(D.cpu().numpy(), np.arange(n_db) // 100, dict((i, "piece%d" % i) for i in range(n_db // 100)))
+    spec = np.abs(rng.normal(0, 0.3, (92, 42 + 300))).astype(np.float32)
+    srv.run(spec[:, :42 + 20], top_k=5, n_candidates=25, running_frames=100, verbose=False)      # warm-up
+    names, probs, fps = srv.run(spec, top_k=5, n_candidates=25, running_frames=100, verbose=False)
+    return {"frames": 300, "db_rows": n_db, "n_candidates": 25, "running_frames": 100, "frames_per_s": fps,
+            "ms_per_frame": 1e3 / fps if fps else None,
+            "api": "AudioSheetServer.run -> process_frame (NumPy window in: compute_view_2, Q = 1 top-k, vote kernel); the "
+                   "reference's tutorial audio runs at 20 frames per second of signal"}
+
+
 def config1_leg(torch, dev, with_cpu):
     """Config 1: rsz model + tutorial pickle, 2000 synthetic pairs through RetrievalWrapper + eval_retrieval;
     R@k / MRR / median rank next to the oracle's on the same inputs (tolerance of the north star: 0.5 % absolute)."""
@@ -701,6 +726,7 @@ def main():
         ]
         if world == 1:
             legs.append(("config1_rsz_eval", lambda: config1_leg(torch, dev, with_cpu)))
+            legs.append(("streaming_identification", lambda: streaming_leg(torch, dev)))
         for name, fn in legs:
             try:
                 line[name] = fn()
