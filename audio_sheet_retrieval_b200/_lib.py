@@ -71,6 +71,9 @@ def _load():
     lib.asr_extract_windows.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                         c_void_p]
     lib.asr_extract_windows.restype = c_int
+    lib.asr_cca_layer_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_void_p,
+                                           c_void_p, c_void_p, c_void_p]
+    lib.asr_cca_layer_backward.restype = c_int
     lib.asr_spectrogram_num_frames.argtypes = [c_int64, c_int, c_double]
     lib.asr_spectrogram_num_frames.restype = c_int
     lib.asr_log_spectrogram.argtypes = [c_void_p, c_int64, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p, c_int, c_void_p,

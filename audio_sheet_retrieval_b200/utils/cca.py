@@ -36,6 +36,23 @@ def cca_solve_device(sums, n_total, shift1=None, shift2=None, r1=1e-3, r2=1e-3, 
     return m1, m2, U, V, sig
 
 
+def cca_layer_backward_device(H1, H2, G1, G2, r1=1e-3, r2=1e-3, rT=1e-3, g_corr=None):
+    """Gradient through the CCALayer's training forward (batch statistics, ALPHA = 1; layers/cca.py:91-203).
+    H1, H2: the layer's inputs (m,32); G1, G2: dL/d(lv1_cca), dL/d(lv2_cca_fixed) (m,32); g_corr: dL/d corr (32,) or None.
+    -> (dL/dH1, dL/dH2) float32 CUDA tensors."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t = [torch.as_tensor(a).to(dev, torch.float32).contiguous() for a in (H1, H2, G1, G2)]
+    m = int(t[0].shape[0])
+    if any(tuple(a.shape) != (m, 32) for a in t):
+        raise ValueError("expected four (m,32) arrays")
+    gc = None if g_corr is None else torch.as_tensor(np.asarray(g_corr, np.float64)).to(dev).contiguous()
+    d1, d2 = torch.empty_like(t[0]), torch.empty_like(t[1])
+    _lib.check(_lib.lib.asr_cca_layer_backward(_lib.dptr(t[0]), _lib.dptr(t[1]), _lib.dptr(t[2]), _lib.dptr(t[3]), m,
+                                               float(r1), float(r2), float(rT), _lib.dptr(gc), _lib.dptr(d1), _lib.dptr(d2),
+                                               _lib.stream_ptr()))
+    return d1, d2
+
+
 class CCA(object):
     """Cannonical correlation analysis"""
 

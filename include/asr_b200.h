@@ -221,6 +221,17 @@ int asr_cca_solve(const double *sums_dev, int64_t n_total, const float *shift1_d
                   double r1, double r2, double rT, int mode, double *m1_dev, double *m2_dev,
                   double *U_dev, double *V_dev, double *sigma_dev, void *stream);
 
+/* CCALayer training backward (asr/models/lasagne_extensions/layers/cca.py:91-203 differentiated -- the reference gets
+ * it from Theano's automatic differentiation: EighGrad through the four eigendecompositions, zero gradient through sgn
+ * and outside the clip range of corr).  Batch statistics only (ALPHA = 1, as asr_cca_solve mode 1).
+ * h1, h2 (n,32): the layer's inputs; g1 = dL/d lv1_cca, g2 = dL/d lv2_cca_fixed (n,32), e.g. from asr_contrastive_loss;
+ * g_corr_dev: dL/d corr (32 doubles: the layer's own loss term -wl * mean(corr) gives -wl/32 each) or NULL.
+ * Writes dL/dh1, dL/dh2 (n,32) float32.  Three Gram passes, one single-CTA fp64 kernel for the 32 x 32 chain, one row
+ * pass; workspace allocated per device at first use. */
+int asr_cca_layer_backward(const float *h1_dev, const float *h2_dev, const float *g1_dev, const float *g2_dev, int64_t n,
+                           double r1, double r2, double rT, const double *g_corr_dev, float *dh1_dev, float *dh2_dev,
+                           void *stream);
+
 /* ------------------------------------------------------------------------- *
  * Spectrogram front-end (SURVEY 8f "next" row 4).  Replaces the madmom processor chain of
  * tutorials/Embedding Tutorial.ipynb cell 28 (and of the microphone stream, asr/audio_sheet_server.py:44-60):

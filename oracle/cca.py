@@ -100,3 +100,69 @@ def synth_latents(n, seed=23, dim=32, scale=0.05):
     H1 = (Z * rho + N1 * np.sqrt(1 - rho ** 2)).dot(A1) * scale + rng.normal(size=dim) * 0.01
     H2 = (Z * rho + N2 * np.sqrt(1 - rho ** 2)).dot(A2) * scale + rng.normal(size=dim) * 0.01
     return H1.astype(np.float32), H2.astype(np.float32)
+
+
+def cca_layer_train_backward(H1, H2, G1, G2, r1=1e-3, r2=1e-3, rT=1e-3, g_corr=None):
+    """Gradient of a scalar loss through CCALayer.get_output_for(deterministic=False) with ALPHA = 1 (cca.py:91-203):
+    given G1 = dL/d lv1_cca, G2 = dL/d lv2_cca_fixed (each (m, d)) and optionally g_corr = dL/d corr (d,) -- the layer's own
+    loss term -wl * mean(corr) -- returns (dL/dH1, dL/dH2).  The reference gets this from Theano's automatic
+    differentiation (EighGrad for the four eigendecompositions, zero gradient through sgn and outside the clip range);
+    this is the same chain written out in fp64 NumPy.  Pinned by central differences of cca_layer_train_forward
+    (tests/test_oracle_golden.py), not by the reference (Theano is not installable)."""
+    H1 = np.asarray(H1, np.float64); H2 = np.asarray(H2, np.float64)
+    G1 = np.asarray(G1, np.float64); G2 = np.asarray(G2, np.float64)
+    m, d = H1.shape
+    Xc, Yc = H1 - H1.mean(0), H2 - H2.mean(0)
+    S12 = Xc.T.dot(Yc) / (m - 1)
+    S11 = Xc.T.dot(Xc) / (m - 1) + r1 * np.eye(d)
+    S22 = Yc.T.dot(Yc) / (m - 1) + r2 * np.eye(d)
+    d1, A1 = np.linalg.eigh(S11)
+    d2, A2 = np.linalg.eigh(S22)
+    S11si = (A1 / np.sqrt(d1)).dot(A1.T)
+    S22si = (A2 / np.sqrt(d2)).dot(A2.T)
+    T = S11si.dot(S12).dot(S22si)
+    E1, E = np.linalg.eigh(T.dot(T.T) + rT * np.eye(d))
+    E2, F = np.linalg.eigh(T.T.dot(T) + rT * np.eye(d))
+    U0, V = S11si.dot(E), S22si.dot(F)
+    s = np.sign(U0.T.dot(S12).dot(V).diagonal())
+    U = U0 * s
+
+    def eigvec_grad(lam, Q, Qbar, lam_bar=None):
+        """A = Q diag(lam) Q' symmetric: dL/dA from dL/dQ (and dL/dlam), symmetrised."""
+        diff = lam[None, :] - lam[:, None]                       # diff[i, j] = lam_j - lam_i
+        K = np.where(diff != 0, 1.0 / np.where(diff != 0, diff, 1.0), 0.0)
+        inner = K * Q.T.dot(Qbar)
+        if lam_bar is not None:
+            inner = inner + np.diag(lam_bar)
+        Abar = Q.dot(inner).dot(Q.T)
+        return 0.5 * (Abar + Abar.T)
+
+    def inv_sqrt_grad(lam, Q, Gbar):
+        """S = Q diag(lam) Q', f(S) = S^-1/2: dL/dS from dL/df(S) (Daleckii-Krein), symmetric."""
+        f = lam ** -0.5
+        diff = lam[:, None] - lam[None, :]
+        Phi = np.where(np.abs(diff) > 1e-12 * lam.max(), (f[:, None] - f[None, :]) / np.where(diff != 0, diff, 1.0),
+                       -0.5 * (0.5 * (lam[:, None] + lam[None, :])) ** -1.5)
+        Gs = 0.5 * (Gbar + Gbar.T)
+        return Q.dot(Phi * Q.T.dot(Gs).dot(Q)).dot(Q.T)
+
+    dU, dV = Xc.T.dot(G1), Yc.T.dot(G2)
+    dU0 = dU * s
+    dS11si = dU0.dot(E.T)
+    dS22si = dV.dot(F.T)
+    dE, dF = S11si.dot(dU0), S22si.dot(dV)
+    lam_bar = None
+    if g_corr is not None:                                         # corr = sqrt(clip(E1, 1e-7, 1)): zero outside the range
+        inside = (E1 > 1e-7) & (E1 < 1.0)
+        lam_bar = np.where(inside, np.asarray(g_corr, np.float64) * 0.5 / np.sqrt(np.clip(E1, 1e-7, 1.0)), 0.0)
+    dM1 = eigvec_grad(E1, E, dE, lam_bar)
+    dM2 = eigvec_grad(E2, F, dF)
+    dT = 2.0 * dM1.dot(T) + 2.0 * T.dot(dM2)
+    dS11si = dS11si + dT.dot(S22si).dot(S12.T)
+    dS22si = dS22si + S12.T.dot(S11si).dot(dT)
+    dS12 = S11si.dot(dT).dot(S22si)
+    dS11 = inv_sqrt_grad(d1, A1, dS11si)
+    dS22 = inv_sqrt_grad(d2, A2, dS22si)
+    dXc = G1.dot(U.T) + (2.0 * Xc.dot(dS11) + Yc.dot(dS12.T)) / (m - 1)
+    dYc = G2.dot(V.T) + (2.0 * Yc.dot(dS22) + Xc.dot(dS12)) / (m - 1)
+    return dXc - dXc.mean(0), dYc - dYc.mean(0)

@@ -111,3 +111,69 @@ def test_counted_layout_sharded_equals_fit():
     np.testing.assert_allclose(sig.cpu().numpy(), sig_ref, atol=1e-12)
     np.testing.assert_allclose(U.cpu().numpy(), c.U, atol=1e-9 * np.abs(c.U).max())
     np.testing.assert_allclose(m1.cpu().numpy(), H1.astype(np.float64).mean(0), atol=1e-12)
+
+
+@pytest.mark.parametrize("m,with_corr", [(64, False), (300, True), (2500, True)])
+def test_layer_backward_matches_oracle(m, with_corr):
+    """asr_cca_layer_backward (three Gram passes + one fp64 CTA + a row pass) vs the oracle's NumPy chain, which is pinned by
+    central differences of the forward (tests/test_oracle_pins.py).  Inputs are float32 on both sides."""
+    from audio_sheet_retrieval_b200.utils.cca import cca_layer_backward_device
+    rng = np.random.RandomState(m)
+    H1, H2 = occa.synth_latents(m, seed=m)
+    G1 = rng.normal(size=(m, 32)).astype(np.float32)
+    G2 = rng.normal(size=(m, 32)).astype(np.float32)
+    gc = rng.normal(size=32) if with_corr else None
+    # The forward is defined up to ONE sign per output column (shared by both views: whichever sign the eigensolver gives
+    # F's columns; cca.py:174-175 only fixes U relative to V).  G1 / G2 are gradients w.r.t. the DEVICE's outputs, so the
+    # oracle gets them in its own convention: column j times sign(<V_device[:, j], V_oracle[:, j]>).
+    from audio_sheet_retrieval_b200.utils.cca import cca_sums_device, cca_solve_device
+    import torch
+    _, _, _, V_dev, _ = cca_solve_device(cca_sums_device(torch.as_tensor(H1).cuda(), torch.as_tensor(H2).cuda()), m, mode=1)
+    sgn = np.sign((V_dev.cpu().numpy() * occa.cca_layer_train_forward(H1, H2)["V"]).sum(0))
+    assert (sgn != 0).all()
+    r1, r2 = occa.cca_layer_train_backward(H1, H2, G1 * sgn, G2 * sgn, g_corr=gc)
+    d1, d2 = cca_layer_backward_device(H1, H2, G1, G2, g_corr=gc)
+    d1, d2 = d1.cpu().numpy(), d2.cpu().numpy()
+    for got, ref in ((d1, r1), (d2, r2)):
+        assert np.isfinite(got).all()
+        assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()      # fp32 outputs of an fp64 chain
+
+
+def test_loss_and_layer_backward_chain():
+    """contrastive loss gradient -> CCALayer backward: the gradient of the training objective w.r.t. the encoder latents,
+    against central differences of (oracle forward -> oracle loss) on a few coordinates."""
+    from audio_sheet_retrieval_b200.models.objectives import get_contrastive_cos_loss
+    from audio_sheet_retrieval_b200.utils.cca import cca_layer_backward_device
+    from oracle import objectives as oobj
+    m = 100
+    H1, H2 = occa.synth_latents(m, seed=11)
+    H1, H2 = H1.astype(np.float64), H2.astype(np.float64)
+
+    import torch
+
+    def total(a, b):
+        o = occa.cca_layer_train_forward(a, b)["out"]
+        return oobj.contrastive_cos_loss_ref(o[:, :32], o[:, 32:], 1.0, 0.7, True)
+
+    # forward on the device (its sign convention per output column is the one its backward differentiates)
+    from audio_sheet_retrieval_b200.utils.cca import cca_sums_device, cca_solve_device
+    m1, m2, U, V, _ = cca_solve_device(cca_sums_device(torch.as_tensor(H1.astype(np.float32)).cuda(),
+                                                       torch.as_tensor(H2.astype(np.float32)).cuda()), m, mode=1)
+    out = np.hstack(((H1 - m1.cpu().numpy()).dot(U.cpu().numpy()), (H2 - m2.cpu().numpy()).dot(V.cpu().numpy())))
+    loss_fn = get_contrastive_cos_loss(1.0, 0.7, symmetric=True)
+    val, g1, g2 = loss_fn.with_grads(torch.as_tensor(out[:, :32].astype(np.float32)).cuda(),
+                                     torch.as_tensor(out[:, 32:].astype(np.float32)).cuda())
+    assert abs(float(val) - total(H1, H2)) <= 1e-5 * abs(total(H1, H2))
+    d1, d2 = cca_layer_backward_device(H1.astype(np.float32), H2.astype(np.float32), g1, g2)
+    d1, d2 = d1.cpu().numpy(), d2.cpu().numpy()
+    rng = np.random.RandomState(2)
+    eps = 1e-5
+    scale = max(np.abs(d1).max(), np.abs(d2).max())
+    for _ in range(6):
+        i, j, which = rng.randint(m), rng.randint(32), rng.randint(2)
+        Hp, Hm = [H1.copy(), H2.copy()], [H1.copy(), H2.copy()]
+        Hp[which][i, j] += eps
+        Hm[which][i, j] -= eps
+        fd = (total(*Hp) - total(*Hm)) / (2 * eps)
+        an = (d1 if which == 0 else d2)[i, j]
+        assert abs(fd - an) <= 2e-3 * scale, (which, i, j, fd, an)

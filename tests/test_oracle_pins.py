@@ -78,3 +78,29 @@ def test_stored_bn_statistics_match_real_sheet_windows(shipped_params):
     swapped = [dict(L, mean=L["gamma"], gamma=L["mean"]) for L in views[0]]
     bad, _ = _layer_stats([swapped], cca, X, flip=False)
     assert max(b[1] for b in bad[:4]) > 1.0, bad[:4]
+
+
+def test_cca_layer_backward_matches_central_differences():
+    """The oracle's CCALayer training backward (the chain Theano's autodiff produces for layers/cca.py:91-203, written out)
+    against central differences of the oracle's forward: a weighted sum of both outputs plus a term in corr."""
+    from oracle import cca as occa
+    rng = np.random.RandomState(0)
+    m, d = 72, 32
+    H1, H2 = (a.astype(np.float64) for a in occa.synth_latents(m, seed=3))
+    W1, W2, gc = rng.normal(size=(m, d)), rng.normal(size=(m, d)), rng.normal(size=d)
+
+    def loss(a, b):
+        o = occa.cca_layer_train_forward(a, b)
+        return (o["out"][:, :d] * W1).sum() + (o["out"][:, d:] * W2).sum() + (o["corr"] * gc).sum()
+
+    g1, g2 = occa.cca_layer_train_backward(H1, H2, W1, W2, g_corr=gc)
+    assert abs(g1.sum(0)).max() < 1e-9 * abs(g1).max() and abs(g2.sum(0)).max() < 1e-9 * abs(g2).max()   # shift invariance
+    eps = 1e-6
+    for _ in range(10):
+        i, j, which = rng.randint(m), rng.randint(d), rng.randint(2)
+        Hp, Hm = [H1.copy(), H2.copy()], [H1.copy(), H2.copy()]
+        Hp[which][i, j] += eps
+        Hm[which][i, j] -= eps
+        fd = (loss(*Hp) - loss(*Hm)) / (2 * eps)
+        an = (g1 if which == 0 else g2)[i, j]
+        assert abs(fd - an) <= 2e-5 * max(1.0, abs(fd)), (which, i, j, fd, an)
