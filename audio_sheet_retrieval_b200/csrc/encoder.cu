@@ -2065,13 +2065,12 @@ int asr_extract_windows(const void *src_dev, int dtype, int src_h, int src_w, co
     return ASR_OK;
 }
 
-// The host-buffer entry of EVERY encoder handle on a device enqueues into one shared pair of streams (copies / kernels).
-// Two callers -- the two branches of a pair, called from two host threads -- then overlap one's copies with the other's
-// kernels, but their kernels never run concurrently: the conv kernels are persistent grids that own whole SMs (shared
-// memory, all 512 TMEM columns), and two of them sharing the GPU was measured bimodal (135 ms per 100 000 pairs in most
-// runs, 270-385 ms in one of four).  Each thread enqueues "copy k, then kernels k" in order and both streams are FIFO,
-// so every dependency (kernels wait for their copy, a copy waits for the kernels two chunks back) points backwards in
-// enqueue order: no deadlock.
+// Streams of the host-buffer entry.  Default: every handle owns a copy stream and a kernel stream, so the two branches of
+// a pair, called from two host threads, overlap not only one's copies with the other's kernels but also the tails of one's
+// persistent kernels with the start of the other's (measured: 771 k pairs/s end to end against 733 k with the shared
+// pair below).  ASR_HOST_SHARED_STREAMS=1 makes all handles of a device enqueue into ONE pair of streams instead (kernels
+// of different handles then never overlap; no deadlock: each thread enqueues "copy k, then kernels k" in order and both
+// streams are FIFO, so every dependency points backwards in enqueue order).
 static cudaStream_t g_host_copy[ASR_MAX_DEVICES] = {nullptr}, g_host_comp[ASR_MAX_DEVICES] = {nullptr};
 static std::mutex g_host_stream_mutex;
 static int host_streams(int dev, cudaStream_t *copy, cudaStream_t *comp) {
@@ -2098,7 +2097,7 @@ int asr_encoder_embed_host(asr_encoder_t *e, const void *x_host, int x_dtype, in
     const size_t sample_bytes = (size_t)e->d.in_h * e->d.in_w * esz;
     const size_t max_bytes = (size_t)e->d.in_h * e->d.in_w * 4 * e->max_batch;
     if (!e->s_copy) {
-        static const int own_streams = getenv("ASR_HOST_OWN_STREAMS") ? atoi(getenv("ASR_HOST_OWN_STREAMS")) : 0;   // A/B switch
+        static const int own_streams = getenv("ASR_HOST_SHARED_STREAMS") ? !atoi(getenv("ASR_HOST_SHARED_STREAMS")) : 1;
         if (own_streams) {
             ASR_CUDA(cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking));
             ASR_CUDA(cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking));

@@ -96,9 +96,9 @@ int asr_encoder_embed(asr_encoder_t *enc, const void *x_dev, int x_dtype, int64_
 /* Host buffers in, host buffers out (what RetrievalWrapper.compute_view_k does,
  * asr/retrieval_wrapper.py:47-77): chunks of max_batch, copy/compute overlap; pinned inputs / outputs are used where
  * they lie, pageable ones go through pinned staging slots.  Everything it needs (two input slots and two result slots of
- * max_batch rows, events) is allocated by the FIRST call of a handle and never again, whatever n.  All handles of a device
- * share one copy stream and one kernel stream: concurrent calls from several host threads (the two branches of a pair)
- * overlap one's copies with the other's kernels.  Blocks (on a blocking-sync event, not a spin) until the results are in
+ * max_batch rows, two streams, events) is allocated by the FIRST call of a handle and never again, whatever n.  Concurrent
+ * calls on DIFFERENT handles from several host threads (the two branches of a pair) overlap each other's copies and kernels.
+ * Blocks (on a blocking-sync event, not a spin) until the results are in
  * codes_host / latents_host. */
 int asr_encoder_embed_host(asr_encoder_t *enc, const void *x_host, int x_dtype, int64_t n,
                            float *codes_host, float *latents_host, int path);
