@@ -1135,6 +1135,7 @@ __global__ void __launch_bounds__(L0T_THREADS, 1) l0_tc_kernel(const L0TcParams 
 }
 
 #include "encoder_fused.cuh"
+#include "encoder_fused23.cuh"
 
 // --------------------------------------------------------------------------------------
 // head: spatial mean -> 1x1 conv + BN (folded) -> latent -> (latent - mean) . P -> unit norm
@@ -1304,9 +1305,14 @@ struct asr_encoder {
     // layers 0 + 1 fused (l01_fused_kernel): Toeplitz blobs with 8 output rows per tile, launch constants
     uint8_t *f01_blob = nullptr, *f01_blob_u8 = nullptr;
     bool f01_ok = false;
-    int fuse_mask = 0;              // bit 0: layers 0 + 1 run fused (asr_encoder_set_fusion)
+    int fuse_mask = 0;              // bit 0: layers 0 + 1 run fused, bit 1: layers 2 + 3 (asr_encoder_set_fusion)
     F01Params f01;                  // geometry / shared-memory layout, filled at create
     int f01_smem = 0, f01_smem_int = 0;
+    // layers 2 + 3 fused (l23_fused_kernel): layer 2's weights in the row-stacked blob format, launch constants
+    uint8_t *f23_blobA = nullptr;
+    bool f23_ok = false;
+    F23Params f23;
+    int f23_smem = 0;
     bf16 *wblob[8] = {nullptr};     // layers 1..7
     ConvPlan plan[8];
     bf16 *act[8] = {nullptr};       // P8 activations (output of layer l)
@@ -1486,7 +1492,7 @@ extern "C" {
 
 int asr_encoder_destroy(asr_encoder_t *e) {
     if (!e) return ASR_OK;
-    cudaFree(e->l0_w); cudaFree(e->l0_blob); cudaFree(e->l0_blob_u8); cudaFree(e->f01_blob); cudaFree(e->f01_blob_u8);
+    cudaFree(e->l0_w); cudaFree(e->l0_blob); cudaFree(e->l0_blob_u8); cudaFree(e->f01_blob); cudaFree(e->f01_blob_u8); cudaFree(e->f23_blobA);
     for (int l = 0; l < 8; ++l) {
         cudaFree(e->wblob[l]); cudaFree(e->act[l]); cudaFree(e->ref_w[l]); cudaFree(e->ref_bn[l]); cudaFree(e->ref_act[l]);
     }
@@ -1668,26 +1674,40 @@ int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *d, int max_b
                         pl.staging_bytes);
             }
             const int KC = g.cinp / 8, NP = g.coutp;
-            const size_t wbytes = (size_t)e->plan[l].wbytes;
-            std::vector<uint8_t> blob(wbytes + NP * 4, 0);
-            bf16 *wb = reinterpret_cast<bf16 *>(blob.data());
-            for (int t = 0; t < 9; ++t)
-                for (int ci = 0; ci < g.cin; ++ci)
-                    for (int co = 0; co < g.cout; ++co) {
-                        float v = wr[((size_t)co * g.cin + ci) * 9 + t] * scale[co];
-                        size_t idx;
-                        if (e->plan[l].rows) {      // [dx][K chunk][block: dy = 2, 1, 0, zeros][NP][8]
-                            const int dy = t / 3, dx = t % 3;
-                            idx = ((((size_t)dx * KC + ci / 8) * RS_R + (2 - dy)) * NP + co) * 8 + (ci & 7);
-                        } else {                    // [tap][K chunk][NP][8]
-                            idx = (((size_t)t * KC + ci / 8) * NP + co) * 8 + (ci & 7);
+            auto pack_blob = [&](bool rows_format) {
+                const size_t wbytes = rows_format ? (size_t)3 * KC * RS_R * NP * 16 : (size_t)9 * KC * NP * 16;
+                std::vector<uint8_t> blob(wbytes + NP * 4, 0);
+                bf16 *wb = reinterpret_cast<bf16 *>(blob.data());
+                for (int t = 0; t < 9; ++t)
+                    for (int ci = 0; ci < g.cin; ++ci)
+                        for (int co = 0; co < g.cout; ++co) {
+                            float v = wr[((size_t)co * g.cin + ci) * 9 + t] * scale[co];
+                            size_t idx;
+                            if (rows_format) {          // [dx][K chunk][block: dy = 2, 1, 0, zeros][NP][8]
+                                const int dy = t / 3, dx = t % 3;
+                                idx = ((((size_t)dx * KC + ci / 8) * RS_R + (2 - dy)) * NP + co) * 8 + (ci & 7);
+                            } else {                    // [tap][K chunk][NP][8]
+                                idx = (((size_t)t * KC + ci / 8) * NP + co) * 8 + (ci & 7);
+                            }
+                            wb[idx] = __float2bfloat16_rn(v);
                         }
-                        wb[idx] = __float2bfloat16_rn(v);
-                    }
-            float *bb = reinterpret_cast<float *>(blob.data() + wbytes);
-            for (int co = 0; co < g.cout; ++co) bb[co] = bias[co];
+                float *bb = reinterpret_cast<float *>(blob.data() + wbytes);
+                for (int co = 0; co < g.cout; ++co) bb[co] = bias[co];
+                return blob;
+            };
+            const std::vector<uint8_t> blob = pack_blob(e->plan[l].rows != 0);
+            if (blob.size() != (size_t)e->plan[l].wbytes + NP * 4) {
+                set_error("asr_encoder_create: weight blob size does not match the launch plan");
+                asr_encoder_destroy(e);
+                return ASR_ERR_UNSUPPORTED;
+            }
             E_CUDA(cudaMalloc(&e->wblob[l], blob.size()));
             E_CUDA(cudaMemcpy(e->wblob[l], blob.data(), blob.size(), cudaMemcpyHostToDevice));
+            if (l == 2 && !g.pool && !e->plan[l].rows) {      // layer A of the fused layer-2 + layer-3 kernel is row-stacked
+                const std::vector<uint8_t> rb = pack_blob(true);
+                E_CUDA(cudaMalloc(&e->f23_blobA, rb.size()));
+                E_CUDA(cudaMemcpy(e->f23_blobA, rb.data(), rb.size(), cudaMemcpyHostToDevice));
+            }
         }
         // activations of both paths
         if (l == 0) {
@@ -1699,7 +1719,7 @@ int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *d, int max_b
         }
         e->act_plane[l] = (long long)(g.Ho + 2) * (g.Wo + 2) * 16;
         e->act_sample[l] = e->act_plane[l] * (g.coutp / 8);
-        if (l > 0) {      // layer 0's buffer: ensure_act0 (first unfused call; never when layers 0 + 1 run fused)
+        if (l != 0 && l != 2) {   // buffers of layers 0 and 2: ensure_act (first unfused call; never while they run fused)
             E_CUDA(cudaMalloc(&e->act[l], (size_t)e->act_sample[l] * B));
             E_CUDA(cudaMemset(e->act[l], 0, (size_t)e->act_sample[l] * B));
         }
@@ -1742,6 +1762,49 @@ int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *d, int max_b
             fprintf(stderr, "[asr] layers 0+1 fused: %s (NB %d NG %d T0 %d JT %d smem %d / %d B)\n", ok ? "available" : "no", f.NB,
                     f.NG, f.T0, f.JT, e->f01_smem, e->f01_smem_int);
     }
+    {   // layers 2 + 3 fused: eligibility, geometry and shared-memory layout of l23_fused_kernel
+        const LayerGeom &ga = e->g[2], &gb = e->g[3];
+        const ConvPlan &pb = e->plan[3];
+        F23Params &f = e->f23;
+        memset(&f, 0, sizeof(f));
+        const int Wp = ga.W + 2;
+        bool ok = e->f23_blobA && !ga.pool && gb.pool && ga.W == gb.W && ga.H == gb.H && ga.W >= 90 && ga.W <= 128 &&
+                  !(ga.W & 1) && ga.H % G_TH == 0 && ga.cinp == 16 && ga.coutp == 32 && gb.cinp == 32 && gb.coutp == 32 &&
+                  pb.rows && pb.SPT == 1 && pb.JT == 1 && pb.Hc == ga.H;
+        if (ok) {
+            f.H = ga.H; f.W = ga.W; f.Wp = Wp; f.NG = ga.H / RS_R; f.bands = ga.H / G_TH;
+            f.KCLA = (ga.cin + 7) / 8; f.NPA = ga.coutp; f.NPB = gb.coutp; f.coutA = ga.cout; f.coutB = gb.cout;
+            f.Ho = gb.Ho; f.Wo = gb.Wo; f.Wpo = gb.Wo + 2;
+            f.in_plane = e->act_plane[1]; f.in_sample = e->act_sample[1];
+            f.out_plane = e->act_plane[3]; f.out_sample = e->act_sample[3];
+            const int KCA = ga.cinp / 8, KCB = gb.cinp / 8;
+            f.wbytesA = 3 * KCA * RS_R * f.NPA * 16; f.wbytesB = 3 * KCB * RS_R * f.NPB * 16;
+            f.sps = (G_TH + 2) * Wp * 16;
+            f.stage_bytes = ((16 + KCA * f.sps + TAIL_SLACK) + 127) / 128 * 128;
+            f.ring_plane = (G_ZROW + 1) * Wp * 16;
+            int off = f.wbytesA + f.NPA * 4; off = (off + 127) / 128 * 128;
+            f.off_wB = off; off += f.wbytesB + f.NPB * 4; off = (off + 127) / 128 * 128;
+            f.off_stage = off;
+            // K pairing (G_PAIR): the all-padding last chunk of layer B's input is never read, so it gets no ring plane
+            f.ring_planes = (G_PAIR && gb.cin <= 8 * (KCB - 1)) ? KCB - 1 : KCB;
+            static const int st_env = getenv("ASR_F23_STAGES") ? atoi(getenv("ASR_F23_STAGES")) : 3;
+            const int ring_bytes = f.ring_planes * f.ring_plane + G_TAIL;
+            f.n_stages = (st_env >= 3 && off + 3 * f.stage_bytes + ring_bytes + 128 + 256 <= SMEM_LIMIT) ? 3 : 2;
+            off += f.n_stages * f.stage_bytes;
+            f.off_ring = off; off += ring_bytes; off = (off + 127) / 128 * 128;
+            f.off_bar = off; off += 256;
+            e->f23_smem = off;
+            ok = off <= SMEM_LIMIT && f.wbytesB == pb.wbytes && (128 + 3 - Wp) * 16 <= G_TAIL && f.ring_plane / 16 < 16384 &&
+                 (!G_PAIR || f.ring_planes == KCB - 1) &&
+                 (long long)((G_TH + 1) * Wp + 128 + 2) * 16 <= (long long)f.sps + TAIL_SLACK;
+        }
+        e->f23_ok = ok;
+        static const int fuse_env = getenv("ASR_FUSE23") ? atoi(getenv("ASR_FUSE23")) : 1;
+        if (ok && fuse_env) e->fuse_mask |= 2;
+        if (getenv("ASR_DEBUG_PLAN"))
+            fprintf(stderr, "[asr] layers 2+3 fused: %s (NG %d bands %d stages %d smem %d B)\n", ok ? "available" : "no", f.NG, f.bands,
+                    f.n_stages, e->f23_smem);
+    }
     {   // head: A[j][c] = W8[j][c] * scale8[j]; b[j] = beta8 - mean8*scale8
         const int C = e->head_c;
         std::vector<float> A((size_t)32 * C + 32);
@@ -1765,6 +1828,7 @@ int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *d, int max_b
         E_CUDA(cudaFuncSetAttribute(conv3x3_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         E_CUDA(cudaFuncSetAttribute(l01_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         E_CUDA(cudaFuncSetAttribute(l01_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        E_CUDA((cudaFuncSetAttribute(l23_fused_kernel<1, 2, 32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)));
         E_CUDA(cudaFuncSetAttribute(conv3x3_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         E_CUDA(cudaFuncSetAttribute(conv3x3_rows_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         E_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
@@ -1782,10 +1846,10 @@ int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *d, int max_b
 
 double asr_encoder_flops_per_sample(const asr_encoder_t *e) { return e ? e->flops : 0.0; }
 
-static int ensure_act0(asr_encoder *e) {
-    if (e->act[0]) return ASR_OK;
-    ASR_CUDA(cudaMalloc(&e->act[0], (size_t)e->act_sample[0] * e->max_batch));
-    ASR_CUDA(cudaMemset(e->act[0], 0, (size_t)e->act_sample[0] * e->max_batch));
+static int ensure_act(asr_encoder *e, int l) {
+    if (e->act[l]) return ASR_OK;
+    ASR_CUDA(cudaMalloc(&e->act[l], (size_t)e->act_sample[l] * e->max_batch));
+    ASR_CUDA(cudaMemset(e->act[l], 0, (size_t)e->act_sample[l] * e->max_batch));
     return ASR_OK;
 }
 
@@ -1920,12 +1984,25 @@ int asr_encoder_embed(asr_encoder_t *e, const void *x_dev, int x_dtype, int64_t 
             ASR_LAUNCH_CHECK();
             return ASR_OK;
         };
+        auto launch_fused23 = [&]() -> int {
+            F23Params f = e->f23;
+            f.in = e->act[1]; f.out = e->act[3]; f.n = (int)n;
+            f.wblobA = e->f23_blobA; f.wblobB = reinterpret_cast<const uint8_t *>(e->wblob[3]);
+            static const int f23_dbg = getenv("ASR_F23_DEBUG") ? atoi(getenv("ASR_F23_DEBUG")) : 0;
+            f.dbg = f23_dbg;
+            const int grid = (int)std::min<int64_t>(n, sm_count());
+            l23_fused_kernel<1, 2, 32, 32><<<grid, G_THREADS, e->f23_smem, st>>>(f);
+            ASR_LAUNCH_CHECK();
+            return ASR_OK;
+        };
         const bool fused01 = (e->fuse_mask & 1) != 0;
+        const bool fused23 = (e->fuse_mask & 2) != 0;
+        if (!fused23 && (rc = ensure_act(e, 2))) return rc;
         if (fused01) {
             mark(e, st, 1, true);
             if ((rc = launch_fused01())) return rc;
             mark(e, st, 1, false);
-        } else if ((rc = ensure_act0(e))) {
+        } else if ((rc = ensure_act(e, 0))) {
             return rc;
         }
         // Layers 0 and 1 can run over sub-chunks that reuse one region of the layer-0 buffer (see create).
@@ -1942,8 +2019,14 @@ int asr_encoder_embed(asr_encoder_t *e, const void *x_dev, int x_dtype, int64_t 
             mark(e, st, 1, false);
         }
         mark(e, st, 1, true);
-        for (int l = 2; l < 8; ++l)
+        for (int l = 2; l < 8; ++l) {
+            if (l == 2 && fused23) {
+                if ((rc = launch_fused23())) return rc;
+                ++l;
+                continue;
+            }
             if ((rc = launch_conv(l, e->act[l - 1], e->act[l], n))) return rc;
+        }
         mark(e, st, 1, false);
         mark(e, st, 2, true);
         hp.in = e->act[7]; hp.is_p8 = 1; hp.plane = e->act_plane[7]; hp.sample = e->act_sample[7];
@@ -1987,7 +2070,7 @@ int asr_encoder_set_timing(asr_encoder_t *e, int enable) {
 
 int asr_encoder_set_fusion(asr_encoder_t *e, int mask) {
     ASR_CHECK_ARG(e != nullptr, "NULL handle");
-    e->fuse_mask = (mask & 1) && e->f01_ok ? 1 : 0;
+    e->fuse_mask = ((mask & 1) && e->f01_ok ? 1 : 0) | ((mask & 2) && e->f23_ok ? 2 : 0);
     return ASR_OK;
 }
 
@@ -2018,6 +2101,8 @@ int asr_encoder_debug_activation(asr_encoder_t *e, int layer, int path, int64_t 
                   "layer-0 activations are only kept for the last sub-chunk");
     ASR_CHECK_ARG(!(layer == 0 && path == ASR_PATH_TCGEN05 && out_host && (e->fuse_mask & 1)),
                   "layer-0 activations never reach memory while layers 0 + 1 run fused (asr_encoder_set_fusion(enc, 0))");
+    ASR_CHECK_ARG(!(layer == 2 && path == ASR_PATH_TCGEN05 && out_host && ((e->fuse_mask & 2) || !e->act[2])),
+                  "layer-2 activations never reach memory while layers 2 + 3 run fused (asr_encoder_set_fusion(enc, 0))");
     const LayerGeom &g = e->g[layer];
     if (c) *c = g.cout;
     if (h) *h = g.Ho;

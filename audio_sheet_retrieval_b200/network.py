@@ -147,7 +147,7 @@ class Encoder(object):
         return codes, latents
 
     def set_fusion(self, mask):
-        """Bit 0: layers 0 + 1 as one kernel (asr_encoder_set_fusion).  Returns the mask in effect."""
+        """Bit 0: layers 0 + 1 as one kernel, bit 1: layers 2 + 3 (asr_encoder_set_fusion).  Returns the mask in effect."""
         _lib.check(_lib.lib.asr_encoder_set_fusion(self.handle, int(mask)))
         return self.fusion
 

@@ -644,18 +644,21 @@ def main():
     head_flops = 2.0 * 48 * 32 * (10 * 12 + 5 * 2)
     conv_flops_pair = flops_pair - head_flops - (0 if f1 else l0_flops[1]) - (0 if f2 else l0_flops[2])
     conv_ms = t1["ms_conv_tc"] + t2["ms_conv_tc"]
-    conv_launches = (7 * t1["calls"]) + (7 * t2["calls"])
+    # tcgen05 launches per call: layers 1..7 (the fused layer-0 + layer-1 kernel counts as layer 1), one fewer where
+    # layers 2 + 3 run as one kernel
+    conv_launches = ((7 - ((e1.fusion >> 1) & 1)) * t1["calls"]) + ((7 - ((e2.fusion >> 1) & 1)) * t2["calls"])
     achieved = conv_flops_pair * n * roof_steps / (conv_ms * 1e-3) / 1e12
     traffic, traffic_src = read_traffic(mb)
     roofline = {"bound": "tensor",
-                "kernel": "l01_fused_kernel (prepare + layer 0 + layer 1, sheet branch) + conv3x3_rows_kernel + conv3x3_tc_kernel "
-                          "(tcgen05 implicit GEMM, layers 1-7 of both branches)",
+                "kernel": "l01_fused_kernel (prepare + layer 0 + layer 1, sheet branch) + l23_fused_kernel (layers 2 + 3, sheet "
+                          "branch) + conv3x3_rows_kernel + conv3x3_tc_kernel (tcgen05 implicit GEMM, layers 1-7 of both branches)",
                 "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
                 "peak_source": pk["src"] + ", sustained figure (kernel timed inside a long step)",
                 "traffic": traffic, "traffic_source": traffic_src,
                 "avg_launch_ms": conv_ms / max(conv_launches, 1), "launches": conv_launches,
                 "algorithmic_flops_per_pair": conv_flops_pair,
                 "fused_layer01": {"sheet_branch": bool(f1), "spectrogram_branch": bool(f2)},
+                "fused_layer23": {"sheet_branch": bool(e1.fusion & 2), "spectrogram_branch": bool(e2.fusion & 2)},
                 "timed_in": "a second pass of %d step(s) on one stream right after the timed region (%.2f ms per step there; the "
                             "timed region runs the branches on two streams: %.2f ms per step)" % (roof_steps, ms_roof_step, ms_step),
                 "share_of_step": conv_ms / (ms_roof_step * roof_steps),

@@ -121,7 +121,10 @@ int asr_encoder_get_timing(asr_encoder_t *enc, double *ms_layer0, double *ms_con
 /* Kernel fusion switches (bit mask).  Bit 0: layers 0 + 1 run as ONE kernel whose layer-0 output stays in shared
  * memory (default on where the geometry qualifies: 12 first-layer channels, width >= 126, no box filter -- the
  * sheet branch of asr/models/mutopia_ccal_cont.py:75-79).  Switching it off restores one launch per layer (and
- * makes layer 0 visible to asr_encoder_debug_activation).  get_fusion returns the mask in effect. */
+ * makes layer 0 visible to asr_encoder_debug_activation).  Bit 1: layers 2 + 3 run as ONE kernel whose layer-2
+ * output only exists as a ring of image rows in shared memory (default on where the geometry qualifies: 12 -> 24
+ * -> 24 channels, width 90..128, height a multiple of 8 -- the sheet branch of the same model, :80-84).
+ * get_fusion returns the mask in effect. */
 int asr_encoder_set_fusion(asr_encoder_t *enc, int mask);
 int asr_encoder_get_fusion(const asr_encoder_t *enc);
 /* algorithmic FLOPs per sample of this branch (2*MACs of the nine convolutions) */

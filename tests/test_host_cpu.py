@@ -36,7 +36,7 @@ def test_library_is_sm100a_with_tcgen05_and_tma():
     assert "LDTM" in sass, "no tcgen05.ld in SASS"
     assert "UBLKCP" in sass and "UTMALDG" in sass, "no TMA bulk / tensor loads in SASS"
     # every hot kernel of the path is in the binary
-    for kernel in ("l0_tc_kernel", "l01_fused_kernel", "conv3x3_rows_kernel", "conv3x3_tc_kernel", "head_kernel", "topk_stream_kernel",
+    for kernel in ("l0_tc_kernel", "l01_fused_kernel", "l23_fused_kernel", "conv3x3_rows_kernel", "conv3x3_tc_kernel", "head_kernel", "topk_stream_kernel",
                    "topk_tc_kernel", "topk_merge_select_kernel", "cca_solve_kernel", "contrastive_rows_kernel"):
         assert kernel in sass, kernel
 
