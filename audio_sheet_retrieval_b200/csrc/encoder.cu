@@ -82,6 +82,7 @@ struct ConvParams {
     int KCL;             // input chunks that hold real channels: the others are never loaded (zeroed in smem once)
     int NCHR;            // output chunks that hold real channels: the others are never stored (buffers are pre-zeroed)
     int dbg;             // diagnostics only (env ASR_CONV_DEBUG): 1 = epilogue releases slots without draining, 2 = no MMAs
+    int pair;            // raster kernel: K pairing of a half-used last chunk (KCL == KC - 1), see the MMA issuers
 };
 
 constexpr int N_MMA_WARPS = 4;           // tile tc is issued by MMA warp (tc & 3) and drained by epilogue group (tc & 3)
@@ -183,6 +184,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(const ConvP
         const uint32_t slot_mask = (uint32_t)p.n_slots - 1u;                   // n_slots is a power of two
         const uint32_t slot_shift = (uint32_t)__ffs(p.n_slots) - 1u;
         const uint32_t wp = (uint32_t)p.Wp;
+        const uint32_t tap_stride = (uint32_t)(p.KC * p.NP);                   // 16-byte units between the taps of the blob
+        const bool pair = KPAIRS >= 2 && p.pair != 0;
         mbar_wait(w_full, 0);
         int it = 0;
         uint32_t tc0 = 0;      // running tile counter (same sequence in the MMA and the epilogue warps)
@@ -204,7 +207,33 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(const ConvP
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + slot * (uint32_t)p.slot_cols;
                 uint32_t b_lo = w_lo;
-                if (!no_mma) {
+                if (!no_mma && pair) {
+                    // K pairing: the last chunk with real channels is only half of a K = 16 step (24 -> 32 channels).
+                    // Pair it with ITSELF one position further (A: LBO = 16 B) and the weights of tap (dy, 0) with
+                    // those of (dy, 1) (B: LBO = the tap stride of the blob); tap (dy, 2) pairs with the all-zero
+                    // padding chunk of the blob.  5 instead of 6 MMAs per dy; the padding plane is never read.
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy) {
+                        const uint32_t row_lo = tile_lo + (uint32_t)dy * wp;
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            uint32_t a_lo = row_lo + (uint32_t)dx;
+                            uint32_t bb = b_lo + (uint32_t)dx * tap_stride;
+#pragma unroll
+                            for (int kp = 0; kp < KPAIRS - 1; ++kp) {
+                                tc_mma_bf16_elect(d_tmem, a_lo, bb, UMMA_DESC_HI, idesc, (dy | dx | kp) != 0 ? 1u : 0u);
+                                a_lo += kstep_a;
+                                bb += kstep_b;
+                            }
+                        }
+                        // descriptors of the last real chunk: A with LBO = 1 position, B with LBO = tap stride
+                        const uint32_t a2 = ((row_lo + (uint32_t)(KPAIRS - 1) * kstep_a) & 0xFFFFu) | (1u << 16);
+                        const uint32_t b2 = (b_lo + (uint32_t)(KPAIRS - 1) * kstep_b) & 0xFFFFu;
+                        tc_mma_bf16_elect(d_tmem, a2, b2 | (tap_stride << 16), UMMA_DESC_HI, idesc, 1u);
+                        tc_mma_bf16_elect(d_tmem, a2 + 2u, (b2 + 2u * tap_stride) | ((uint32_t)p.NP << 16), UMMA_DESC_HI, idesc, 1u);
+                        b_lo += 3u * tap_stride;
+                    }
+                } else if (!no_mma) {
 #pragma unroll
                     for (int t = 0; t < 9; ++t) {
                         uint32_t a_lo = tile_lo + (uint32_t)(t / 3) * wp + (uint32_t)(t % 3);
@@ -1938,6 +1967,10 @@ int asr_encoder_embed(asr_encoder_t *e, const void *x_dev, int x_dtype, int64_t 
             p.sp_magic = pl.rows && pl.SPT > 1 ? (unsigned)((0x100000000ull + (unsigned)pl.SP - 1) / (unsigned)pl.SP) : 0u;
             static const int conv_dbg = getenv("ASR_CONV_DEBUG") ? atoi(getenv("ASR_CONV_DEBUG")) : 0;
             p.dbg = conv_dbg;
+            static const int pair_env = getenv("ASR_CONV_PAIR") ? atoi(getenv("ASR_CONV_PAIR")) : 1;
+            // descriptor low words carry the 14-bit start address in bits 0-13: the masks in the kernel keep 16 bits,
+            // which is exact because shared-memory addresses stay below 2^18 bytes
+            p.pair = (pair_env && !pl.rows && p.KC >= 4 && p.KCL == p.KC - 1) ? 1 : 0;
             const int items = (int)nn * pl.bands;
             const int grid = std::min(items, sm_count());
             if (pl.rows) {
