@@ -329,6 +329,18 @@ __device__ __forceinline__ void tmem_ld12(uint32_t taddr, float *v) {
     for (int i = 0; i < 12; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// the same without the wait (valid after tmem_ld_wait())
+__device__ __forceinline__ void tmem_ld12_issue(uint32_t taddr, uint32_t *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11])
+                 : "r"(taddr + 8u)
+                 : "memory");
+}
+
 // shared-memory progress counters (producer: red.release after its stores; consumer: ld.acquire poll)
 __device__ __forceinline__ uint32_t ld_acquire_shared(const uint32_t *p) {
     uint32_t v;

@@ -1857,6 +1857,7 @@ int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *d, int max_b
         E_CUDA(cudaFuncSetAttribute(conv3x3_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         E_CUDA(cudaFuncSetAttribute(l01_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         E_CUDA(cudaFuncSetAttribute(l01_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        E_CUDA((cudaFuncSetAttribute(l01_fused_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)));
         E_CUDA((cudaFuncSetAttribute(l23_fused_kernel<1, 2, 32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)));
         E_CUDA(cudaFuncSetAttribute(conv3x3_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         E_CUDA(cudaFuncSetAttribute(conv3x3_rows_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
@@ -2013,6 +2014,7 @@ int asr_encoder_embed(asr_encoder_t *e, const void *x_dev, int x_dtype, int64_t 
             const int grid = (int)std::min<int64_t>(n, sm_count());
             static const int variant = getenv("ASR_F01_VARIANT") ? atoi(getenv("ASR_F01_VARIANT")) : 0;
             if (variant == 1) l01_fused_kernel<1><<<grid, 32 * (F_DRAIN_WARP0 + 4 * (1 + F_EG)), smem, st>>>(f);
+            else if (variant == 2) l01_fused_kernel<4, 2><<<grid, 32 * (F_DRAIN_WARP0 + 4 * (4 + 2)), smem, st>>>(f);
             else l01_fused_kernel<2><<<grid, 32 * (F_DRAIN_WARP0 + 4 * (2 + F_EG)), smem, st>>>(f);
             ASR_LAUNCH_CHECK();
             return ASR_OK;

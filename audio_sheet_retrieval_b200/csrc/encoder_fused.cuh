@@ -205,10 +205,14 @@ __device__ __forceinline__ void f01_mma1(const F01Params &p, uint8_t *smem, int 
 // exactly one producer and one consumer -- slot 2 w + (u & 1) belongs to MMA-1 warp w (u = its running tile count)
 // and is drained by epilogue group 2 w + (u & 1) -- so nobody can run two mbarrier phases ahead of a slot (with
 // shared slots a wait on "parity p" is satisfied by the phase before the previous one).
+// EG = 2: one epilogue group per MMA-1 warp, which then drains both of that warp's slots alternately (still one
+// consumer per slot, tiles in order); the freed warps go to the drain (DG = 4: two rows per warp, both TMEM loads of a
+// tile in one round trip -- the drain is a latency chain per warp).
 constexpr int F_EG = 4;
-template <int DG>
-__global__ void __launch_bounds__(32 * (F_DRAIN_WARP0 + 4 * (DG + F_EG)), 1) l01_fused_kernel(const F01Params p) {
-    constexpr int NTHREADS = 32 * (F_DRAIN_WARP0 + 4 * (DG + F_EG));
+template <int DG, int EG = F_EG>
+__global__ void __launch_bounds__(32 * (F_DRAIN_WARP0 + 4 * (DG + EG)), 1) l01_fused_kernel(const F01Params p) {
+    static_assert(EG == 4 || EG == 2, "two MMA-1 warps: four or two epilogue groups");
+    constexpr int NTHREADS = 32 * (F_DRAIN_WARP0 + 4 * (DG + EG));
     constexpr int EPI_WARP0_F = F_DRAIN_WARP0 + 4 * DG;
     extern __shared__ __align__(128) uint8_t smem[];
     // The warp index goes through a lane-0 broadcast so that the compiler KNOWS it is warp-uniform: the role branches
@@ -325,6 +329,28 @@ __global__ void __launch_bounds__(32 * (F_DRAIN_WARP0 + 4 * (DG + F_EG)), 1) l01
             const uint32_t taddr = tmem_base + (uint32_t)slot * F_SLOT0 + ((uint32_t)(q * 32) << 16);
             const bool col_real = xp >= 1 && xp <= p.W;
             uint8_t *dst = ring + ((size_t)(((B0 + rbl) % F_RB) * F_R0) * p.Wp + xp) * 16;
+            if (2 * DG == F_R0 && !(p.dbg & 4)) {
+                // two rows per warp (grp, grp + DG): both loads in flight, one wait
+                uint32_t raw[2][12];
+                tmem_ld12_issue(taddr + (uint32_t)(grp * F_C0), raw[0]);
+                tmem_ld12_issue(taddr + (uint32_t)((grp + DG) * F_C0), raw[1]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int r = grp + h2 * DG;
+                    uint32_t pk[6];
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) {
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(elu_f(__uint_as_float(raw[h2][2 * j])),
+                                                                       elu_f(__uint_as_float(raw[h2][2 * j + 1])));
+                        pk[j] = col_real ? *reinterpret_cast<const uint32_t *>(&h) : 0u;
+                    }
+                    if (rbl < p.NB && rbl * F_R0 + r < p.H) {
+                        *reinterpret_cast<uint4 *>(dst + (size_t)r * p.Wp * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4 *>(dst + (size_t)r * p.Wp * 16 + p.ring_plane) = make_uint4(pk[4], pk[5], 0u, 0u);
+                    }
+                }
+            } else {
 #pragma unroll 1
             for (int r = grp; r < ((p.dbg & 4) ? 0 : F_R0); r += DG) {
                 float v[12];
@@ -339,6 +365,7 @@ __global__ void __launch_bounds__(32 * (F_DRAIN_WARP0 + 4 * (DG + F_EG)), 1) l01
                     *reinterpret_cast<uint4 *>(dst + (size_t)r * p.Wp * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     *reinterpret_cast<uint4 *>(dst + (size_t)r * p.Wp * 16 + p.ring_plane) = make_uint4(pk[4], pk[5], 0u, 0u);
                 }
+            }
             }
             fence_proxy_async();
             tc_fence_before();
@@ -357,13 +384,13 @@ __global__ void __launch_bounds__(32 * (F_DRAIN_WARP0 + 4 * (DG + F_EG)), 1) l01
         // ================= epilogue: TMEM -> 2x2 max -> bias + ELU -> bf16 -> global =================
         const int q = warp & 3, grp = (warp - EPI_WARP0_F) >> 2;
         const int odd = lane & 1;
-        const int w = grp >> 1;                                   // the MMA-1 warp whose tiles this group drains
+        const int w = EG == 4 ? grp >> 1 : grp;                   // the MMA-1 warp whose tiles this group drains
         const int ngw = (p.NG - w + 1) / 2;                       // row groups per sample of that warp
         const int total1 = n_it * ngw * p.JT;                     // its tiles
         const int n_groups16 = (p.cout1 + 3) >> 2;
         const int nchr = (p.cout1 + 7) >> 3;
-        const uint32_t slot = (uint32_t)grp;
-        for (int u = grp & 1; u < total1; u += 2) {
+        for (int u = (EG == 4 ? grp & 1 : 0); u < total1; u += (EG == 4 ? 2 : 1)) {
+            const uint32_t slot = EG == 4 ? (uint32_t)grp : (uint32_t)(2 * w + (u & 1));
             const uint32_t sph = ((uint32_t)u >> 1) & 1u;
             const int G = u / p.JT, j = u - G * p.JT;
             const int it = G / ngw, rg = w + 2 * (G - it * ngw);

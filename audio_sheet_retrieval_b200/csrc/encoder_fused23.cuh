@@ -24,6 +24,10 @@ constexpr int G_TAIL = 2176;
 #ifndef ASR_F23_PAIR
 #define ASR_F23_PAIR 1
 #endif
+#ifndef ASR_F23_LANE0_WAIT
+#define ASR_F23_LANE0_WAIT 1
+#endif
+constexpr bool G_LANE0_WAIT = ASR_F23_LANE0_WAIT != 0;    // drain / epilogue warps wait on their mbarriers with one lane
 constexpr int G_PAIR = ASR_F23_PAIR;          // layer B: 5 instead of 6 MMAs per (input row, 3 taps) -- see f23_mma_b
 constexpr int G_DRAIN_WARP0 = 4, G_DRAIN_WARPS = 16, G_EPI_WARP0 = G_DRAIN_WARP0 + G_DRAIN_WARPS, G_EPI_WARPS = 8;
 constexpr int G_THREADS = 32 * (G_EPI_WARP0 + G_EPI_WARPS);
@@ -262,8 +266,16 @@ __global__ void __launch_bounds__(G_THREADS, 1) l23_fused_kernel(const F23Params
         for (int k = 0; k < total; ++k) {
             const uint32_t slot = (uint32_t)k & 1u;
             const int blk = k % G_RB;
-            mbar_wait_tag(&mid_free[blk], (uint32_t)(((k / G_RB) & 1) ^ 1), 6100000 + k);
-            mbar_wait_tag(&accA_full[slot], (uint32_t)((k >> 1) & 1), 6200000 + k);
+            if (G_LANE0_WAIT) {       // one polling lane per warp: 32 lanes on one mbarrier count as 32 shared-memory wavefronts
+                if (lane == 0) {
+                    mbar_wait_tag(&mid_free[blk], (uint32_t)(((k / G_RB) & 1) ^ 1), 6100000 + k);
+                    mbar_wait_tag(&accA_full[slot], (uint32_t)((k >> 1) & 1), 6200000 + k);
+                }
+                __syncwarp();
+            } else {
+                mbar_wait_tag(&mid_free[blk], (uint32_t)(((k / G_RB) & 1) ^ 1), 6100000 + k);
+                mbar_wait_tag(&accA_full[slot], (uint32_t)((k >> 1) & 1), 6200000 + k);
+            }
             tc_fence_after();
             const uint32_t taddr = slot * G_SLOT + ((uint32_t)(q * 32) << 16) + (uint32_t)(jr * NPA);
             if (!(p.dbg & 4)) {
@@ -322,7 +334,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) l23_fused_kernel(const F23Params
             const int it = u / p.NG, rg = u - it * p.NG;
             const uint32_t slot = (uint32_t)rg & 1u;                 // NG is even: parity of u = parity of rg
             const long long n = (long long)blockIdx.x + (long long)it * gridDim.x;
-            mbar_wait_tag(&accB_full[slot], (uint32_t)((u >> 1) & 1), 7100000 + u);
+            if (G_LANE0_WAIT) {
+                if (lane == 0) mbar_wait_tag(&accB_full[slot], (uint32_t)((u >> 1) & 1), 7100000 + u);
+                __syncwarp();
+            } else {
+                mbar_wait_tag(&accB_full[slot], (uint32_t)((u >> 1) & 1), 7100000 + u);
+            }
             tc_fence_after();
             uint8_t *out_n = reinterpret_cast<uint8_t *>(p.out) + n * p.out_sample;
             const uint32_t taddr = 2u * G_SLOT + slot * G_SLOT + ((uint32_t)(q * 32) << 16);

@@ -264,7 +264,7 @@ np.savez({dst!r}, **out)
 
 
 @pytest.mark.parametrize("env", [{}, {"ASR_CONV_ROWS": "0"}, {"ASR_L0_TC": "0"}, {"ASR_CONV_ROWS_MULTI": "1"},
-                                 {"ASR_CONV_ROWS": "2"}, {"ASR_FUSE01": "0"}, {"ASR_F01_VARIANT": "1"}, {"ASR_FUSE23": "0"}])
+                                 {"ASR_CONV_ROWS": "2"}, {"ASR_FUSE01": "0"}, {"ASR_F01_VARIANT": "1"}, {"ASR_F01_VARIANT": "2"}, {"ASR_FUSE23": "0"}])
 def test_kernel_variants_agree(env, tmp_path):
     """The kernel-selection switches are read once per process, so each variant runs in its own interpreter:
     raster-only conv, CUDA-core layer 0, side-by-side narrow tiles and row-stacked non-pooled layers must all
