@@ -1550,6 +1550,8 @@ int asr_encoder_set_cca(asr_encoder_t *e, const float *cca_mean, const float *cc
     return ASR_OK;
 }
 
+static int ensure_act(asr_encoder *e, int l);
+
 int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *d, int max_batch) {
     ASR_CHECK_ARG(out && d, "NULL argument");
     int rc = ensure_device();
@@ -1870,6 +1872,14 @@ int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *d, int max_b
         attr_done[attr_dev] = true;
     }
 #undef E_CUDA
+    // Activation buffers of layers whose output stays on the SM in the default configuration are only allocated when a
+    // caller switches that fusion off (asr_encoder_set_fusion); everything the default path needs exists from here on,
+    // so asr_encoder_embed never allocates.
+    for (int l = 0; l <= 2; l += 2)
+        if (!(e->fuse_mask & (l == 0 ? 1 : 2)) && ensure_act(e, l) != ASR_OK) {
+            asr_encoder_destroy(e);
+            return ASR_ERR_CUDA;
+        }
     *out = e;
     return ASR_OK;
 }
