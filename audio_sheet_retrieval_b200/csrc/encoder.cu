@@ -334,43 +334,42 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(const ConvP
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");   // band staged
                 const int per_ch = (p.TH / 2) * p.Wo;
                 const int yo0 = y0 / 2;
-                for (int ch = 0; ch < p.NCHR; ++ch) {
+                // one pass over (chunk, pooled position): the small bands of the deep layers have far fewer pooled
+                // positions per chunk than epilogue threads, so a loop over the chunks would run them one after the other
+                for (int idx = etid; idx < p.NCHR * per_ch; idx += EPI_THREADS) {
+                    const int ch = idx / per_ch, e = idx - ch * per_ch;
                     const int nreal = min(8, p.cout - 8 * ch);       // real channels of this chunk (<= 0: padding only)
-                    float bch[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) bch[j] = bias_sm[ch * 8 + j];
                     const uint8_t *sch = staging_sm + (size_t)ch * p.TH * p.Wp * 16 + 16;
                     uint8_t *och = out_n + (long long)ch * p.out_plane + 16;
-                    for (int e = etid; e < per_ch; e += EPI_THREADS) {
-                        const int pr = p.wo_magic ? (int)__umulhi((unsigned)e, p.wo_magic) : e;
-                        const int pc = e - pr * p.Wo;
-                        if (yo0 + pr < p.Ho) {
-                            uint4 o4 = make_uint4(0u, 0u, 0u, 0u);
-                            if (nreal > 0) {
-                                const uint8_t *b = sch + ((size_t)(2 * pr) * p.Wp + 2 * pc) * 16;
-                                const uint4 q00 = *reinterpret_cast<const uint4 *>(b);
-                                const uint4 q01 = *reinterpret_cast<const uint4 *>(b + 16);
-                                const uint4 q10 = *reinterpret_cast<const uint4 *>(b + (size_t)p.Wp * 16);
-                                const uint4 q11 = *reinterpret_cast<const uint4 *>(b + (size_t)p.Wp * 16 + 16);
-                                const uint32_t *a0 = &q00.x, *a1 = &q01.x, *a2 = &q10.x, *a3 = &q11.x;
-                                uint32_t *oo = &o4.x;
+                    const int pr = p.wo_magic ? (int)__umulhi((unsigned)e, p.wo_magic) : e;
+                    const int pc = e - pr * p.Wo;
+                    if (yo0 + pr < p.Ho) {
+                        uint4 o4 = make_uint4(0u, 0u, 0u, 0u);
+                        if (nreal > 0) {
+                            const uint8_t *b = sch + ((size_t)(2 * pr) * p.Wp + 2 * pc) * 16;
+                            const uint4 q00 = *reinterpret_cast<const uint4 *>(b);
+                            const uint4 q01 = *reinterpret_cast<const uint4 *>(b + 16);
+                            const uint4 q10 = *reinterpret_cast<const uint4 *>(b + (size_t)p.Wp * 16);
+                            const uint4 q11 = *reinterpret_cast<const uint4 *>(b + (size_t)p.Wp * 16 + 16);
+                            const uint32_t *a0 = &q00.x, *a1 = &q01.x, *a2 = &q10.x, *a3 = &q11.x;
+                            uint32_t *oo = &o4.x;
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    if (2 * j < nreal) {          // warp-uniform; channel counts are multiples of 4... or 2
-                                        const __half2 m0 = __hmax2(*reinterpret_cast<const __half2 *>(&a0[j]),
-                                                                   *reinterpret_cast<const __half2 *>(&a1[j]));
-                                        const __half2 m1 = __hmax2(*reinterpret_cast<const __half2 *>(&a2[j]),
-                                                                   *reinterpret_cast<const __half2 *>(&a3[j]));
-                                        const float2 f = __half22float2(__hmax2(m0, m1));
-                                        const float r0 = elu_f(f.x + bch[2 * j]);
-                                        const float r1 = (2 * j + 1 < nreal) ? elu_f(f.y + bch[2 * j + 1]) : 0.f;
-                                        __nv_bfloat162 h = __floats2bfloat162_rn(r0, r1);
-                                        oo[j] = *reinterpret_cast<uint32_t *>(&h);
-                                    }
+                            for (int j = 0; j < 4; ++j) {
+                                if (2 * j < nreal) {          // channel counts are multiples of 4 ... or 2
+                                    const __half2 m0 = __hmax2(*reinterpret_cast<const __half2 *>(&a0[j]),
+                                                               *reinterpret_cast<const __half2 *>(&a1[j]));
+                                    const __half2 m1 = __hmax2(*reinterpret_cast<const __half2 *>(&a2[j]),
+                                                               *reinterpret_cast<const __half2 *>(&a3[j]));
+                                    const float2 f = __half22float2(__hmax2(m0, m1));
+                                    const float2 b2 = *reinterpret_cast<const float2 *>(&bias_sm[ch * 8 + 2 * j]);
+                                    const float r0 = elu_f(f.x + b2.x);
+                                    const float r1 = (2 * j + 1 < nreal) ? elu_f(f.y + b2.y) : 0.f;
+                                    __nv_bfloat162 h = __floats2bfloat162_rn(r0, r1);
+                                    oo[j] = *reinterpret_cast<uint32_t *>(&h);
                                 }
                             }
-                            *reinterpret_cast<uint4 *>(och + ((long long)(yo0 + pr + 1) * p.Wpo + pc) * 16) = o4;
                         }
+                        *reinterpret_cast<uint4 *>(och + ((long long)(yo0 + pr + 1) * p.Wpo + pc) * 16) = o4;
                     }
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");   // staging free again
