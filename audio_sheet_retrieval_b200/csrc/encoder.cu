@@ -1578,13 +1578,14 @@ int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *d, int max_b
         e->flops += 2.0 * 9.0 * cin * g.cout * H * W;
         H = g.Ho; W = g.Wo; cin = g.cout;
         if (H < 1 || W < 1) { delete e; set_error("input too small for four 2x2 pools"); return ASR_ERR_ARG; }
-        ASR_CHECK_ARG(g.coutp <= 128, "at most 128 channels per layer");
-        ASR_CHECK_ARG(l == 0 || g.cinp == 16 || g.cinp == 32 || g.cinp == 48 || g.cinp == 64 || g.cinp == 96 || g.cinp == 128,
-                      "input channels must pad to 16, 32, 48, 64, 96 or 128");
+        const char *bad = g.coutp > 128 ? "at most 128 channels per layer"
+                          : !(l == 0 || g.cinp == 16 || g.cinp == 32 || g.cinp == 48 || g.cinp == 64 || g.cinp == 96 || g.cinp == 128)
+                              ? "input channels must pad to 16, 32, 48, 64, 96 or 128" : nullptr;
+        if (bad) { delete e; set_error(std::string("asr_encoder_create: ") + bad); return ASR_ERR_ARG; }
     }
     e->head_c = cin; e->head_h = H; e->head_w = W;
     e->flops += 2.0 * cin * 32 * H * W;
-    ASR_CHECK_ARG(e->head_c <= 128, "head supports at most 128 input channels");
+    if (e->head_c > 128) { delete e; set_error("asr_encoder_create: head supports at most 128 input channels"); return ASR_ERR_ARG; }
 
     const size_t B = (size_t)max_batch;
 #define E_CUDA(expr)                                                                                   \
