@@ -242,6 +242,34 @@ def test_small_and_ragged_batches(n):
     assert (got1[:m] == full1[:m]).all() and (got2[:m] == full2[:m]).all()
 
 
+def test_fused_kernels_several_samples_per_cta():
+    """More samples than SMs, not a multiple of the grid: the persistent fused kernels (layers 0 + 1, layers 2 + 3) walk
+    several samples per CTA, so their ring / accumulator phases wrap many times; rows must equal the per-layer launches
+    to bf16 round-off, and a sample's result must not depend on its position in the batch."""
+    from audio_sheet_retrieval_b200 import _lib
+    n = 2 * torch.cuda.get_device_properties(0).multi_processor_count + 37
+    model, net = _net("mutopia_ccal_cont", max_batch=n)
+    rng = np.random.RandomState(5)
+    base = rng.randint(0, 256, size=(8, 1, 160, 200)).astype(np.uint8)
+    base[base > 60] = 255                                   # sheet-like: mostly white
+    X = base[rng.randint(0, 8, size=n)]                     # every sample is one of 8 images
+    enc = net.encoder(1, model.prepare.asr_prepare_mode)
+    if not (enc.fusion & 2):
+        pytest.skip("layers 2 + 3 do not run fused on this geometry")
+    fused = enc.embed_host(X, path=_lib.PATH_TCGEN05)
+    enc.set_fusion(enc.fusion & 1)
+    per_layer = enc.embed_host(X, path=_lib.PATH_TCGEN05)
+    assert _cos(fused, per_layer).min() > 0.9999
+    # identical inputs -> identical rows, wherever they sit in the batch
+    first = {}
+    for i in range(n):
+        key = X[i].tobytes()
+        if key in first:
+            assert (fused[i] == fused[first[key]]).all(), (i, first[key])
+        else:
+            first[key] = i
+
+
 _VARIANT_SNIPPET = r"""
 import sys, numpy as np
 sys.path.insert(0, {root!r})
