@@ -1801,7 +1801,8 @@ int asr_encoder_create(asr_encoder_t **out, const asr_encoder_desc *d, int max_b
         const int Wp = ga.W + 2;
         bool ok = e->f23_blobA && !ga.pool && gb.pool && ga.W == gb.W && ga.H == gb.H && ga.W >= 90 && ga.W <= 128 &&
                   !(ga.W & 1) && ga.H % G_TH == 0 && ga.cinp == 16 && ga.coutp == 32 && gb.cinp == 32 && gb.coutp == 32 &&
-                  pb.rows && pb.SPT == 1 && pb.JT == 1 && pb.Hc == ga.H;
+                  pb.rows && pb.SPT == 1 && pb.JT == 1 && pb.Hc == ga.H &&
+                  (ga.cin + 7) / 8 == ga.cinp / 8;     // every input plane of layer A is loaded (none left uninitialised)
         if (ok) {
             f.H = ga.H; f.W = ga.W; f.Wp = Wp; f.NG = ga.H / RS_R; f.bands = ga.H / G_TH;
             f.KCLA = (ga.cin + 7) / 8; f.NPA = ga.coutp; f.NPB = gb.coutp; f.coutA = ga.cout; f.coutB = gb.cout;
